@@ -1,0 +1,100 @@
+"""
+ctypes binding of libdeepbinner_b200.so (C ABI: include/deepbinner_b200.h), following the reference's
+own FFI convention (`dtw_semi_global.py:26-41`: a .so located relative to the module, loaded with
+ctypes, C-contiguous numpy arrays, caller-allocated outputs).
+
+Fails loudly (ImportError / RuntimeError) when the library is missing or no B200 is usable - the
+product path has no CPU fallback.
+"""
+
+import ctypes
+import os
+import pathlib
+
+import numpy as np
+
+_PKG = pathlib.Path(__file__).resolve().parent
+LIB_PATH = _PKG / 'libdeepbinner_b200.so'
+
+DBN_OK = 0
+SIDE_START, SIDE_END = 0, 1
+ENGINE_FP32, ENGINE_TCGEN05 = 0, 1
+ENGINE_NAMES = {ENGINE_FP32: 'fp32', ENGINE_TCGEN05: 'tcgen05'}
+ABI_VERSION = 1
+
+_lib = None
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+def load_library():
+    """Load (building first if absent and nvcc exists) the C-ABI library; raises if impossible."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not LIB_PATH.exists() or os.environ.get('DEEPBINNER_B200_REBUILD'):
+        from . import build
+        try:
+            build.build_library(force=True)
+        except Exception as e:  # noqa: BLE001
+            raise ImportError('libdeepbinner_b200.so is missing and could not be built: {}\n'
+                              'deepbinner_b200 has no CPU fallback.'.format(e))
+    lib = ctypes.CDLL(str(LIB_PATH))
+    c_void_pp = ctypes.POINTER(ctypes.c_void_p)
+    sigs = {
+        'db_abi_version': (ctypes.c_int, []),
+        'db_last_error': (ctypes.c_char_p, []),
+        'db_create': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, c_void_pp]),
+        'db_destroy': (None, [ctypes.c_void_p]),
+        'db_info': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int),
+                                   ctypes.POINTER(ctypes.c_int)]),
+        'db_set_engine': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int]),
+        'db_get_engine': (ctypes.c_int, [ctypes.c_void_p]),
+        'db_predict_windows': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                              ctypes.c_void_p]),
+        'db_predict_windows_f64': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64,
+                                                  ctypes.c_void_p]),
+        'db_predict_windows_device': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p,
+                                                     ctypes.c_int64, ctypes.c_void_p,
+                                                     ctypes.c_void_p]),
+        'db_call_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                         ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                         ctypes.c_void_p, ctypes.c_void_p]),
+        'db_call_batch_device': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                                ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_void_p, ctypes.c_void_p]),
+        'db_last_gpu_ms': (ctypes.c_float, [ctypes.c_void_p]),
+        'db_kernel_launches': (ctypes.c_int64, [ctypes.c_void_p]),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(lib, name)   # AttributeError if the symbol is missing: fail loudly
+        fn.restype = res
+        fn.argtypes = args
+    if lib.db_abi_version() != ABI_VERSION:
+        raise ImportError('libdeepbinner_b200.so ABI version mismatch')
+    _lib = lib
+    return lib
+
+
+EXPORTED_SYMBOLS = ['db_abi_version', 'db_last_error', 'db_create', 'db_destroy', 'db_info',
+                    'db_set_engine', 'db_get_engine', 'db_predict_windows',
+                    'db_predict_windows_f64', 'db_predict_windows_device', 'db_call_batch',
+                    'db_call_batch_device', 'db_last_gpu_ms', 'db_kernel_launches']
+
+
+def check(rc, what):
+    if rc != DBN_OK:
+        msg = load_library().db_last_error().decode('utf-8', 'replace')
+        raise NativeError('{} failed ({}): {}'.format(what, rc, msg))
+
+
+def as_ptr(arr):
+    return ctypes.c_void_p(arr.ctypes.data)
+
+
+def require(arr, dtype):
+    """C-contiguous array of `dtype` (copying only if needed)."""
+    return np.ascontiguousarray(arr, dtype=dtype)

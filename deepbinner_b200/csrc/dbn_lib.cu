@@ -1,0 +1,505 @@
+// libdeepbinner_b200: C-ABI (include/deepbinner_b200.h) over hand-written sm_100a CUDA kernels that
+// run Deepbinner's barcode classifier (reference classify.py:325-384 call_batch /
+// classify.py:361 model.predict / network_architecture.py:18-95).  No CPU fallback.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <string>
+#include <vector>
+
+#include "../../include/deepbinner_b200.h"
+#include "dbn_engine.h"
+#include "dbn_weights.h"
+
+namespace dbn {
+
+// ---------------------------------------------------------------------------------------------
+// errors
+// ---------------------------------------------------------------------------------------------
+static thread_local std::string g_last_error;
+
+int fail(int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof buf, fmt, ap);
+    va_end(ap);
+    g_last_error = buf;
+    return code;
+}
+
+#define DBN_CUDA(expr)                                                                            \
+    do {                                                                                          \
+        cudaError_t e_ = (expr);                                                                  \
+        if (e_ != cudaSuccess)                                                                    \
+            return ::dbn::fail(DBN_ECUDA, "%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), \
+                               __FILE__, __LINE__);                                               \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// fp32 engine kernels (one CTA = one window; see dbn_fp32_net.cuh)
+// ---------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(kThreads, 1)
+    k_fp32_predict(Fp32Net net, const T* __restrict__ x, float* __restrict__ probs) {
+    extern __shared__ __align__(16) float smem[];
+    const size_t w = blockIdx.x;
+    float* B = smem + kBufFloats;
+    DBN_PHASE(stage_window_from_values(tid, x + w * kInputSize, B));
+    fp32_forward_window(net, smem, probs + w * net.n_classes);
+}
+
+// Fused call_batch front end: window w = step * n_reads + read (the reference's step-major order,
+// classify.py:337-361); slices, z-scores and pads the window straight from the int16 scan region.
+__global__ void __launch_bounds__(kThreads, 1)
+    k_fp32_call_windows(Fp32Net net, const int16_t* __restrict__ samples,
+                        const int64_t* __restrict__ offsets, int n_reads, int side,
+                        float* __restrict__ step_probs) {
+    extern __shared__ __align__(16) float smem[];
+    const int w = blockIdx.x;
+    const int step = w / n_reads, read = w % n_reads;
+    const int64_t off = offsets[read];
+    const int region_len = static_cast<int>(offsets[read + 1] - off);
+    const int16_t* region = samples + off;
+    const WindowGeom g = window_geometry(region_len, step, side);
+    long long* red = reinterpret_cast<long long*>(smem);  // buffer A is free during staging
+    float* B = smem + kBufFloats;
+    DBN_PHASE(window_partial_sums(tid, region, g, red));
+    DBN_PHASE(window_reduce(tid, red));
+    DBN_PHASE(window_normalise(tid, region, g, red, B));
+    fp32_forward_window(net, smem, step_probs + static_cast<size_t>(w) * net.n_classes);
+}
+
+// ---------------------------------------------------------------------------------------------
+// per-read merge + renormalise + call (classify.py:363-384, :387-393, :285-295)
+// ---------------------------------------------------------------------------------------------
+__global__ void k_merge_call(const float* __restrict__ step_probs, int n_reads, int steps, int nc,
+                             double score_diff, float* __restrict__ probs,
+                             int8_t* __restrict__ calls) {
+    const int r = blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= n_reads) return;
+    float m[kMaxClasses];
+    for (int j = 0; j < nc; ++j) m[j] = step_probs[static_cast<size_t>(r) * nc + j];
+    for (int s = 1; s < steps; ++s) {
+        const float* row = step_probs + (static_cast<size_t>(s) * n_reads + r) * nc;
+        m[0] = fminf(m[0], row[0]);                               // :373 no-barcode: minimum
+        for (int j = 1; j < nc; ++j) m[j] = fmaxf(m[j], row[j]);  // :374-375 barcodes: maximum
+    }
+    // make_sum_to_one (:387-393).  With the numpy of the reference's era these scalar expressions
+    // promote the float32 softmax values to float64; same order of operations here.
+    const double none = static_cast<double>(m[0]);
+    double sum = 0.0;
+    for (int j = 1; j < nc; ++j) sum += static_cast<double>(m[j]);
+    const double factor = (1.0 - none) / sum;
+    double p[kMaxClasses];
+    p[0] = none;
+    for (int j = 1; j < nc; ++j) p[j] = static_cast<double>(m[j]) * factor;
+    // get_barcode_call_from_probabilities (:285-295): stable descending sort => first maximum wins
+    int best = 0;
+    for (int j = 1; j < nc; ++j)
+        if (p[j] > p[best]) best = j;
+    double second = -1.0;
+    for (int j = 0; j < nc; ++j)
+        if (j != best && p[j] > second) second = p[j];
+    int call = 0;
+    if (best != 0 && (p[best] - second) >= score_diff) call = best;
+    for (int j = 0; j < nc; ++j) probs[static_cast<size_t>(r) * nc + j] = static_cast<float>(p[j]);
+    calls[r] = static_cast<int8_t>(call);
+}
+
+// float64 windows -> float32 (Keras casts model inputs to floatx; Appendix B.7) is folded into
+// k_fp32_predict<double>.
+
+}  // namespace dbn
+
+// =================================================================================================
+// handle
+// =================================================================================================
+struct db_model {
+    int device = 0;
+    int input_size = 0;
+    int n_classes = 0;
+    int engine = DBN_ENGINE_FP32;
+    bool tc_available = false;
+    int sm_count = 0;
+    dbn::Blob blob;
+    // fp32 engine
+    float* d_fp32_w = nullptr;
+    dbn::Fp32Net fp32{};
+    // tcgen05 engine
+    dbn::TcEngine* tc = nullptr;
+    // streams / events
+    cudaStream_t streams[2] = {nullptr, nullptr};
+    cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    float last_ms = 0.f;
+    int64_t launches = 0;
+    // device scratch (grown on demand)
+    void* d_in[2] = {nullptr, nullptr};
+    size_t d_in_bytes[2] = {0, 0};
+    float* d_out[2] = {nullptr, nullptr};
+    size_t d_out_bytes[2] = {0, 0};
+    int64_t* d_offsets = nullptr;
+    size_t d_offsets_bytes = 0;
+    float* d_step = nullptr;
+    size_t d_step_bytes = 0;
+    int8_t* d_calls = nullptr;
+    size_t d_calls_bytes = 0;
+    // pinned host staging for call_batch gathers
+    int16_t* h_samples = nullptr;
+    size_t h_samples_bytes = 0;
+    int64_t* h_offsets = nullptr;
+    size_t h_offsets_bytes = 0;
+};
+
+namespace dbn {
+
+template <typename T>
+static int grow(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFree(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = std::max(need, static_cast<size_t>(1) << 20);
+    DBN_CUDA(cudaMalloc(reinterpret_cast<void**>(p), want));
+    *cap = want;
+    return 0;
+}
+
+template <typename T>
+static int grow_host(T** p, size_t* cap, size_t need) {
+    if (need <= *cap) return 0;
+    if (*p) cudaFreeHost(*p);
+    *p = nullptr;
+    *cap = 0;
+    size_t want = std::max(need, static_cast<size_t>(1) << 20);
+    DBN_CUDA(cudaMallocHost(reinterpret_cast<void**>(p), want));
+    *cap = want;
+    return 0;
+}
+
+static constexpr size_t kFp32SmemBytes = sizeof(float) * kFp32SmemFloats;
+
+static int launch_predict(db_model* m, const void* d_x, bool is_f64, int64_t n, float* d_probs,
+                          cudaStream_t st) {
+    if (n <= 0) return 0;
+    if (n > 0x7fffffff) return fail(DBN_EINVAL, "too many windows in one launch");
+    if (m->engine == DBN_ENGINE_TCGEN05 && !is_f64) {
+        int rc = tc_predict(m->tc, static_cast<const float*>(d_x), n, d_probs, st);
+        if (rc) return rc;
+        m->launches += 1;
+        return 0;
+    }
+    const dim3 grid(static_cast<unsigned>(n));
+    if (is_f64)
+        k_fp32_predict<double><<<grid, kThreads, kFp32SmemBytes, st>>>(
+            m->fp32, static_cast<const double*>(d_x), d_probs);
+    else
+        k_fp32_predict<float><<<grid, kThreads, kFp32SmemBytes, st>>>(
+            m->fp32, static_cast<const float*>(d_x), d_probs);
+    DBN_CUDA(cudaGetLastError());
+    m->launches += 1;
+    return 0;
+}
+
+static int launch_call_batch(db_model* m, const int16_t* d_samples, const int64_t* d_offsets,
+                             int n_reads, int side, int steps, double score_diff, float* d_step,
+                             float* d_probs, int8_t* d_calls, cudaStream_t st) {
+    if (n_reads <= 0) return 0;
+    const int64_t windows = static_cast<int64_t>(n_reads) * steps;
+    if (windows > 0x7fffffff) return fail(DBN_EINVAL, "too many windows in one launch");
+    if (m->engine == DBN_ENGINE_TCGEN05) {
+        int rc = tc_call_windows(m->tc, d_samples, d_offsets, n_reads, side, steps, d_step, st);
+        if (rc) return rc;
+    } else {
+        k_fp32_call_windows<<<static_cast<unsigned>(windows), kThreads, kFp32SmemBytes, st>>>(
+            m->fp32, d_samples, d_offsets, n_reads, side, d_step);
+        DBN_CUDA(cudaGetLastError());
+    }
+    k_merge_call<<<(n_reads + 127) / 128, 128, 0, st>>>(d_step, n_reads, steps, m->n_classes,
+                                                        score_diff, d_probs, d_calls);
+    DBN_CUDA(cudaGetLastError());
+    m->launches += 2;
+    return 0;
+}
+
+static int check_scan(const db_model* m, int scan_size, int* steps) {
+    const int step = m->input_size / 2;
+    if (scan_size <= 0 || scan_size % step != 0)
+        return fail(DBN_EINVAL, "--scan_size must be a multiple of half the model input size");
+    *steps = scan_size / step;
+    return 0;
+}
+
+}  // namespace dbn
+
+using namespace dbn;
+
+// =================================================================================================
+// C ABI
+// =================================================================================================
+#pragma GCC visibility push(default)
+extern "C" {
+
+int db_abi_version(void) { return DBN_ABI_VERSION; }
+
+const char* db_last_error(void) { return g_last_error.c_str(); }
+
+void db_destroy(db_model* m) {
+    if (!m) return;
+    cudaSetDevice(m->device);
+    if (m->tc) tc_destroy(m->tc);
+    cudaFree(m->d_fp32_w);
+    for (int i = 0; i < 2; ++i) {
+        cudaFree(m->d_in[i]);
+        cudaFree(m->d_out[i]);
+        if (m->streams[i]) cudaStreamDestroy(m->streams[i]);
+    }
+    cudaFree(m->d_offsets);
+    cudaFree(m->d_step);
+    cudaFree(m->d_calls);
+    if (m->h_samples) cudaFreeHost(m->h_samples);
+    if (m->h_offsets) cudaFreeHost(m->h_offsets);
+    if (m->ev_start) cudaEventDestroy(m->ev_start);
+    if (m->ev_stop) cudaEventDestroy(m->ev_stop);
+    delete m;
+}
+
+int db_create(const void* weights_blob, size_t blob_bytes, int device, db_model** out) {
+    if (!out) return fail(DBN_EINVAL, "db_create: out is NULL");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        return fail(DBN_ENODEVICE, "no CUDA device available (this library has no CPU fallback)");
+    if (device < 0 || device >= ndev) return fail(DBN_EINVAL, "device %d out of range", device);
+    cudaDeviceProp prop;
+    DBN_CUDA(cudaGetDeviceProperties(&prop, device));
+    if (prop.major != 10)
+        return fail(DBN_ENODEVICE, "device %d is sm_%d%d; this library is built for sm_100a (B200)",
+                    device, prop.major, prop.minor);
+    db_model* m = new (std::nothrow) db_model();
+    if (!m) return fail(DBN_ENOMEM, "out of host memory");
+    m->device = device;
+    m->sm_count = prop.multiProcessorCount;
+    const std::string err = parse_blob(weights_blob, blob_bytes, &m->blob);
+    if (!err.empty()) {
+        delete m;
+        return fail(DBN_EFORMAT, "%s", err.c_str());
+    }
+    m->input_size = m->blob.input_size;
+    m->n_classes = m->blob.n_classes;
+    int rc = [&]() -> int {
+        DBN_CUDA(cudaSetDevice(device));
+        std::vector<float> packed;
+        pack_fp32(m->blob, &packed, &m->fp32.lay);
+        DBN_CUDA(cudaMalloc(&m->d_fp32_w, packed.size() * sizeof(float)));
+        DBN_CUDA(cudaMemcpy(m->d_fp32_w, packed.data(), packed.size() * sizeof(float),
+                            cudaMemcpyHostToDevice));
+        m->fp32.w = m->d_fp32_w;
+        m->fp32.n_classes = m->n_classes;
+        DBN_CUDA(cudaFuncSetAttribute(k_fp32_predict<float>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32SmemBytes));
+        DBN_CUDA(cudaFuncSetAttribute(k_fp32_predict<double>,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32SmemBytes));
+        DBN_CUDA(cudaFuncSetAttribute(k_fp32_call_windows,
+                                      cudaFuncAttributeMaxDynamicSharedMemorySize, kFp32SmemBytes));
+        for (int i = 0; i < 2; ++i)
+            DBN_CUDA(cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking));
+        DBN_CUDA(cudaEventCreate(&m->ev_start));
+        DBN_CUDA(cudaEventCreate(&m->ev_stop));
+        return 0;
+    }();
+    if (rc) {
+        db_destroy(m);
+        return rc;
+    }
+    // tensor-core engine: optional at creation (falls back to the fp32 CUDA engine - still GPU -
+    // if it cannot be set up); selected by default when available.
+    m->tc = tc_create(m->blob, m->sm_count);
+    m->tc_available = (m->tc != nullptr);
+    m->engine = m->tc_available ? DBN_ENGINE_TCGEN05 : DBN_ENGINE_FP32;
+    *out = m;
+    return DBN_OK;
+}
+
+int db_info(const db_model* m, int* input_size, int* n_classes) {
+    if (!m) return fail(DBN_EINVAL, "db_info: model is NULL");
+    if (input_size) *input_size = m->input_size;
+    if (n_classes) *n_classes = m->n_classes;
+    return DBN_OK;
+}
+
+int db_set_engine(db_model* m, int engine) {
+    if (!m) return fail(DBN_EINVAL, "db_set_engine: model is NULL");
+    if (engine == DBN_ENGINE_FP32) {
+        m->engine = engine;
+        return DBN_OK;
+    }
+    if (engine == DBN_ENGINE_TCGEN05) {
+        if (!m->tc_available) return fail(DBN_EINVAL, "tcgen05 engine is not available in this build");
+        m->engine = engine;
+        return DBN_OK;
+    }
+    return fail(DBN_EINVAL, "unknown engine %d", engine);
+}
+
+int db_get_engine(const db_model* m) { return m ? m->engine : DBN_EINVAL; }
+
+static int predict_host(db_model* m, const void* x, bool is_f64, int64_t n, float* probs) {
+    if (!m) return fail(DBN_EINVAL, "predict: model is NULL");
+    if (n < 0) return fail(DBN_EINVAL, "predict: n < 0");
+    if (n == 0) return DBN_OK;
+    if (!x || !probs) return fail(DBN_EINVAL, "predict: NULL buffer");
+    DBN_CUDA(cudaSetDevice(m->device));
+    const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
+    const int64_t kChunk = 16384;  // windows per pipelined chunk (64 MiB of fp32 input)
+    const size_t row_in = static_cast<size_t>(m->input_size) * esz;
+    const size_t row_out = static_cast<size_t>(m->n_classes) * sizeof(float);
+    DBN_CUDA(cudaEventRecord(m->ev_start, m->streams[0]));
+    int64_t done = 0;
+    int slot = 0;
+    while (done < n) {
+        const int64_t cnt = std::min(kChunk, n - done);
+        cudaStream_t st = m->streams[slot];
+        if (slot == 1 && done == kChunk)  // first use of stream 1: order it after the start event
+            DBN_CUDA(cudaStreamWaitEvent(st, m->ev_start, 0));
+        int rc = grow(&m->d_in[slot], &m->d_in_bytes[slot], cnt * row_in);
+        if (rc) return rc;
+        rc = grow(&m->d_out[slot], &m->d_out_bytes[slot], cnt * row_out);
+        if (rc) return rc;
+        DBN_CUDA(cudaMemcpyAsync(m->d_in[slot], static_cast<const char*>(x) + done * row_in,
+                                 cnt * row_in, cudaMemcpyHostToDevice, st));
+        rc = launch_predict(m, m->d_in[slot], is_f64, cnt, m->d_out[slot], st);
+        if (rc) return rc;
+        DBN_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(probs) + done * row_out, m->d_out[slot],
+                                 cnt * row_out, cudaMemcpyDeviceToHost, st));
+        done += cnt;
+        slot ^= 1;
+    }
+    if (n > kChunk) {
+        // join stream 1 into stream 0 before the stop event
+        cudaEvent_t join;
+        DBN_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
+        DBN_CUDA(cudaEventRecord(join, m->streams[1]));
+        DBN_CUDA(cudaStreamWaitEvent(m->streams[0], join, 0));
+        DBN_CUDA(cudaEventDestroy(join));
+    }
+    DBN_CUDA(cudaEventRecord(m->ev_stop, m->streams[0]));
+    DBN_CUDA(cudaEventSynchronize(m->ev_stop));
+    DBN_CUDA(cudaStreamSynchronize(m->streams[1]));
+    DBN_CUDA(cudaEventElapsedTime(&m->last_ms, m->ev_start, m->ev_stop));
+    return DBN_OK;
+}
+
+int db_predict_windows(db_model* m, const float* x, int64_t n, float* probs) {
+    return predict_host(m, x, false, n, probs);
+}
+
+int db_predict_windows_f64(db_model* m, const double* x, int64_t n, float* probs) {
+    return predict_host(m, x, true, n, probs);
+}
+
+int db_predict_windows_device(db_model* m, const float* d_x, int64_t n, float* d_probs,
+                              void* stream) {
+    if (!m) return fail(DBN_EINVAL, "predict: model is NULL");
+    if (n < 0) return fail(DBN_EINVAL, "predict: n < 0");
+    if (n == 0) return DBN_OK;
+    if (!d_x || !d_probs) return fail(DBN_EINVAL, "predict: NULL buffer");
+    DBN_CUDA(cudaSetDevice(m->device));
+    return launch_predict(m, d_x, false, n, d_probs, static_cast<cudaStream_t>(stream));
+}
+
+int db_call_batch(db_model* m, const int16_t* samples, const int64_t* offsets, int n_reads,
+                  int side, int scan_size, double score_diff, float* probs, int8_t* calls) {
+    if (!m) return fail(DBN_EINVAL, "call_batch: model is NULL");
+    if (n_reads < 0) return fail(DBN_EINVAL, "call_batch: n_reads < 0");
+    if (side != DBN_SIDE_START && side != DBN_SIDE_END) return fail(DBN_EINVAL, "call_batch: bad side");
+    int steps = 0;
+    int rc = check_scan(m, scan_size, &steps);
+    if (rc) return rc;
+    if (n_reads == 0) return DBN_OK;
+    if (!samples || !offsets || !probs || !calls) return fail(DBN_EINVAL, "call_batch: NULL buffer");
+    DBN_CUDA(cudaSetDevice(m->device));
+    // Gather each read's scan region (the only samples call_batch ever looks at: the first / last
+    // scan_size + input_size/2 samples, classify.py:337-349) into pinned staging.
+    const int64_t region_max = static_cast<int64_t>(scan_size) + m->input_size / 2;
+    rc = grow_host(&m->h_offsets, &m->h_offsets_bytes, sizeof(int64_t) * (n_reads + 1));
+    if (rc) return rc;
+    int64_t total = 0;
+    for (int i = 0; i < n_reads; ++i) {
+        const int64_t len = offsets[i + 1] - offsets[i];
+        if (len < 0) return fail(DBN_EINVAL, "call_batch: offsets must be non-decreasing");
+        m->h_offsets[i] = total;
+        total += std::min(len, region_max);
+    }
+    m->h_offsets[n_reads] = total;
+    rc = grow_host(&m->h_samples, &m->h_samples_bytes, sizeof(int16_t) * std::max<int64_t>(total, 1));
+    if (rc) return rc;
+    for (int i = 0; i < n_reads; ++i) {
+        const int64_t len = offsets[i + 1] - offsets[i];
+        const int64_t r = std::min(len, region_max);
+        const int16_t* src = samples + offsets[i] + (side == DBN_SIDE_START ? 0 : len - r);
+        std::memcpy(m->h_samples + m->h_offsets[i], src, sizeof(int16_t) * r);
+    }
+    cudaStream_t st = m->streams[0];
+    const size_t nc = m->n_classes;
+    rc = grow(&m->d_in[0], &m->d_in_bytes[0], sizeof(int16_t) * std::max<int64_t>(total, 1));
+    if (rc) return rc;
+    rc = grow(&m->d_offsets, &m->d_offsets_bytes, sizeof(int64_t) * (n_reads + 1));
+    if (rc) return rc;
+    rc = grow(&m->d_step, &m->d_step_bytes, sizeof(float) * nc * n_reads * steps);
+    if (rc) return rc;
+    rc = grow(&m->d_out[0], &m->d_out_bytes[0], sizeof(float) * nc * n_reads);
+    if (rc) return rc;
+    rc = grow(&m->d_calls, &m->d_calls_bytes, static_cast<size_t>(n_reads));
+    if (rc) return rc;
+    DBN_CUDA(cudaMemcpyAsync(m->d_in[0], m->h_samples, sizeof(int16_t) * total,
+                             cudaMemcpyHostToDevice, st));
+    DBN_CUDA(cudaMemcpyAsync(m->d_offsets, m->h_offsets, sizeof(int64_t) * (n_reads + 1),
+                             cudaMemcpyHostToDevice, st));
+    DBN_CUDA(cudaEventRecord(m->ev_start, st));
+    rc = launch_call_batch(m, static_cast<const int16_t*>(m->d_in[0]), m->d_offsets, n_reads, side,
+                           steps, score_diff, m->d_step, m->d_out[0], m->d_calls, st);
+    if (rc) return rc;
+    DBN_CUDA(cudaEventRecord(m->ev_stop, st));
+    DBN_CUDA(cudaMemcpyAsync(probs, m->d_out[0], sizeof(float) * nc * n_reads,
+                             cudaMemcpyDeviceToHost, st));
+    DBN_CUDA(cudaMemcpyAsync(calls, m->d_calls, static_cast<size_t>(n_reads),
+                             cudaMemcpyDeviceToHost, st));
+    DBN_CUDA(cudaStreamSynchronize(st));
+    DBN_CUDA(cudaEventElapsedTime(&m->last_ms, m->ev_start, m->ev_stop));
+    return DBN_OK;
+}
+
+int db_call_batch_device(db_model* m, const int16_t* d_samples, const int64_t* d_offsets,
+                         int n_reads, int side, int scan_size, double score_diff, float* d_probs,
+                         int8_t* d_calls, float* d_step_probs, void* stream) {
+    if (!m) return fail(DBN_EINVAL, "call_batch: model is NULL");
+    if (n_reads < 0) return fail(DBN_EINVAL, "call_batch: n_reads < 0");
+    if (side != DBN_SIDE_START && side != DBN_SIDE_END) return fail(DBN_EINVAL, "call_batch: bad side");
+    int steps = 0;
+    int rc = check_scan(m, scan_size, &steps);
+    if (rc) return rc;
+    if (n_reads == 0) return DBN_OK;
+    if (!d_samples || !d_offsets || !d_probs || !d_calls) return fail(DBN_EINVAL, "call_batch: NULL buffer");
+    DBN_CUDA(cudaSetDevice(m->device));
+    float* d_step = d_step_probs;
+    if (!d_step) {
+        rc = grow(&m->d_step, &m->d_step_bytes,
+                  sizeof(float) * static_cast<size_t>(m->n_classes) * n_reads * steps);
+        if (rc) return rc;
+        d_step = m->d_step;
+    }
+    return launch_call_batch(m, d_samples, d_offsets, n_reads, side, steps, score_diff, d_step,
+                             d_probs, d_calls, static_cast<cudaStream_t>(stream));
+}
+
+float db_last_gpu_ms(const db_model* m) { return m ? m->last_ms : 0.f; }
+
+int64_t db_kernel_launches(const db_model* m) { return m ? m->launches : 0; }
+
+}  // extern "C"
+#pragma GCC visibility pop

@@ -1,0 +1,165 @@
+"""
+B200Model: the model object of the classification path.
+
+Stands in for the Keras `Model` that reference `classify.py:86-103 load_trained_model` returns and
+that `call_batch` drives at `classify.py:361` (seam b1 of SURVEY section 8b): `.inputs[0].shape`,
+`.outputs[0].shape` and `.predict(x, batch_size)`.  It additionally exposes the fused
+`call_batch`-level entry (seam b2) that runs windowing + z-score + CNN + merge + call on the GPU.
+"""
+
+import ctypes
+
+import numpy as np
+
+from . import _native, weights
+
+
+class _TensorSpec:
+    """Mimics a Keras tensor just enough for `int(model.inputs[0].shape[1])`."""
+
+    def __init__(self, shape):
+        self.shape = tuple(shape)
+
+
+class B200Model:
+
+    def __init__(self, model_file=None, blob=None, device=0, engine=None):
+        if blob is None:
+            blob = weights.load_blob(model_file)
+        self._lib = _native.load_library()
+        self._handle = ctypes.c_void_p()
+        self._blob = bytes(blob)
+        rc = self._lib.db_create(self._blob, len(self._blob), int(device),
+                                 ctypes.byref(self._handle))
+        _native.check(rc, 'db_create')
+        isz, ncl = ctypes.c_int(), ctypes.c_int()
+        _native.check(self._lib.db_info(self._handle, ctypes.byref(isz), ctypes.byref(ncl)),
+                      'db_info')
+        self.input_size = isz.value
+        self.n_classes = ncl.value
+        self.device = int(device)
+        self.model_file = model_file
+        self.inputs = [_TensorSpec((None, self.input_size, 1))]
+        self.outputs = [_TensorSpec((None, self.n_classes))]
+        if engine is not None:
+            self.set_engine(engine)
+
+    # -- lifetime ------------------------------------------------------------------------------
+    def close(self):
+        if getattr(self, '_handle', None) is not None and self._handle:
+            self._lib.db_destroy(self._handle)
+            self._handle = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:  # noqa: BLE001
+            pass
+
+    # -- engine --------------------------------------------------------------------------------
+    def set_engine(self, engine):
+        if isinstance(engine, str):
+            engine = {v: k for k, v in _native.ENGINE_NAMES.items()}[engine]
+        _native.check(self._lib.db_set_engine(self._handle, int(engine)), 'db_set_engine')
+
+    @property
+    def engine(self):
+        return _native.ENGINE_NAMES[self._lib.db_get_engine(self._handle)]
+
+    @property
+    def blob(self):
+        return self._blob
+
+    # -- seam b1: model.predict (classify.py:361) -----------------------------------------------
+    def predict(self, x, batch_size=256, verbose=0):
+        """x: [n, input_size, 1] or [n, input_size] float array (the reference passes float64).
+        Returns a freshly allocated, writable float32 [n, n_classes] array of softmax rows
+        (the caller keeps and mutates rows, classify.py:370-374)."""
+        x = np.asarray(x)
+        if x.ndim == 3 and x.shape[2] == 1:
+            x = x.reshape(x.shape[0], x.shape[1])
+        if x.ndim != 2 or x.shape[1] != self.input_size:
+            raise ValueError('expected input of shape (n, {}, 1), got {}'
+                             .format(self.input_size, x.shape))
+        n = x.shape[0]
+        probs = np.empty((n, self.n_classes), dtype=np.float32)
+        if n == 0:
+            return probs
+        if x.dtype == np.float64:
+            x = _native.require(x, np.float64)
+            rc = self._lib.db_predict_windows_f64(self._handle, _native.as_ptr(x), n,
+                                                  _native.as_ptr(probs))
+        else:
+            x = _native.require(x, np.float32)
+            rc = self._lib.db_predict_windows(self._handle, _native.as_ptr(x), n,
+                                              _native.as_ptr(probs))
+        _native.check(rc, 'db_predict_windows')
+        return probs
+
+    # -- seam b2: fused call_batch (classify.py:325-384) -------------------------------------------
+    def call_batch(self, signals, side, scan_size, score_diff):
+        """signals: list of 1-D integer arrays.  Returns (calls int8 [n] with 0 = 'none',
+        probabilities float32 [n, n_classes] after make_sum_to_one)."""
+        samples, offsets = pack_scan_regions(signals, side, int(scan_size), self.input_size)
+        n = len(signals)
+        probs = np.empty((n, self.n_classes), dtype=np.float32)
+        calls = np.empty(n, dtype=np.int8)
+        rc = self._lib.db_call_batch(self._handle, _native.as_ptr(samples), _native.as_ptr(offsets),
+                                     n, _native.SIDE_START if side == 'start' else _native.SIDE_END,
+                                     int(scan_size), float(score_diff), _native.as_ptr(probs),
+                                     _native.as_ptr(calls))
+        _native.check(rc, 'db_call_batch')
+        return calls, probs
+
+    # -- device-resident entry points (used by bench.py for kernel-only timing) --------------------
+    def predict_device(self, d_x_ptr, n, d_probs_ptr, stream_ptr=0):
+        rc = self._lib.db_predict_windows_device(self._handle, ctypes.c_void_p(d_x_ptr), int(n),
+                                                 ctypes.c_void_p(d_probs_ptr),
+                                                 ctypes.c_void_p(stream_ptr))
+        _native.check(rc, 'db_predict_windows_device')
+
+    def call_batch_device(self, d_samples_ptr, d_offsets_ptr, n_reads, side, scan_size, score_diff,
+                          d_probs_ptr, d_calls_ptr, d_step_ptr=0, stream_ptr=0):
+        rc = self._lib.db_call_batch_device(
+            self._handle, ctypes.c_void_p(d_samples_ptr), ctypes.c_void_p(d_offsets_ptr),
+            int(n_reads), _native.SIDE_START if side == 'start' else _native.SIDE_END,
+            int(scan_size), float(score_diff), ctypes.c_void_p(d_probs_ptr),
+            ctypes.c_void_p(d_calls_ptr), ctypes.c_void_p(d_step_ptr), ctypes.c_void_p(stream_ptr))
+        _native.check(rc, 'db_call_batch_device')
+
+    @property
+    def last_gpu_ms(self):
+        return float(self._lib.db_last_gpu_ms(self._handle))
+
+    @property
+    def kernel_launches(self):
+        return int(self._lib.db_kernel_launches(self._handle))
+
+
+def signals_fit_int16(signals):
+    for s in signals:
+        s = np.asarray(s)
+        if s.dtype == np.int16:
+            continue
+        if s.dtype.kind not in 'iu':
+            return False
+        if s.size and (s.min() < -32768 or s.max() > 32767):
+            return False
+    return True
+
+
+def pack_scan_regions(signals, side, scan_size, input_size):
+    """Concatenate the part of each read that call_batch can ever look at - its first ('start') or
+    last ('end') scan_size + input_size/2 samples (classify.py:337-349) - as int16 + int64 offsets."""
+    region = scan_size + input_size // 2
+    parts = []
+    offsets = np.zeros(len(signals) + 1, dtype=np.int64)
+    for i, s in enumerate(signals):
+        s = np.asarray(s)
+        piece = s[:region] if side == 'start' else s[max(len(s) - region, 0):]
+        parts.append(piece.astype(np.int16, copy=False))
+        offsets[i + 1] = offsets[i] + len(piece)
+    samples = np.concatenate(parts) if parts else np.zeros(0, dtype=np.int16)
+    if samples.size == 0:
+        samples = np.zeros(1, dtype=np.int16)
+    return np.ascontiguousarray(samples, dtype=np.int16), offsets

@@ -1,0 +1,138 @@
+/*
+ * deepbinner_b200 - C ABI of the B200-native barcode-from-squiggle classifier.
+ *
+ * This is the drop-in boundary for the one hot path of rrwick/Deepbinner that this library
+ * accelerates (raw signal window -> 1-D CNN -> softmax -> per-read barcode call).  The reference has
+ * no plugin registry; its seams are Python call sites, and its only FFI
+ * convention is `deepbinner/dtw/dtw.h:16-19` + `deepbinner/dtw_semi_global.py:26-58`:
+ * `extern "C"` free functions, C-contiguous caller-allocated arrays, scalars by value.  The entry
+ * points below follow that convention; each one cites the reference interface it replaces.
+ *
+ * All functions return 0 on success or a negative DBN_E* code; db_last_error() returns a
+ * thread-local human-readable message for the last failure.  A handle may be used from one host
+ * thread at a time.  Host pointers may be pageable or pinned; "_device" variants take device
+ * pointers on the handle's device and run asynchronously on the given stream.
+ *
+ * There is no CPU fallback: db_create() fails (DBN_ENODEVICE) when no sm_100 GPU is usable.
+ */
+#ifndef DEEPBINNER_B200_H
+#define DEEPBINNER_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DBN_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define DBN_API __attribute__((visibility("default")))
+#else
+#define DBN_API
+#endif
+
+#define DBN_OK 0
+#define DBN_EINVAL (-1)    /* bad argument */
+#define DBN_EFORMAT (-2)   /* weight blob is not a valid DBNW v1 blob / unsupported topology */
+#define DBN_ENODEVICE (-3) /* no usable CUDA device (compute capability 10.x required) */
+#define DBN_ECUDA (-4)     /* CUDA runtime error; see db_last_error() */
+#define DBN_ENOMEM (-5)
+
+#define DBN_SIDE_START 0 /* call_batch side='start' (classify.py:343-344) */
+#define DBN_SIDE_END 1   /* call_batch side='end'   (classify.py:345-349) */
+
+/* Engines (db_set_engine).  Both are hand-written sm_100a CUDA; results agree to ~1e-4. */
+#define DBN_ENGINE_FP32 0    /* CUDA-core fp32 fused per-window kernel (parity anchor) */
+#define DBN_ENGINE_TCGEN05 1 /* tcgen05/TMEM split-bf16 tensor-core kernel */
+
+typedef struct db_model db_model;
+
+/* ABI version of the loaded library (== DBN_ABI_VERSION at build time). */
+DBN_API int db_abi_version(void);
+
+/* Thread-local message describing the last error on this thread ("" if none). */
+DBN_API const char *db_last_error(void);
+
+/*
+ * Replaces keras.models.load_model at classify.py:86-103 (load_trained_model).
+ * weights_blob: DBNW v1 blob (deepbinner_b200/weights.py) with the parameters of the
+ * network_architecture.py:18-95 graph; copied - the caller may free it after the call.
+ * device: CUDA device ordinal.  *out receives the handle.
+ */
+DBN_API int db_create(const void *weights_blob, size_t blob_bytes, int device, db_model **out);
+
+/* Releases all device and host resources of the handle (NULL is a no-op). */
+DBN_API void db_destroy(db_model *model);
+
+/*
+ * model.inputs[0].shape[1] and model.outputs[0].shape[1] as read at classify.py:92-99
+ * (1024 and 13 for the shipped models).
+ */
+DBN_API int db_info(const db_model *model, int *input_size, int *n_classes);
+
+/* Select the compute engine (DBN_ENGINE_*).  Default: the fastest engine that passed self-test. */
+DBN_API int db_set_engine(db_model *model, int engine);
+DBN_API int db_get_engine(const db_model *model);
+
+/*
+ * Seam b1 - model.predict(x, batch_size) at classify.py:361.
+ * x: host [n, input_size] already-normalised windows (float32, C-contiguous; the _f64 variant
+ * takes the float64 array the reference builds at classify.py:340 and casts to float32 on the
+ * device, as Keras does).  probs: host [n, n_classes] float32 softmax rows, written in full.
+ * n may be any size >= 0; the library tiles it over the device.
+ */
+DBN_API int db_predict_windows(db_model *model, const float *x, int64_t n, float *probs);
+DBN_API int db_predict_windows_f64(db_model *model, const double *x, int64_t n, float *probs);
+
+/* Same with device-resident input/output, asynchronous on `stream` (a cudaStream_t, may be 0). */
+DBN_API int db_predict_windows_device(db_model *model, const float *d_x, int64_t n, float *d_probs,
+                              void *stream);
+
+/*
+ * Seam b2 - call_batch(input_size, output_size, read_ids, signals, model, args, side) at
+ * classify.py:325-384, fused: windowing (:337-349), normalise (trim_signal.py:61-69), zero padding
+ * (:352-357), predict (:361), the min/max merge over scan steps (:363-377), make_sum_to_one
+ * (:387-393) and get_barcode_call_from_probabilities (:285-295) all run on the device.
+ *
+ * samples:  host int16, the raw signals of the batch concatenated
+ * offsets:  host int64 [n_reads + 1]; read i is samples[offsets[i] .. offsets[i+1])
+ * side:     DBN_SIDE_START / DBN_SIDE_END
+ * scan_size: args.scan_size; must be a positive multiple of input_size/2 (check_input_size,
+ *            classify.py:396-407) else DBN_EINVAL
+ * score_diff: args.score_diff
+ * probs:    host float32 [n_reads, n_classes] - per-read probabilities after make_sum_to_one
+ * calls:    host int8 [n_reads] - 0 = 'none', k = barcode 'k'
+ * Only the scan region of each read - its first (side start) / last (side end)
+ * min(len, scan_size + input_size/2) samples, which is all call_batch ever slices
+ * (classify.py:337-349: the last step reads [scan_size - step, scan_size + step)) - is transferred
+ * to the device.
+ */
+DBN_API int db_call_batch(db_model *model, const int16_t *samples, const int64_t *offsets, int n_reads,
+                  int side, int scan_size, double score_diff, float *probs, int8_t *calls);
+
+/*
+ * Device-resident variant: d_samples holds, for read i, its scan region (first/last
+ * min(len_i, scan_size + input_size/2) samples) at d_samples[d_offsets[i] .. d_offsets[i+1]).
+ * Asynchronous on `stream`.  d_step_probs receives the per-step softmax rows
+ * [steps, n_reads, n_classes]; it may be NULL, in which case a scratch buffer owned by the handle
+ * is used (then do not overlap calls on different streams).
+ */
+DBN_API int db_call_batch_device(db_model *model, const int16_t *d_samples, const int64_t *d_offsets,
+                         int n_reads, int side, int scan_size, double score_diff, float *d_probs,
+                         int8_t *d_calls, float *d_step_probs, void *stream);
+
+/*
+ * Profiling helpers.  db_last_gpu_ms: device time (CUDA events on the handle's stream) of the
+ * network kernel(s) launched by the most recent host-buffer call.  db_kernel_launches: number of
+ * this library's kernels launched on this handle since creation.
+ */
+DBN_API float db_last_gpu_ms(const db_model *model);
+DBN_API int64_t db_kernel_launches(const db_model *model);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* DEEPBINNER_B200_H */

@@ -1,0 +1,256 @@
+"""GPU parity tests proper: the CUDA path, called through the C-ABI library, against the CPU oracle
+and the committed goldens.  Tolerance from BASELINE.json north_star: identical calls, probabilities
+within 1e-3 max-abs.  Run with `pytest -m gpu` on a B200."""
+import io
+import types
+
+import numpy as np
+import pytest
+
+from conftest import MODELS, model_path, sliding_windows, synthetic_signals
+from oracle import deepbinner_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+TOL = 1e-3   # north_star: softmax probabilities within 1e-3 max-abs of the CPU reference
+
+
+def engines(model):
+    names = ['fp32']
+    try:
+        model.set_engine('tcgen05')
+        names.append('tcgen05')
+    except Exception:  # noqa: BLE001
+        pass
+    return names
+
+
+@pytest.fixture(scope='module')
+def models():
+    from deepbinner_b200.model import B200Model
+    return {m: B200Model(model_path(m)) for m in MODELS}
+
+
+@pytest.fixture(scope='module')
+def oracle_weights():
+    return {m: orc.load_weights(model_path(m)) for m in MODELS}
+
+
+def make_args(**kw):
+    d = dict(verbose=False, batch_size=128, scan_size=6144, score_diff=0.5,
+             require_either=False, require_start=False, require_both=False)
+    d.update(kw)
+    return types.SimpleNamespace(**d)
+
+
+def test_library_is_loaded_and_reports_shapes(models):
+    import deepbinner_b200._native as nat
+    assert nat.LIB_PATH.exists()
+    for m in models.values():
+        assert int(m.inputs[0].shape[1]) == 1024 and int(m.outputs[0].shape[1]) == 13
+        assert m.inputs[0].shape[2] == 1 and len(m.inputs) == 1
+
+
+def test_predict_parity_on_real_windows(models, oracle_weights, fixture_reads, multi_reads):
+    """Windows of the reference fixtures (all scan steps, both sides) + 1000 sliding windows cut at
+    random offsets from real reads (where the unsaturated softmaxes are)."""
+    _, sigs, _ = fixture_reads
+    _, msigs = multi_reads
+    x = np.concatenate([orc.make_windows(sigs, 1024, s, side) for side in ('start', 'end')
+                        for s in range(12)] + [sliding_windows(sigs + msigs, 1000, seed=11)])
+    for name, model in models.items():
+        ref = orc.forward(oracle_weights[name], x.astype(np.float32))
+        unsat = int((ref.max(axis=1) < 0.99).sum())
+        for eng in engines(model):
+            model.set_engine(eng)
+            got = model.predict(x[:, :, None], batch_size=256)
+            assert got.dtype == np.float32 and got.shape == ref.shape and got.flags.writeable
+            err = np.abs(got - ref).max(axis=1)
+            print('{} [{}]: max {:.2e} p99 {:.2e} unsaturated {}/{}'.format(
+                name, eng, err.max(), np.percentile(err, 99), unsat, len(x)))
+            assert err.max() <= TOL
+            assert np.array_equal(got.argmax(axis=1), ref.argmax(axis=1))
+            assert np.allclose(got.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_predict_accepts_f32_f64_and_returns_fresh_arrays(models, fixture_reads):
+    _, sigs, _ = fixture_reads
+    x = orc.make_windows(sigs, 1024, 0, 'start')
+    m = models['EXP-NBD103_read_starts']
+    for eng in engines(m):
+        m.set_engine(eng)
+        a = m.predict(x[:, :, None])
+        b = m.predict(x.astype(np.float32))
+        assert np.abs(a - b).max() < 1e-6 and a is not b
+        a[:] = 0            # caller mutates rows in place (classify.py:370-374)
+        c = m.predict(x[:, :, None])
+        assert np.abs(c - b).max() < 1e-6
+        assert m.predict(np.zeros((0, 1024, 1))).shape == (0, 13)
+
+
+def test_call_batch_goldens(models, fixture_reads, reference_goldens, oracle_outputs):
+    """Fused GPU call_batch on the reference's fixture reads: calls equal the goldens of
+    tests/test_classify.py:115-180, probabilities within 1e-3 of the fp64 oracle."""
+    from deepbinner_b200 import classify as cls
+    ids, sigs, _ = fixture_reads
+    results = {}
+    for name, side in (('EXP-NBD103_read_starts', 'start'), ('EXP-NBD103_read_ends', 'end'),
+                       ('SQK-RBK004_read_starts', 'start')):
+        model = models[name]
+        for eng in engines(model):
+            model.set_engine(eng)
+            calls, probs = cls.call_batch(1024, 13, ids, sigs, model, make_args(), side)
+            key = '{}|{}'.format(name, side)
+            assert calls == list(oracle_outputs[key + '|calls'])
+            assert np.abs(np.array(probs) - oracle_outputs[key + '|probs']).max() <= TOL
+            results[(name, eng)] = dict(zip(ids, calls))
+    for eng in engines(models['EXP-NBD103_read_starts']):
+        start = results[('EXP-NBD103_read_starts', eng)]
+        end = results[('EXP-NBD103_read_ends', eng)]
+        assert start == reference_goldens['start_only']
+        assert end == reference_goldens['end_only']
+        either = {r: cls.combine_calls(start[r], end[r], make_args(require_either=True)) for r in ids}
+        both = {r: cls.combine_calls(start[r], end[r], make_args(require_both=True)) for r in ids}
+        assert either == reference_goldens['both_require_either']
+        assert both == reference_goldens['both_require_both']
+
+
+def test_fused_call_batch_equals_predict_seam(models, fixture_reads, multi_reads):
+    """Seam b2 (fused kernel: device windowing + z-score) == seam b1 (host windowing + predict)."""
+    from deepbinner_b200 import classify as cls
+    _, sigs, _ = fixture_reads
+    _, msigs = multi_reads
+    reads = sigs + msigs[:10]
+    ids = ['r%d' % i for i in range(len(reads))]
+    model = models['EXP-NBD103_read_ends']
+
+    class Foreign:          # hides the B200Model type so call_batch takes the generic path
+        inputs, outputs = model.inputs, model.outputs
+
+        def predict(self, x, batch_size=256):
+            return model.predict(x, batch_size)
+
+    for eng in engines(model):
+        model.set_engine(eng)
+        for side in ('start', 'end'):
+            for scan in (6144, 512, 1024):
+                args = make_args(scan_size=scan, score_diff=0.3)
+                c1, p1 = cls.call_batch(1024, 13, ids, reads, model, args, side)
+                c2, p2 = cls.call_batch(1024, 13, ids, reads, Foreign(), args, side)
+                assert c1 == c2
+                assert np.abs(np.array(p1) - np.array(p2, dtype=float)).max() < 2e-6
+
+
+def test_edge_cases(models, oracle_weights):
+    """Empty, one-sample, constant, short and extreme-valued reads (reference semantics:
+    trim_signal.py:61-69, classify.py:342-357)."""
+    from deepbinner_b200 import classify as cls
+    reads = [np.zeros(0, np.int16), np.array([7], np.int16), np.full(300, -5, np.int16),
+             np.full(5000, 123, np.int16), np.arange(1023, dtype=np.int16),
+             np.arange(1025, dtype=np.int16), (np.arange(9000) % 2 * 65535 - 32768).astype(np.int16),
+             np.full(7000, 32767, np.int16)]
+    ids = ['e%d' % i for i in range(len(reads))]
+    name = 'EXP-NBD103_read_starts'
+    model = models[name]
+    for eng in engines(model):
+        model.set_engine(eng)
+        for side in ('start', 'end'):
+            calls, probs = cls.call_batch(1024, 13, ids, reads, model, make_args(), side)
+            ocalls, oprobs = orc.call_batch(oracle_weights[name], reads, side, 6144, 0.5)
+            assert calls == ocalls
+            assert np.abs(np.array(probs) - np.array(oprobs, dtype=float)).max() <= TOL
+        assert cls.call_batch(1024, 13, [], [], model, make_args(), 'start') == ([], [])
+    # all-zero window (empty slice of a short read) -> p(none) ~ 1
+    p = model.predict(np.zeros((1, 1024, 1)))
+    assert p[0, 0] > 0.9999
+    # int64 signals (training-data TSV path) take the same fused path
+    calls64, _ = cls.call_batch(1024, 13, ids, [r.astype(np.int64) for r in reads], model,
+                                make_args(), 'start')
+    assert calls64 == orc.call_batch(oracle_weights[name], reads, 'start', 6144, 0.5)[0]
+
+
+def test_classify_fast5_files_end_to_end(models, fixture_reads, reference_goldens, monkeypatch, capsys):
+    """classify_fast5_files (seam b3) with the fast5 loader fed from the committed signals (the
+    fast5 fixtures themselves live in the reference checkout, absent on the GPU box)."""
+    from deepbinner_b200 import classify as cls
+    ids, sigs, names = fixture_reads
+    table = {n: (i, s) for n, i, s in zip(names, ids, sigs)}
+    monkeypatch.setattr(cls, 'get_read_id_and_signal',
+                        lambda f: table.get(str(f).split('/')[-1], (None, None)))
+    monkeypatch.setattr(cls, 'determine_single_or_multi_fast5s', lambda files: 'single')
+    start, end = models['EXP-NBD103_read_starts'], models['EXP-NBD103_read_ends']
+    files = ['/x/' + n for n in names] + ['/x/unreadable.fast5']
+    got, where = cls.classify_fast5_files(files, start, 1024, None, None, 13, make_args(),
+                                          full_output=False)
+    assert got == reference_goldens['start_only'] and len(where) == 7
+    got, _ = cls.classify_fast5_files(files, None, None, end, 1024, 13, make_args(), full_output=False)
+    assert got == reference_goldens['end_only']
+    got, _ = cls.classify_fast5_files(files, start, 1024, end, 1024, 13,
+                                      make_args(require_either=True, batch_size=3), full_output=False)
+    assert got == reference_goldens['both_require_either']
+    got, _ = cls.classify_fast5_files(files, start, 1024, end, 1024, 13,
+                                      make_args(require_both=True), full_output=False)
+    assert got == reference_goldens['both_require_both']
+    capsys.readouterr()
+    # verbose TSV row pinned by the reference (tests/test_classify.py:287-296)
+    g = reference_goldens['verbose_row_177c3867']
+    one = ['/x/' + names[ids.index(g['read_id'])]]
+    cls.classify_fast5_files(one, start, 1024, end, 1024, 13,
+                             make_args(require_either=True, verbose=True), full_output=True,
+                             summary_table=False)
+    lines = capsys.readouterr().out.splitlines()
+    assert len(lines) == 2
+    assert lines[1] == '\t'.join([g['read_id'], '3'] + g['start'] + ['3'] + g['end'] + ['3'])
+    with pytest.raises(SystemExit):
+        cls.classify_fast5_files([], start, 1024, None, None, 13, make_args())
+
+
+def test_full_batch_properties(models):
+    """BASELINE config sizes (256 reads x 12 steps): size-independent properties - duplicated reads
+    give bit-identical rows, results are independent of batch composition and order, rows sum to 1,
+    and a large predict() (pipelined chunks) equals per-row predict."""
+    model = models['EXP-NBD103_read_starts']
+    reads = synthetic_signals(128, seed=5, length=np.random.RandomState(2).randint(600, 9000, 128))
+    reads = reads + reads
+    for eng in engines(model):
+        model.set_engine(eng)
+        calls, probs = model.call_batch(reads, 'start', 6144, 0.5)
+        assert np.array_equal(probs[:128], probs[128:]) and np.array_equal(calls[:128], calls[128:])
+        assert np.allclose(probs.sum(axis=1), 1.0, atol=1e-5)
+        perm = np.random.RandomState(3).permutation(256)
+        c2, p2 = model.call_batch([reads[i] for i in perm], 'start', 6144, 0.5)
+        assert np.array_equal(p2, probs[perm]) and np.array_equal(c2, calls[perm])
+        c3, p3 = model.call_batch(reads[:5], 'start', 6144, 0.5)
+        assert np.array_equal(p3, probs[:5])
+        x = np.random.RandomState(4).randn(40000, 1024).astype(np.float32)
+        big = model.predict(x)
+        idx = [0, 1, 16383, 16384, 16385, 32767, 32768, 39999]
+        assert np.array_equal(big[idx], model.predict(x[idx]))
+        assert np.allclose(big.sum(axis=1), 1.0, atol=1e-5)
+
+
+def test_synthetic_parity_sample(models, oracle_weights):
+    """The benchmark's synthetic gaussian reads: calls identical and probabilities within 1e-3 of
+    the oracle on a sample the oracle finishes in seconds."""
+    reads = synthetic_signals(64, seed=0, length=1024)
+    for name in ('EXP-NBD103_read_starts', 'SQK-RBK004_read_starts'):
+        model = models[name]
+        ocalls, oprobs = orc.call_batch(oracle_weights[name], reads, 'start', 512, 0.5)
+        for eng in engines(model):
+            model.set_engine(eng)
+            calls, probs = model.call_batch(reads, 'start', 512, 0.5)
+            assert ['none' if c == 0 else str(c) for c in calls] == ocalls
+            assert np.abs(probs - np.array(oprobs, dtype=float)).max() <= TOL
+
+
+def test_errors_are_loud(models):
+    from deepbinner_b200 import _native
+    from deepbinner_b200.model import B200Model
+    model = models['EXP-NBD103_read_starts']
+    with pytest.raises(_native.NativeError):
+        model.call_batch([np.zeros(10, np.int16)], 'start', 6143, 0.5)
+    with pytest.raises(_native.NativeError):
+        B200Model(blob=b'DBNWGT1\x00' + b'\x00' * 100)
+    with pytest.raises(ValueError):
+        model.predict(np.zeros((2, 1000, 1)))
+    assert model.kernel_launches > 0
