@@ -14,10 +14,15 @@ int fail(int code, const char* fmt, ...);
 // Returns nullptr when the engine cannot be set up (the caller then stays on the fp32 CUDA engine).
 TcEngine* tc_create(const Blob& blob, int sm_count);
 void tc_destroy(TcEngine* e);
-// d_x: [n][1024] normalised fp32 windows -> d_probs [n][n_classes]
-int tc_predict(TcEngine* e, const float* d_x, int64_t n, float* d_probs, cudaStream_t st);
+// d_x (float32) or d_xd (float64): [n][1024] normalised windows -> d_probs [n][n_classes]
+int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, float* d_probs,
+               cudaStream_t st);
 // fused call_batch front end: window w = step*n_reads + read -> d_step_probs [steps][n_reads][nc]
 int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offsets, int n_reads,
                     int side, int steps, float* d_step_probs, cudaStream_t st);
+
+int tc_num_jobs(const TcEngine* e);
+// Debug: run windows d_x[0..1] through jobs 0..job and dump both activation regions.
+int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, cudaStream_t st);
 
 }  // namespace dbn

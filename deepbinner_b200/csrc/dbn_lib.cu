@@ -187,8 +187,9 @@ static int launch_predict(db_model* m, const void* d_x, bool is_f64, int64_t n, 
                           cudaStream_t st) {
     if (n <= 0) return 0;
     if (n > 0x7fffffff) return fail(DBN_EINVAL, "too many windows in one launch");
-    if (m->engine == DBN_ENGINE_TCGEN05 && !is_f64) {
-        int rc = tc_predict(m->tc, static_cast<const float*>(d_x), n, d_probs, st);
+    if (m->engine == DBN_ENGINE_TCGEN05) {
+        int rc = tc_predict(m->tc, is_f64 ? nullptr : static_cast<const float*>(d_x),
+                            is_f64 ? static_cast<const double*>(d_x) : nullptr, n, d_probs, st);
         if (rc) return rc;
         m->launches += 1;
         return 0;
@@ -495,6 +496,27 @@ int db_call_batch_device(db_model* m, const int16_t* d_samples, const int64_t* d
     }
     return launch_call_batch(m, d_samples, d_offsets, n_reads, side, steps, score_diff, d_step,
                              d_probs, d_calls, static_cast<cudaStream_t>(stream));
+}
+
+int db_tc_num_jobs(const db_model* m) { return (m && m->tc) ? tc_num_jobs(m->tc) : 0; }
+
+int db_tc_debug_dump(db_model* m, const float* x, int job, unsigned char* out) {
+    if (!m || !m->tc) return fail(DBN_EINVAL, "tcgen05 engine not available");
+    if (!x || !out) return fail(DBN_EINVAL, "NULL buffer");
+    DBN_CUDA(cudaSetDevice(m->device));
+    const size_t dump = 2 * 98688;
+    int rc = grow(&m->d_in[0], &m->d_in_bytes[0], 2 * 1024 * sizeof(float));
+    if (rc) return rc;
+    rc = grow(&m->d_out[0], &m->d_out_bytes[0], dump);
+    if (rc) return rc;
+    cudaStream_t st = m->streams[0];
+    DBN_CUDA(cudaMemcpyAsync(m->d_in[0], x, 2 * 1024 * sizeof(float), cudaMemcpyHostToDevice, st));
+    rc = tc_debug_dump(m->tc, static_cast<const float*>(m->d_in[0]), job,
+                       reinterpret_cast<unsigned char*>(m->d_out[0]), st);
+    if (rc) return rc;
+    DBN_CUDA(cudaMemcpyAsync(out, m->d_out[0], dump, cudaMemcpyDeviceToHost, st));
+    DBN_CUDA(cudaStreamSynchronize(st));
+    return DBN_OK;
 }
 
 float db_last_gpu_ms(const db_model* m) { return m ? m->last_ms : 0.f; }

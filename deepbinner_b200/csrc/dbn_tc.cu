@@ -1,16 +1,843 @@
-// tcgen05 / TMEM tensor-core engine (placeholder until the kernel lands: reports "unavailable" so
-// the library runs on the fp32 CUDA-core engine).
+// tcgen05 / TMEM tensor-core engine for the Deepbinner network (reference
+// network_architecture.py:18-95; executed by model.predict at classify.py:361).
+//
+// One CTA processes TWO windows.  All activations stay in shared memory as split-bf16 pairs
+// (hi = bf16(x), lo = bf16(x - hi)); every Conv1D from conv1d_2 to conv1d_20 is a sequence of
+// tcgen05.mma (kind::f16, M=128 positions x N=Cout x K=16) instructions that accumulate in fp32 in
+// tensor memory, issued by one thread.  A k=3 'same' convolution is three accumulating MMAs per
+// 16-channel block over the SAME shared-memory tile: activations are stored [C/8][L+2][8] (one
+// 16-byte row per position and channel-group, zero halo rows), which is the canonical K-major
+// no-swizzle UMMA layout, so a tap shift is a +16 B start-address offset in the descriptor - no
+// im2col is ever materialised.  Precision: three MMA terms per block (A_hi*W_hi + A_lo*W_hi +
+// A_hi*W_lo) give ~16 mantissa bits on both operands, which SURVEY Appendix C shows is needed for
+// the 1e-3 probability bar (single bf16 fails, fp16 overflows).
+//
+// A whole layer's output for one window (up to 4 tiles x 48 fp32 columns) lives in TMEM, so the
+// epilogue (bias, ReLU, [MaxPool2], [BatchNorm affine], hi/lo split) can overwrite the layer's
+// input in place once its MMAs have completed; the two windows of a CTA alternate so that the
+// tensor pipe works on one while the 4 epilogue warps drain the other.
+//
+// Warp roles: warps 0-3 = epilogue / CUDA-core stages (conv1d_1, average pool, softmax head),
+// warp 4 = TMEM allocator, weight loader (cp.async.bulk + mbarrier) and MMA issuer.
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/deepbinner_b200.h"
 #include "dbn_engine.h"
+#include "dbn_weights.h"
 
 namespace dbn {
 
-TcEngine* tc_create(const Blob&, int) { return nullptr; }
-void tc_destroy(TcEngine*) {}
-int tc_predict(TcEngine*, const float*, int64_t, float*, cudaStream_t) {
-    return fail(-1, "tcgen05 engine not built");
+// ---------------------------------------------------------------------------------------------
+// geometry
+// ---------------------------------------------------------------------------------------------
+constexpr int kTcThreads = 160;
+constexpr int kEpiThreads = 128;
+constexpr int kActBytes = 98688;           // 2 x [6][514][8] bf16
+constexpr int kWbufBytes = 27648;          // hi+lo bf16 of a 48->48 k=3 layer
+constexpr int kSmemAct0 = 0;
+constexpr int kSmemAct1 = kActBytes;
+constexpr int kSmemWbuf = 2 * kActBytes;
+constexpr int kSmemBar = kSmemWbuf + kWbufBytes;   // mbarriers, tmem pointer, reduction scratch
+constexpr int kTcSmemBytes = kSmemBar + 256;
+constexpr int kTmemCols = 512;
+constexpr int kTmemWindowCols = 256;
+constexpr int kTmemTileCols = 64;
+constexpr int kYOff = 72576;               // parity-split concat buffer (top of the ACT region)
+constexpr int kYArray = 6528;              // 24 cg x 17 rows x 16 B
+static_assert(kYOff + 4 * kYArray == kActBytes, "Y buffer placement");
+
+enum EpiMode { EPI_NORMAL = 0, EPI_PARITY = 1, EPI_HEAD = 2 };
+
+struct TcJob {
+    int n;            // MMA N (Cout padded to a multiple of 16)
+    int cout;         // real Cout
+    int ntiles;       // M tiles of 128 positions
+    int L;            // valid positions
+    int lp;           // rows per channel-group of the input tensor
+    int ntaps;
+    int tap_off[3];   // byte offset (from the window's ACT base) of row 0 of each tap, hi array
+    int lo_delta;     // bytes from hi array to lo array of the input
+    int ncb;          // 16-channel K blocks per tap handled by this job
+    int cb0;          // first K block (conv1d_17 is split in 4 jobs)
+    int w_goff;       // byte offset of this job's packed weights in global memory
+    int w_bytes;
+    int first, last;  // first: zero the accumulators; last: run the epilogue
+    // epilogue
+    int mode, pool, bias_off, bn_off;  // float offsets into params (bn_off < 0: none)
+    int out_off, out_lp, out_lo_delta, out_cg_base, out_ncg, out_L;
+    int avgpool_after, zero_y;
+};
+
+struct TcParams {
+    const TcJob* jobs;
+    int njobs;
+    const unsigned char* w;   // packed bf16 weights
+    const float* prm;         // biases + folded BN + conv1 weights
+    int conv1_w, conv1_b, bn1_s, bn1_h;   // float offsets
+    int n_classes;
+    int dbg_job;              // >= 0: stop after this job's epilogue and dump ACT of both windows
+    unsigned char* dbg_out;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
 }
-int tc_call_windows(TcEngine*, const int16_t*, const int64_t*, int, int, int, float*, cudaStream_t) {
-    return fail(-1, "tcgen05 engine not built");
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a protocol bug must become a trap (reported as a CUDA error), never a hang.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
+        if (spin > (1u << 24)) {
+            printf("dbn_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
+                   blockIdx.x, threadIdx.x, bar, parity);
+            __trap();
+        }
+    }
+}
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+        "l"(src), "r"(bytes), "r"(bar)
+        : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() {
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void fence_barrier_init() {
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_before() {
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tc_fence_after() {
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem),
+                 "r"(ncols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
+                 : "memory");
+}
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
+                 : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.
+__device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                       uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
+          "=r"(r[15])
+        : "r"(taddr)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() {
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void epi_bar_sync() {   // the 128 epilogue threads only
+    asm volatile("bar.sync 1, 128;" ::: "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+    asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
+                 "r"(v.w)
+                 : "memory");
+}
+__device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
+    uint4 v;
+    asm volatile("ld.shared.v4.b32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w)
+                 : "r"(addr));
+    return v;
+}
+
+// K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): core matrices
+// of 8 rows x 16 bytes; LBO = byte distance between the two 8-element K chunks of one MMA,
+// SBO = byte distance between consecutive 8-row groups.  version = 1 (Blackwell).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
+    return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) |
+           (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
+           (static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A/B, both K-major.
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+// split-bf16 helpers ----------------------------------------------------------------------------
+__device__ __forceinline__ void split8(const float (&v)[8], uint4* hi, uint4* lo) {
+    uint32_t h[4], l[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]);
+        const __nv_bfloat16 h1 = __float2bfloat16_rn(v[2 * i + 1]);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
+        h[i] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+               (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+        l[i] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+               (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    }
+    *hi = make_uint4(h[0], h[1], h[2], h[3]);
+    *lo = make_uint4(l[0], l[1], l[2], l[3]);
+}
+__device__ __forceinline__ void unpack8(uint4 hi, uint4 lo, float (&v)[8]) {
+    const uint32_t h[4] = {hi.x, hi.y, hi.z, hi.w};
+    const uint32_t l[4] = {lo.x, lo.y, lo.z, lo.w};
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        v[2 * i] = __uint_as_float(h[i] << 16) + __uint_as_float(l[i] << 16);
+        v[2 * i + 1] = __uint_as_float(h[i] & 0xFFFF0000u) + __uint_as_float(l[i] & 0xFFFF0000u);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// CUDA-core stages (epilogue warps)
+// ---------------------------------------------------------------------------------------------
+
+// Input of one window: either normalised fp32 values (predict seam) or an int16 scan region that
+// is z-scored on the fly (fused call_batch; classify.py:342-357, trim_signal.py:61-69).
+struct WindowInput {
+    const float* x;          // predict mode, float32 windows (nullptr otherwise)
+    const double* xd;        // predict mode, float64 windows (cast to float32 as Keras does)
+    const int16_t* region;   // call mode
+    WindowGeom g;
+    double mean, stdev;
+    __device__ __forceinline__ float at(int i) const {
+        if (x) return i < kInputSize ? __ldg(x + i) : 0.f;
+        if (xd) return i < kInputSize ? static_cast<float>(__ldg(xd + i)) : 0.f;
+        const int k = i - g.dst;
+        if (i >= kInputSize || k < 0 || k >= g.n) return 0.f;
+        const double d = static_cast<double>(region[g.a + k]) - mean;
+        return static_cast<float>(stdev > 0.0 ? d / stdev : d);
+    }
+};
+
+// conv1d_1 (1 -> 48, k=3, stride 2, pad right) + ReLU + BatchNorm_1 -> T1 [6][514][8] hi/lo.
+__device__ void conv1_stage(const TcParams& P, const WindowInput& in, uint32_t act, int tid) {
+    const float* w = P.prm + P.conv1_w;   // Keras layout [3][1][48]
+    const float* b = P.prm + P.conv1_b;
+    const float* sc = P.prm + P.bn1_s;
+    const float* sh = P.prm + P.bn1_h;
+    for (int j = 0; j < 4; ++j) {
+        const int p = tid + 128 * j;
+        const float x0 = in.at(2 * p), x1 = in.at(2 * p + 1), x2 = in.at(2 * p + 2);
+#pragma unroll
+        for (int cg = 0; cg < 6; ++cg) {
+            float v[8];
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+                const int c = cg * 8 + e;
+                float a = __ldg(b + c);
+                a = fmaf(__ldg(w + c), x0, a);
+                a = fmaf(__ldg(w + 48 + c), x1, a);
+                a = fmaf(__ldg(w + 96 + c), x2, a);
+                v[e] = fmaf(__ldg(sc + c), fmaxf(a, 0.f), __ldg(sh + c));
+            }
+            uint4 hi, lo;
+            split8(v, &hi, &lo);
+            const uint32_t a0 = act + (cg * 514 + p + 1) * 16;
+            st_shared_v4(a0, hi);
+            st_shared_v4(a0 + 49344, lo);
+        }
+    }
+    if (tid < 24) {   // zero halo rows 0 and 513 of every channel-group, hi and lo
+        const int cg = tid % 6, which = tid / 6;
+        const uint32_t a0 = act + (which & 1 ? 49344 : 0) + (cg * 514 + (which & 2 ? 513 : 0)) * 16;
+        st_shared_v4(a0, make_uint4(0, 0, 0, 0));
+    }
+}
+
+// AveragePooling1D(3, stride 1, 'same') with TF's in-range divisor (Appendix B.3): X -> P, both
+// [6][66][8] hi/lo (X at ACT+0, P at ACT+12672).
+__device__ void avgpool_stage(uint32_t act, int tid) {
+    const int p = tid & 63;
+    const float inv = (p == 0 || p == 63) ? 0.5f : (1.0f / 3.0f);
+    for (int cg = (tid >> 6) * 3; cg < (tid >> 6) * 3 + 3; ++cg) {
+        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+#pragma unroll
+        for (int t = 0; t < 3; ++t) {
+            const uint32_t a0 = act + (cg * 66 + p + t) * 16;
+            float v[8];
+            unpack8(ld_shared_v4(a0), ld_shared_v4(a0 + 6336), v);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] += v[e];
+        }
+        if (inv == 0.5f) {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] = s[e] / 2.0f;
+        } else {
+#pragma unroll
+            for (int e = 0; e < 8; ++e) s[e] = s[e] / 3.0f;
+        }
+        uint4 hi, lo;
+        split8(s, &hi, &lo);
+        const uint32_t o = act + 12672 + (cg * 66 + p + 1) * 16;
+        st_shared_v4(o, hi);
+        st_shared_v4(o + 6336, lo);
+    }
+    if (tid < 24) {
+        const int cg = tid % 6, which = tid / 6;
+        const uint32_t a0 = act + 12672 + (which & 1 ? 6336 : 0) + (cg * 66 + (which & 2 ? 65 : 0)) * 16;
+        st_shared_v4(a0, make_uint4(0, 0, 0, 0));
+    }
+}
+
+// Epilogue of one job for one window: TMEM accumulators -> bias, ReLU, [pool], [BN], split -> smem.
+__device__ void epilogue(const TcParams& P, const TcJob& J, uint32_t act, uint32_t tmem_win, int tid,
+                         float* probs_out) {
+    const int warp = tid >> 5;
+    const float* bias = P.prm + J.bias_off;
+    const float* bns = J.bn_off >= 0 ? P.prm + J.bn_off : nullptr;
+    const float* bnh = J.bn_off >= 0 ? P.prm + J.bn_off + J.cout : nullptr;
+    const int out_L = J.out_L;
+
+    if (J.mode == EPI_NORMAL) {
+        if (tid < 4 * J.out_ncg) {   // zero halo rows of the output tensor
+            const int cg = tid % J.out_ncg, which = tid / J.out_ncg;
+            const uint32_t a0 = act + J.out_off + (which & 1 ? J.out_lo_delta : 0) +
+                                (cg * J.out_lp + (which & 2 ? out_L + 1 : 0)) * 16;
+            st_shared_v4(a0, make_uint4(0, 0, 0, 0));
+        }
+    } else if (J.mode == EPI_PARITY && J.zero_y) {
+        if (tid < 96) {              // zero row 16 of every channel-group of Ye/Yo, hi and lo
+            const int cg = tid % 24, arr = tid / 24;
+            st_shared_v4(act + kYOff + arr * kYArray + (cg * 17 + 16) * 16, make_uint4(0, 0, 0, 0));
+        }
+    }
+
+    for (int tile = 0; tile < J.ntiles; ++tile) {
+        const int p = tile * 128 + tid;                     // position of this thread's row
+        const uint32_t taddr = tmem_win + tile * kTmemTileCols + (static_cast<uint32_t>(warp * 32) << 16);
+        float head_logit[16];
+        for (int chunk = 0; chunk < J.n / 16; ++chunk) {
+            uint32_t r[16];
+            tmem_ld16(taddr + chunk * 16, r);
+            tmem_wait_ld();
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                const int c0 = chunk * 16 + half * 8;
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const int c = c0 + e;
+                    const float b = c < J.cout ? __ldg(bias + c) : 0.f;
+                    v[e] = fmaxf(__uint_as_float(r[half * 8 + e]) + b, 0.f);
+                }
+                if (J.mode == EPI_HEAD) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) head_logit[half * 8 + e] = v[e];
+                    continue;
+                }
+                if (J.pool) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
+                }
+                if (bns) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = fmaf(__ldg(bns + c0 + e), v[e], __ldg(bnh + c0 + e));
+                }
+                uint4 hi, lo;
+                split8(v, &hi, &lo);
+                const int q = J.pool ? p >> 1 : p;          // output position
+                const bool writer = (p < J.L) && (!J.pool || (p & 1) == 0);
+                if (writer) {
+                    const int cg = J.out_cg_base + (c0 >> 3);
+                    if (J.mode == EPI_NORMAL) {
+                        const uint32_t o = act + J.out_off + (cg * J.out_lp + q + 1) * 16;
+                        st_shared_v4(o, hi);
+                        st_shared_v4(o + J.out_lo_delta, lo);
+                    } else {   // EPI_PARITY: even/odd pooled positions in separate arrays
+                        const uint32_t o = act + kYOff + (q & 1) * (2 * kYArray) + (cg * 17 + (q >> 1)) * 16;
+                        st_shared_v4(o, hi);
+                        st_shared_v4(o + kYArray, lo);
+                    }
+                }
+            }
+        }
+        if (J.mode == EPI_HEAD && warp == 0) {
+            // GlobalAveragePooling1D over the 8 positions (lanes 0..7), then softmax
+            // (network_architecture.py:90-91)
+            float logit[16];
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                float s = head_logit[c];
+                s += __shfl_xor_sync(0xffffffffu, s, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4);
+                logit[c] = s / 8.0f;
+            }
+            if (tid == 0 && probs_out) {
+                float m = logit[0];
+                for (int c = 1; c < P.n_classes; ++c) m = fmaxf(m, logit[c]);
+                float e[16], den = 0.f;
+                for (int c = 0; c < P.n_classes; ++c) {
+                    e[c] = expf(logit[c] - m);
+                    den += e[c];
+                }
+                for (int c = 0; c < P.n_classes; ++c) probs_out[c] = e[c] / den;
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+// the kernel
+// ---------------------------------------------------------------------------------------------
+template <bool kCallMode>
+__global__ void __launch_bounds__(kTcThreads, 1)
+    k_tc_forward(TcParams P, const float* __restrict__ x, const double* __restrict__ xd,
+                 const int16_t* __restrict__ samples,
+                 const int64_t* __restrict__ offsets, int n_reads, int side, int n_windows,
+                 float* __restrict__ probs) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t wbuf = sbase + kSmemWbuf;
+    const uint32_t bar_wfull = sbase + kSmemBar + 0;
+    const uint32_t bar_wfree = sbase + kSmemBar + 8;
+    const uint32_t bar_mma[2] = {sbase + kSmemBar + 16, sbase + kSmemBar + 24};
+    const uint32_t bar_epi[2] = {sbase + kSmemBar + 32, sbase + kSmemBar + 40};
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 64);
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5;
+
+    if (tid == 0) {
+        mbar_init(bar_wfull, 1);
+        mbar_init(bar_wfree, 1);
+        mbar_init(bar_mma[0], 1);
+        mbar_init(bar_mma[1], 1);
+        mbar_init(bar_epi[0], kEpiThreads);
+        mbar_init(bar_epi[1], kEpiThreads);
+        fence_barrier_init();
+    }
+    if (warp == 4) tmem_alloc(sbase + kSmemBar + 64, kTmemCols);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    const int njobs = (P.dbg_job >= 0 && P.dbg_job < P.njobs) ? P.dbg_job + 1 : P.njobs;
+
+    if (warp < 4) {
+        // ================= epilogue / CUDA-core warps =================
+        int win[2];
+        bool valid[2];
+        for (int w = 0; w < 2; ++w) {
+            const int idx = 2 * blockIdx.x + w;
+            valid[w] = idx < n_windows;
+            win[w] = valid[w] ? idx : n_windows - 1;
+        }
+        for (int w = 0; w < 2; ++w) {
+            WindowInput in{};
+            if (kCallMode) {
+                const int step = win[w] / n_reads, read = win[w] % n_reads;
+                const int64_t off = offsets[read];
+                in.region = samples + off;
+                in.g = window_geometry(static_cast<int>(offsets[read + 1] - off), step, side);
+                // exact integer sums over the slice, reduced over the 128 threads
+                long long s1 = 0, s2 = 0;
+                for (int i = tid; i < in.g.n; i += kEpiThreads) {
+                    const long long v = in.region[in.g.a + i];
+                    s1 += v;
+                    s2 += v * v;
+                }
+                for (int o = 16; o > 0; o >>= 1) {
+                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
+                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
+                }
+                // cross-warp: through the scratch slots behind the barriers
+                long long* red = reinterpret_cast<long long*>(smem + kSmemBar + 128) + w * 8;
+                if ((tid & 31) == 0) { red[warp] = s1; red[4 + warp] = s2; }
+                epi_bar_sync();
+                s1 = red[0] + red[1] + red[2] + red[3];
+                s2 = red[4] + red[5] + red[6] + red[7];
+                in.mean = 0.0; in.stdev = 0.0;
+                if (in.g.n > 0) zscore_params(s1, s2, in.g.n, &in.mean, &in.stdev);
+            } else if (x) {
+                in.x = x + static_cast<size_t>(win[w]) * kInputSize;
+            } else {
+                in.xd = xd + static_cast<size_t>(win[w]) * kInputSize;
+            }
+            conv1_stage(P, in, sbase + (w ? kSmemAct1 : kSmemAct0), tid);
+            fence_proxy_async();
+            mbar_arrive(bar_epi[w]);
+        }
+        uint32_t mma_phase[2] = {0, 0};
+        for (int j = 0; j < njobs; ++j) {
+            const TcJob J = P.jobs[j];
+            if (!J.last) continue;
+            for (int w = 0; w < 2; ++w) {
+                const uint32_t act = sbase + (w ? kSmemAct1 : kSmemAct0);
+                mbar_wait(bar_mma[w], mma_phase[w]);
+                mma_phase[w] ^= 1;
+                tc_fence_after();
+                float* pout = (J.mode == EPI_HEAD && valid[w])
+                                  ? probs + static_cast<size_t>(win[w]) * P.n_classes : nullptr;
+                epilogue(P, J, act, tmem_base + w * kTmemWindowCols, tid, pout);
+                if (J.avgpool_after) {
+                    epi_bar_sync();
+                    avgpool_stage(act, tid);
+                }
+                fence_proxy_async();
+                tc_fence_before();
+                mbar_arrive(bar_epi[w]);
+            }
+        }
+        if (P.dbg_job >= 0) {   // debug: dump both ACT regions after the last processed job
+            epi_bar_sync();
+            if (blockIdx.x == 0)
+                for (int i = tid; i < 2 * kActBytes / 16; i += kEpiThreads)
+                    reinterpret_cast<uint4*>(P.dbg_out)[i] = reinterpret_cast<const uint4*>(smem)[i];
+        }
+    } else if (tid == 128) {
+        // ================= weight loader + MMA issuer (one thread) =================
+        uint32_t wfull_phase = 0, wfree_phase = 0, epi_phase[2] = {0, 0};
+        for (int j = 0; j < njobs; ++j) {
+            const TcJob J = P.jobs[j];
+            if (j > 0) {   // weight buffer is free once every MMA of the previous job has completed
+                mbar_wait(bar_wfree, wfree_phase);
+                wfree_phase ^= 1;
+            }
+            mbar_expect_tx(bar_wfull, J.w_bytes);
+            bulk_g2s(wbuf, P.w + J.w_goff, J.w_bytes, bar_wfull);
+            mbar_wait(bar_wfull, wfull_phase);
+            wfull_phase ^= 1;
+            const uint32_t idesc = make_idesc(128, J.n);
+            const uint32_t blk_bytes = 2u * J.n * 16u;           // one K=16 block of B
+            const int nkb = J.ntaps * J.ncb;                     // K blocks per term in this job
+            for (int w = 0; w < 2; ++w) {
+                if (J.first) {   // input written and previous accumulators drained
+                    mbar_wait(bar_epi[w], epi_phase[w]);
+                    epi_phase[w] ^= 1;
+                }
+                tc_fence_after();
+                const uint32_t act = sbase + (w ? kSmemAct1 : kSmemAct0);
+                for (int tile = 0; tile < J.ntiles; ++tile) {
+                    const uint32_t d = tmem_base + w * kTmemWindowCols + tile * kTmemTileCols;
+                    uint32_t acc = J.first ? 0u : 1u;
+                    for (int term = 0; term < 3; ++term) {
+                        const uint32_t a_lo = term == 1 ? J.lo_delta : 0;
+                        const uint32_t b_lo = term == 2 ? nkb * blk_bytes : 0;
+                        for (int t = 0; t < J.ntaps; ++t) {
+                            for (int cb = 0; cb < J.ncb; ++cb) {
+                                const uint32_t a = act + J.tap_off[t] + a_lo +
+                                                   (2 * (J.cb0 + cb) * J.lp + tile * 128) * 16;
+                                const uint32_t b = wbuf + b_lo + (t * J.ncb + cb) * blk_bytes;
+                                tc_mma(d, make_desc(a, J.lp * 16, 128), make_desc(b, J.n * 16, 128),
+                                       idesc, acc);
+                                acc = 1u;
+                            }
+                        }
+                    }
+                }
+                if (J.last) tc_commit(bar_mma[w]);
+            }
+            tc_commit(bar_wfree);
+        }
+        // drain: the last wfree commit covers every MMA issued by this thread
+        mbar_wait(bar_wfree, wfree_phase);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+struct TcEngine {
+    TcJob* d_jobs = nullptr;
+    unsigned char* d_w = nullptr;
+    float* d_prm = nullptr;
+    TcParams params{};
+    int njobs = 0;
+};
+
+static uint16_t bf16_rn(float f) {
+    uint32_t u;
+    std::memcpy(&u, &f, 4);
+    if ((u & 0x7F800000u) == 0x7F800000u) return static_cast<uint16_t>(u >> 16);   // inf / nan
+    u += 0x7FFFu + ((u >> 16) & 1u);
+    return static_cast<uint16_t>(u >> 16);
+}
+static float bf16_to_float(uint16_t h) {
+    uint32_t u = static_cast<uint32_t>(h) << 16;
+    float f;
+    std::memcpy(&f, &u, 4);
+    return f;
+}
+
+struct JobBuilder {
+    const Blob& blob;
+    std::vector<TcJob> jobs;
+    std::vector<unsigned char> w;
+    std::vector<float> prm;
+    int bias_off[21];
+    int bn_off[8];
+
+    explicit JobBuilder(const Blob& b) : blob(b) {
+        for (int i = 1; i <= 20; ++i) {
+            const BlobTensor* t = blob.find("conv1d_" + std::to_string(i) + "/bias");
+            while (prm.size() % 4) prm.push_back(0.f);
+            bias_off[i] = static_cast<int>(prm.size());
+            prm.insert(prm.end(), t->data, t->data + t->count);
+            for (int k = 0; k < 16; ++k) prm.push_back(0.f);   // padding for N-padded reads
+        }
+        for (int i = 1; i <= 7; ++i) {
+            std::vector<float> sc, sh;
+            fold_bn(blob, i, &sc, &sh);
+            while (prm.size() % 4) prm.push_back(0.f);
+            bn_off[i] = static_cast<int>(prm.size());
+            prm.insert(prm.end(), sc.begin(), sc.end());   // scale[C] then shift[C]
+            prm.insert(prm.end(), sh.begin(), sh.end());
+        }
+    }
+
+    // pack W[tap][cin][cout] -> [hi | lo][tap][cb in job][2 chunks][n rows][8] bf16
+    void pack_weights(int layer, int n, int cb0, int ncb, TcJob* J) {
+        const ConvSpec& s = kConvSpecs[layer];
+        const int cout = s.cout ? s.cout : blob.n_classes;
+        const float* k = blob.find("conv1d_" + std::to_string(layer) + "/kernel")->data;
+        const int nkb = s.k * ncb;
+        const size_t blk = static_cast<size_t>(2) * n * 8;   // bf16 elements per K block
+        while (w.size() % 128) w.push_back(0);
+        J->w_goff = static_cast<int>(w.size());
+        J->w_bytes = static_cast<int>(2 * nkb * blk * 2);
+        std::vector<uint16_t> buf(2 * nkb * blk, 0);
+        for (int t = 0; t < s.k; ++t)
+            for (int cb = 0; cb < ncb; ++cb)
+                for (int j = 0; j < 2; ++j)
+                    for (int row = 0; row < n; ++row)
+                        for (int e = 0; e < 8; ++e) {
+                            const int cin = (cb0 + cb) * 16 + j * 8 + e;
+                            float v = 0.f;
+                            if (row < cout && cin < s.cin) v = k[(t * s.cin + cin) * cout + row];
+                            const uint16_t hi = bf16_rn(v);
+                            const uint16_t lo = bf16_rn(v - bf16_to_float(hi));
+                            const size_t idx = (static_cast<size_t>(t * ncb + cb) * 2 + j) * n * 8 + row * 8 + e;
+                            buf[idx] = hi;
+                            buf[nkb * blk + idx] = lo;
+                        }
+        const unsigned char* p = reinterpret_cast<const unsigned char*>(buf.data());
+        w.insert(w.end(), p, p + buf.size() * 2);
+    }
+
+    // generic conv job; in_* describe the input tensor, out_* the output tensor
+    TcJob& add(int layer, int L, int in_off, int in_lp, int in_lo_delta, int mode, int pool, int bn,
+               int out_off, int out_cg_base) {
+        const ConvSpec& s = kConvSpecs[layer];
+        const int cout = s.cout ? s.cout : blob.n_classes;
+        TcJob J{};
+        J.n = (cout + 15) / 16 * 16;
+        J.cout = cout;
+        J.ntiles = (L + 127) / 128;
+        J.L = L;
+        J.lp = in_lp;
+        J.ntaps = s.k;
+        for (int t = 0; t < 3; ++t) J.tap_off[t] = in_off + (s.k == 3 ? t : 1) * 16;
+        J.lo_delta = in_lo_delta;
+        J.ncb = s.cin / 16;
+        J.cb0 = 0;
+        J.first = J.last = 1;
+        J.mode = mode;
+        J.pool = pool;
+        J.bias_off = bias_off[layer];
+        J.bn_off = bn > 0 ? bn_off[bn] : -1;
+        J.out_L = pool ? L / 2 : L;
+        J.out_off = out_off;
+        J.out_lp = J.out_L + 2;
+        J.out_ncg = cout / 8;
+        J.out_lo_delta = J.out_ncg * J.out_lp * 16;
+        J.out_cg_base = out_cg_base;
+        pack_weights(layer, J.n, 0, J.ncb, &J);
+        jobs.push_back(J);
+        return jobs.back();
+    }
+};
+
+static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
+    if (blob.n_classes > 16) return false;
+    // T1 (BN1 output) is written by conv1_stage: [6][514][8], lo at +49344
+    B->add(2, 512, 0, 514, 49344, EPI_NORMAL, 0, 0, 0, 0);
+    B->add(3, 512, 0, 514, 49344, EPI_NORMAL, 0, 0, 0, 0);
+    B->add(4, 512, 0, 514, 49344, EPI_NORMAL, 1, 2, 0, 0);          // -> [6][258][8], lo +24768
+    B->add(5, 256, 0, 258, 24768, EPI_NORMAL, 0, 0, 0, 0);          // -> [2][258][8], lo +8256
+    B->add(6, 256, 0, 258, 8256, EPI_NORMAL, 0, 0, 0, 0);           // -> [6][258][8]
+    B->add(7, 256, 0, 258, 24768, EPI_NORMAL, 1, 3, 0, 0);          // -> [6][130][8], lo +12480
+    B->add(8, 128, 0, 130, 12480, EPI_NORMAL, 0, 0, 0, 0);
+    B->add(9, 128, 0, 130, 12480, EPI_NORMAL, 1, 4, 0, 0).avgpool_after = 1;   // X [6][66][8], lo +6336
+    // inception block: X @0, P @12672, T12 @25344, T14 @29568, T15 @33792, Y (parity split) @72576
+    B->add(10, 64, 12672, 66, 6336, EPI_PARITY, 1, 5, 0, 0).zero_y = 1;
+    B->add(11, 64, 0, 66, 6336, EPI_PARITY, 1, 5, 0, 6);
+    B->add(12, 64, 0, 66, 6336, EPI_NORMAL, 0, 0, 25344, 0);
+    B->add(13, 64, 25344, 66, 2112, EPI_PARITY, 1, 5, 0, 12);
+    B->add(14, 64, 0, 66, 6336, EPI_NORMAL, 0, 0, 29568, 0);
+    B->add(15, 64, 29568, 66, 2112, EPI_NORMAL, 0, 0, 33792, 0);
+    B->add(16, 64, 33792, 66, 6336, EPI_PARITY, 1, 5, 0, 18);
+    // BN5 parameters are per concatenated channel: offset the folded scale/shift per branch
+    {
+        const int base = B->bn_off[5];
+        (void)base;
+    }
+    // conv1d_17: stride 2 on the parity-split Y (tap0 = Ye[i], tap1 = Yo[i], tap2 = Ye[i+1]),
+    // K = 3 x 192 split in 4 jobs of 3 channel blocks so each weight chunk fits the buffer
+    for (int s = 0; s < 4; ++s) {
+        TcJob J{};
+        J.n = 48; J.cout = 48; J.ntiles = 1; J.L = 16; J.lp = 17; J.ntaps = 3;
+        J.tap_off[0] = kYOff; J.tap_off[1] = kYOff + 2 * kYArray; J.tap_off[2] = kYOff + 16;
+        J.lo_delta = kYArray; J.ncb = 3; J.cb0 = 3 * s;
+        J.first = (s == 0); J.last = (s == 3);
+        J.mode = EPI_NORMAL; J.pool = 0; J.bias_off = B->bias_off[17]; J.bn_off = B->bn_off[6];
+        J.out_L = 16; J.out_off = 0; J.out_lp = 18; J.out_ncg = 6; J.out_lo_delta = 6 * 18 * 16;
+        J.out_cg_base = 0;
+        B->pack_weights(17, 48, 3 * s, 3, &J);
+        B->jobs.push_back(J);
+    }
+    B->add(18, 16, 0, 18, 1728, EPI_NORMAL, 0, 0, 0, 0);
+    B->add(19, 16, 0, 18, 1728, EPI_NORMAL, 1, 7, 0, 0);            // -> [6][10][8], lo +960
+    B->add(20, 8, 0, 10, 960, EPI_HEAD, 0, 0, 0, 0);
+
+    // conv1 parameters
+    auto push = [&](const float* p, size_t n) {
+        while (B->prm.size() % 4) B->prm.push_back(0.f);
+        const int off = static_cast<int>(B->prm.size());
+        B->prm.insert(B->prm.end(), p, p + n);
+        return off;
+    };
+    P->conv1_w = push(blob.find("conv1d_1/kernel")->data, 144);
+    P->conv1_b = B->bias_off[1];
+    P->bn1_s = B->bn_off[1];
+    P->bn1_h = B->bn_off[1] + 48;
+    P->n_classes = blob.n_classes;
+    return true;
+}
+
+TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
+    if (getenv("DBN_DISABLE_TC")) return nullptr;
+    JobBuilder B(blob);
+    TcParams P{};
+    if (!build_jobs(blob, &B, &P)) return nullptr;
+    // BN5 covers the 192 concatenated channels: each branch's job reads scale at bn_off + cg_base*8
+    // and shift at bn_off + 192 + cg_base*8 -> handled by giving those jobs cout-relative offsets
+    for (TcJob& J : B.jobs)
+        if (J.mode == EPI_PARITY) {
+            // scale[c] at bn_off + c, shift[c] at bn_off + J.cout + c inside epilogue(); for the
+            // concat we need scale at base + 8*cg_base + c and shift at base + 192 + 8*cg_base + c.
+            // Re-pack a private [scale48 | shift48] pair for the branch.
+            const int base = B.bn_off[5], ch0 = J.out_cg_base * 8;
+            while (B.prm.size() % 4) B.prm.push_back(0.f);
+            const int off = static_cast<int>(B.prm.size());
+            for (int c = 0; c < 48; ++c) B.prm.push_back(B.prm[base + ch0 + c]);
+            for (int c = 0; c < 48; ++c) B.prm.push_back(B.prm[base + 192 + ch0 + c]);
+            J.bn_off = off;
+        }
+    TcEngine* e = new TcEngine();
+    bool ok = cudaMalloc(&e->d_jobs, B.jobs.size() * sizeof(TcJob)) == cudaSuccess &&
+              cudaMalloc(&e->d_w, B.w.size()) == cudaSuccess &&
+              cudaMalloc(&e->d_prm, B.prm.size() * sizeof(float)) == cudaSuccess &&
+              cudaMemcpy(e->d_jobs, B.jobs.data(), B.jobs.size() * sizeof(TcJob), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(e->d_w, B.w.data(), B.w.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMemcpy(e->d_prm, B.prm.data(), B.prm.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaFuncSetAttribute(k_tc_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+              cudaFuncSetAttribute(k_tc_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess;
+    if (!ok) {
+        cudaGetLastError();
+        tc_destroy(e);
+        return nullptr;
+    }
+    e->njobs = static_cast<int>(B.jobs.size());
+    P.jobs = e->d_jobs;
+    P.njobs = e->njobs;
+    P.w = e->d_w;
+    P.prm = e->d_prm;
+    P.dbg_job = -1;
+    P.dbg_out = nullptr;
+    e->params = P;
+    return e;
+}
+
+void tc_destroy(TcEngine* e) {
+    if (!e) return;
+    cudaFree(e->d_jobs);
+    cudaFree(e->d_w);
+    cudaFree(e->d_prm);
+    delete e;
+}
+
+int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, float* d_probs,
+               cudaStream_t st) {
+    const int grid = static_cast<int>((n + 1) / 2);
+    k_tc_forward<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(e->params, d_x, d_xd, nullptr, nullptr,
+                                                               0, 0, static_cast<int>(n), d_probs);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(DBN_ECUDA, "tcgen05 kernel launch failed: %s", cudaGetErrorString(err));
+    return 0;
+}
+
+int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offsets, int n_reads,
+                    int side, int steps, float* d_step_probs, cudaStream_t st) {
+    const int n = n_reads * steps;
+    k_tc_forward<true><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(e->params, nullptr, nullptr, d_samples,
+                                                                      d_offsets, n_reads, side, n,
+                                                                      d_step_probs);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(DBN_ECUDA, "tcgen05 kernel launch failed: %s", cudaGetErrorString(err));
+    return 0;
+}
+
+int tc_num_jobs(const TcEngine* e) { return e ? e->njobs : 0; }
+
+// Debug: run windows d_x[0..1] up to and including job `job`, dump both ACT regions (2*98688 B).
+int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, cudaStream_t st) {
+    TcParams P = e->params;
+    P.dbg_job = job;
+    P.dbg_out = d_out;
+    k_tc_forward<false><<<1, kTcThreads, kTcSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0, 2,
+                                                            nullptr);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(DBN_ECUDA, "tcgen05 debug launch failed: %s", cudaGetErrorString(err));
+    return 0;
 }
 
 }  // namespace dbn

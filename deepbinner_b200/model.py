@@ -163,3 +163,17 @@ def pack_scan_regions(signals, side, scan_size, input_size):
     if samples.size == 0:
         samples = np.zeros(1, dtype=np.int16)
     return np.ascontiguousarray(samples, dtype=np.int16), offsets
+
+
+def tc_debug_dump(model, x2, job):
+    """Diagnostics for tests: run two windows through tcgen05 jobs 0..job and return the raw bytes of
+    both shared-memory activation regions (uint8 [2, 98688])."""
+    x2 = _native.require(np.asarray(x2).reshape(2, model.input_size), np.float32)
+    out = np.zeros((2, 98688), dtype=np.uint8)
+    rc = model._lib.db_tc_debug_dump(model._handle, _native.as_ptr(x2), int(job), _native.as_ptr(out))
+    _native.check(rc, 'db_tc_debug_dump')
+    return out
+
+
+def tc_num_jobs(model):
+    return int(model._lib.db_tc_num_jobs(model._handle))

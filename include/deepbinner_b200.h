@@ -131,6 +131,14 @@ DBN_API int db_call_batch_device(db_model *model, const int16_t *d_samples, cons
 DBN_API float db_last_gpu_ms(const db_model *model);
 DBN_API int64_t db_kernel_launches(const db_model *model);
 
+/*
+ * Diagnostics of the tcgen05 engine (used by tests/test_gpu_tc_layers.py): number of MMA jobs, and a
+ * dump of the two shared-memory activation regions (2 x 98688 bytes, split-bf16 layout documented in
+ * csrc/dbn_tc.cu) after running host windows x[0..1] through jobs 0..job.
+ */
+DBN_API int db_tc_num_jobs(const db_model *model);
+DBN_API int db_tc_debug_dump(db_model *model, const float *x, int job, unsigned char *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -156,10 +156,13 @@ def softmax(x):
     return e / e.sum(axis=-1, keepdims=True)
 
 
-def forward(w, x, return_logits=False):
+def forward(w, x, return_logits=False, taps=None):
     """The network of network_architecture.py:18-95 at inference (GaussianNoise and Dropout are
-    identity).  x: [N, input_size] or [N, input_size, 1]; returns softmax rows [N, n_classes]."""
+    identity).  x: [N, input_size] or [N, input_size, 1]; returns softmax rows [N, n_classes].
+    If `taps` is a dict it receives the intermediate tensors (for per-layer kernel tests)."""
     dtype = w['conv1d_1/kernel'].dtype
+    if taps is None:
+        taps = {}
     x = np.asarray(x, dtype=dtype)
     if x.ndim == 2:
         x = x[:, :, None]
@@ -169,20 +172,33 @@ def forward(w, x, return_logits=False):
 
     x = conv('conv1d_1', x, stride=2)                       # :26
     x = batch_norm(x, w, 'batch_normalization_1')           # :28
+    taps['bn1'] = x
     x = conv('conv1d_2', x)                                 # :32-34
+    taps['conv2'] = x
     x = conv('conv1d_3', x)
+    taps['conv3'] = x
     x = conv('conv1d_4', x)
     x = max_pool2(x)                                        # :35
     x = batch_norm(x, w, 'batch_normalization_2')           # :37
+    taps['bn2'] = x
     x = conv('conv1d_5', x)                                 # :41 bottleneck (k=1)
+    taps['conv5'] = x
     x = conv('conv1d_6', x)                                 # :44-45
+    taps['conv6'] = x
     x = conv('conv1d_7', x)
     x = max_pool2(x)                                        # :46
     x = batch_norm(x, w, 'batch_normalization_3')           # :48
+    taps['bn3'] = x
     x = conv('conv1d_8', x)                                 # :52-53
+    taps['conv8'] = x
     x = conv('conv1d_9', x)
     x = max_pool2(x)                                        # :54
     x = batch_norm(x, w, 'batch_normalization_4')           # :56
+    taps['bn4'] = x
+    taps['avgpool'] = avg_pool3_same(x)
+    taps['conv12'] = conv('conv1d_12', x)
+    taps['conv14'] = conv('conv1d_14', x)
+    taps['conv15'] = conv('conv1d_15', taps['conv14'])
     x1 = conv('conv1d_10', avg_pool3_same(x))               # :60-61
     x2 = conv('conv1d_11', x)                               # :62
     x3 = conv('conv1d_13', conv('conv1d_12', x))            # :63-64
@@ -190,12 +206,16 @@ def forward(w, x, return_logits=False):
     x = np.concatenate([x1, x2, x3, x4], axis=2)            # :68
     x = max_pool2(x)                                        # :69
     x = batch_norm(x, w, 'batch_normalization_5')           # :71
+    taps['bn5'] = x
     x = conv('conv1d_17', x, stride=2)                      # :75
     x = batch_norm(x, w, 'batch_normalization_6')           # :77
+    taps['bn6'] = x
     x = conv('conv1d_18', x)                                # :81-82
+    taps['conv18'] = x
     x = conv('conv1d_19', x)
     x = max_pool2(x)                                        # :83
     x = batch_norm(x, w, 'batch_normalization_7')           # :85
+    taps['bn7'] = x
     x = conv('conv1d_20', x)                                # :89 (ReLU before the pooling)
     logits = x.mean(axis=1)                                 # :90 GlobalAveragePooling1D
     if return_logits:

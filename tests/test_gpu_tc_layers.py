@@ -1,0 +1,92 @@
+"""Per-layer check of the tcgen05 engine: the split-bf16 activation tensors left in shared memory
+after every MMA job are dumped and compared with the oracle's intermediate tensors."""
+import numpy as np
+import pytest
+
+from conftest import model_path
+from oracle import deepbinner_oracle as orc
+
+pytestmark = pytest.mark.gpu
+
+
+def bf16_to_f32(u16):
+    return (u16.astype(np.uint32) << 16).view(np.float32)
+
+
+def decode(region, off, ncg, lp, length, lo_delta):
+    """[ncg][lp][8] hi/lo arrays -> float [length, ncg*8]; also returns the two halo rows."""
+    def arr(o):
+        a = region[o:o + ncg * lp * 16].view(np.uint16).reshape(ncg, lp, 8)
+        return bf16_to_f32(a)
+    full = arr(off) + arr(off + lo_delta)
+    t = full[:, 1:length + 1, :].transpose(1, 0, 2).reshape(length, ncg * 8)
+    return t, full[:, 0, :], full[:, length + 1, :]
+
+
+def decode_parity(region, cg0, ncg):
+    off, arr_bytes = 72576, 6528
+    def arr(o):
+        return bf16_to_f32(region[o:o + 24 * 17 * 16].view(np.uint16).reshape(24, 17, 8))
+    ye = arr(off) + arr(off + arr_bytes)
+    yo = arr(off + 2 * arr_bytes) + arr(off + 3 * arr_bytes)
+    y = np.zeros((32, ncg * 8), np.float32)
+    y[0::2] = ye[cg0:cg0 + ncg, :16].transpose(1, 0, 2).reshape(16, ncg * 8)
+    y[1::2] = yo[cg0:cg0 + ncg, :16].transpose(1, 0, 2).reshape(16, ncg * 8)
+    return y, ye[:, 16, :], None
+
+
+# job index -> (oracle tap, decoder)
+JOBS = [
+    (0, 'conv2', lambda r: decode(r, 0, 6, 514, 512, 49344)),
+    (1, 'conv3', lambda r: decode(r, 0, 6, 514, 512, 49344)),
+    (2, 'bn2', lambda r: decode(r, 0, 6, 258, 256, 24768)),
+    (3, 'conv5', lambda r: decode(r, 0, 2, 258, 256, 8256)),
+    (4, 'conv6', lambda r: decode(r, 0, 6, 258, 256, 24768)),
+    (5, 'bn3', lambda r: decode(r, 0, 6, 130, 128, 12480)),
+    (6, 'conv8', lambda r: decode(r, 0, 6, 130, 128, 12480)),
+    (7, 'bn4', lambda r: decode(r, 0, 6, 66, 64, 6336)),
+    (7, 'avgpool', lambda r: decode(r, 12672, 6, 66, 64, 6336)),
+    (8, 'bn5:0', lambda r: decode_parity(r, 0, 6)),
+    (9, 'bn5:48', lambda r: decode_parity(r, 6, 6)),
+    (10, 'conv12', lambda r: decode(r, 25344, 2, 66, 64, 2112)),
+    (11, 'bn5:96', lambda r: decode_parity(r, 12, 6)),
+    (12, 'conv14', lambda r: decode(r, 29568, 2, 66, 64, 2112)),
+    (13, 'conv15', lambda r: decode(r, 33792, 6, 66, 64, 6336)),
+    (14, 'bn5:144', lambda r: decode_parity(r, 18, 6)),
+    (18, 'bn6', lambda r: decode(r, 0, 6, 18, 16, 1728)),
+    (19, 'conv18', lambda r: decode(r, 0, 6, 18, 16, 1728)),
+    (20, 'bn7', lambda r: decode(r, 0, 6, 10, 8, 960)),
+]
+
+
+def test_every_job_against_oracle(fixture_reads):
+    from deepbinner_b200.model import B200Model, tc_debug_dump, tc_num_jobs
+    _, sigs, _ = fixture_reads
+    name = 'EXP-NBD103_read_starts'
+    model = B200Model(model_path(name))
+    try:
+        model.set_engine('tcgen05')
+    except Exception:  # noqa: BLE001
+        pytest.skip('tcgen05 engine unavailable')
+    assert tc_num_jobs(model) == 22
+    x = orc.make_windows(sigs[2:4], 1024, 1, 'start').astype(np.float32)
+    taps = {}
+    orc.forward(orc.load_weights(model_path(name)), x, taps=taps)
+    failures = []
+    for job, tap, dec in JOBS:
+        dump = tc_debug_dump(model, x, job)
+        for w in range(2):
+            got, halo_a, halo_b = dec(dump[w])
+            if tap.startswith('bn5:'):
+                c0 = int(tap.split(':')[1])
+                ref = taps['bn5'][w][:, c0:c0 + 48]
+            else:
+                ref = taps[tap][w]
+            scale = np.abs(ref).max() + 1e-30
+            err = np.abs(got - ref).max() / scale
+            halo = max(np.abs(halo_a).max(), np.abs(halo_b).max() if halo_b is not None else 0.0)
+            print('job {:2d} {:8s} window {}: rel err {:.2e} (max |ref| {:.3g}) halo {:.1e}'.format(
+                job, tap, w, err, scale, halo))
+            if not (err < 2e-4 and halo == 0.0):
+                failures.append((job, tap, w, float(err), float(halo)))
+    assert not failures, failures
