@@ -36,23 +36,38 @@ namespace dbn {
 // ---------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------
-constexpr int kTcThreads = 160;
-constexpr int kEpiThreads = 128;
-constexpr int kActBytes = 98688;           // 2 x [6][514][8] bf16
-constexpr int kWbufBytes = 27648;          // hi+lo bf16 of a 48->48 k=3 layer
+constexpr int kEpiWarps = 8;
+constexpr int kEpiThreads = kEpiWarps * 32;     // warps 0-7: epilogue / CUDA-core stages
+constexpr int kMmaWarp = 8;                     // warp 8: TMEM allocator + MMA issuer
+constexpr int kLoadWarp = 9;                    // warp 9: weight loader
+constexpr int kTcThreads = 320;
+constexpr int kActBytes = 98688;                // 2 x [6][514][8] bf16
+constexpr int kWHalf = 13824;                   // bf16 hi (or lo) part of a 48->48 k=3 layer
+constexpr int kWbufBytes = 2 * kWHalf;
+constexpr int kPrmFloats = 1664;                // per-job bias / folded BN, resident in smem
 constexpr int kSmemAct0 = 0;
 constexpr int kSmemAct1 = kActBytes;
 constexpr int kSmemWbuf = 2 * kActBytes;
-constexpr int kSmemBar = kSmemWbuf + kWbufBytes;   // mbarriers, tmem pointer, reduction scratch
+constexpr int kSmemPrm = kSmemWbuf + kWbufBytes;
+constexpr int kSmemBar = kSmemPrm + kPrmFloats * 4;   // mbarriers, tmem pointer, reduction scratch
 constexpr int kTcSmemBytes = kSmemBar + 256;
+static_assert(kTcSmemBytes <= 232448, "shared memory budget");
 constexpr int kTmemCols = 512;
 constexpr int kTmemWindowCols = 256;
 constexpr int kTmemTileCols = 64;
 constexpr int kYOff = 72576;               // parity-split concat buffer (top of the ACT region)
 constexpr int kYArray = 6528;              // 24 cg x 17 rows x 16 B
 static_assert(kYOff + 4 * kYArray == kActBytes, "Y buffer placement");
+constexpr int kMaxJobs = 32;
 
-enum EpiMode { EPI_NORMAL = 0, EPI_PARITY = 1, EPI_HEAD = 2 };
+enum EpiKind {
+    EPI_N48 = 0,          // bias + ReLU
+    EPI_N48_POOL_BN = 1,  // bias + ReLU + MaxPool2 + BN
+    EPI_N48_BN = 2,       // bias + ReLU + BN
+    EPI_N16 = 3,          // 16-channel bottleneck, bias + ReLU
+    EPI_PARITY = 4,       // bias + ReLU + MaxPool2 + BN5 -> even/odd split concat buffer
+    EPI_HEAD = 5          // bias + ReLU + global average pool + softmax
+};
 
 struct TcJob {
     int n;            // MMA N (Cout padded to a multiple of 16)
@@ -65,21 +80,23 @@ struct TcJob {
     int lo_delta;     // bytes from hi array to lo array of the input
     int ncb;          // 16-channel K blocks per tap handled by this job
     int cb0;          // first K block (conv1d_17 is split in 4 jobs)
-    int w_goff;       // byte offset of this job's packed weights in global memory
-    int w_bytes;
+    int w_goff;       // byte offset of this job's packed weights in global memory ([hi | lo])
+    int w_half;       // bytes of the hi part (== bytes of the lo part)
     int first, last;  // first: zero the accumulators; last: run the epilogue
     // epilogue
-    int mode, pool, bias_off, bn_off;  // float offsets into params (bn_off < 0: none)
+    int kind, bias_off, bn_off;  // float offsets into the smem parameter block
     int out_off, out_lp, out_lo_delta, out_cg_base, out_ncg, out_L;
     int avgpool_after, zero_y;
 };
 
+__constant__ TcJob c_jobs[kMaxJobs];
+
 struct TcParams {
-    const TcJob* jobs;
     int njobs;
     const unsigned char* w;   // packed bf16 weights
-    const float* prm;         // biases + folded BN + conv1 weights
-    int conv1_w, conv1_b, bn1_s, bn1_h;   // float offsets
+    const float* prm;         // global copy of the smem parameter block + conv1 parameters
+    int prm_floats;
+    int conv1_w, conv1_b, bn1_s, bn1_h;   // float offsets into prm
     int n_classes;
     int dbg_job;              // >= 0: stop after this job's epilogue and dump ACT of both windows
     unsigned char* dbg_out;
@@ -114,13 +131,8 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must become a trap (reported as a CUDA error), never a hang.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin) {
-        if (spin > (1u << 24)) {
-            printf("dbn_tc: mbarrier wait timed out (block %d thread %d bar %u parity %u)\n",
-                   blockIdx.x, threadIdx.x, bar, parity);
-            __trap();
-        }
-    }
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 26)) __trap();
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile(
@@ -164,20 +176,18 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
-__device__ __forceinline__ void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
-    asm volatile(
-        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15}, [%16];"
-        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
-          "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]),
-          "=r"(r[15])
-        : "r"(taddr)
-        : "memory");
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]),
+                   "=r"(r[7])
+                 : "r"(taddr)
+                 : "memory");
 }
 __device__ __forceinline__ void tmem_wait_ld() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() {   // the 128 epilogue threads only
-    asm volatile("bar.sync 1, 128;" ::: "memory");
+__device__ __forceinline__ void epi_bar_sync() {   // the 256 epilogue threads only
+    asm volatile("bar.sync 1, 256;" ::: "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
@@ -190,14 +200,20 @@ __device__ __forceinline__ uint4 ld_shared_v4(uint32_t addr) {
                  : "r"(addr));
     return v;
 }
+__device__ __forceinline__ float4 ld_shared_f4(uint32_t addr) {
+    float4 v;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                 : "r"(addr));
+    return v;
+}
 
 // K-major, no-swizzle shared-memory matrix descriptor (cute::UMMA::SmemDescriptor): core matrices
 // of 8 rows x 16 bytes; LBO = byte distance between the two 8-element K chunks of one MMA,
-// SBO = byte distance between consecutive 8-row groups.  version = 1 (Blackwell).
-__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo, uint32_t sbo) {
-    return static_cast<uint64_t>((saddr >> 4) & 0x3FFF) |
-           (static_cast<uint64_t>((lbo >> 4) & 0x3FFF) << 16) |
-           (static_cast<uint64_t>((sbo >> 4) & 0x3FFF) << 32) | (1ull << 46);
+// SBO = byte distance between consecutive 8-row groups (always 128 here); version = 1 (Blackwell).
+// `addr16` and `lbo16` are in 16-byte units.
+__device__ __forceinline__ uint64_t make_desc16(uint32_t addr16, uint32_t lbo16) {
+    return (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(lbo16 & 0x3FFF) << 16) |
+           static_cast<uint64_t>(addr16 & 0x3FFF);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A/B, both K-major.
 __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
@@ -205,19 +221,20 @@ __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
            (static_cast<uint32_t>(m >> 4) << 24);
 }
 
-// split-bf16 helpers ----------------------------------------------------------------------------
+// split-bf16 helpers: x = hi + lo with hi = bf16_rn(x), lo = bf16_rn(x - hi) ----------------------
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
+    return r;
+}
 __device__ __forceinline__ void split8(const float (&v)[8], uint4* hi, uint4* lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * i]);
-        const __nv_bfloat16 h1 = __float2bfloat16_rn(v[2 * i + 1]);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * i] - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * i + 1] - __bfloat162float(h1));
-        h[i] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-               (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-        l[i] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-               (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+        h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+        const float h0 = __uint_as_float(h[i] << 16);
+        const float h1 = __uint_as_float(h[i] & 0xFFFF0000u);
+        l[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
     }
     *hi = make_uint4(h[0], h[1], h[2], h[3]);
     *lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -233,11 +250,11 @@ __device__ __forceinline__ void unpack8(uint4 hi, uint4 lo, float (&v)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// CUDA-core stages (epilogue warps)
+// CUDA-core stages (epilogue warps, 256 threads)
 // ---------------------------------------------------------------------------------------------
 
-// Input of one window: either normalised fp32 values (predict seam) or an int16 scan region that
-// is z-scored on the fly (fused call_batch; classify.py:342-357, trim_signal.py:61-69).
+// Input of one window: either normalised values (predict seam) or an int16 scan region that is
+// z-scored on the fly (fused call_batch; classify.py:342-357, trim_signal.py:61-69).
 struct WindowInput {
     const float* x;          // predict mode, float32 windows (nullptr otherwise)
     const double* xd;        // predict mode, float64 windows (cast to float32 as Keras does)
@@ -256,24 +273,44 @@ struct WindowInput {
 
 // conv1d_1 (1 -> 48, k=3, stride 2, pad right) + ReLU + BatchNorm_1 -> T1 [6][514][8] hi/lo.
 __device__ void conv1_stage(const TcParams& P, const WindowInput& in, uint32_t act, int tid) {
-    const float* w = P.prm + P.conv1_w;   // Keras layout [3][1][48]
-    const float* b = P.prm + P.conv1_b;
-    const float* sc = P.prm + P.bn1_s;
-    const float* sh = P.prm + P.bn1_h;
-    for (int j = 0; j < 4; ++j) {
-        const int p = tid + 128 * j;
-        const float x0 = in.at(2 * p), x1 = in.at(2 * p + 1), x2 = in.at(2 * p + 2);
+    const float4* w4 = reinterpret_cast<const float4*>(P.prm + P.conv1_w);   // [3][48]
+    const float4* b4 = reinterpret_cast<const float4*>(P.prm + P.conv1_b);
+    const float4* s4 = reinterpret_cast<const float4*>(P.prm + P.bn1_s);
+    const float4* h4 = reinterpret_cast<const float4*>(P.prm + P.bn1_h);
+    float xs[2][3];
 #pragma unroll
-        for (int cg = 0; cg < 6; ++cg) {
+    for (int j = 0; j < 2; ++j) {
+        const int p = tid + 256 * j;
+        xs[j][0] = in.at(2 * p);
+        xs[j][1] = in.at(2 * p + 1);
+        xs[j][2] = in.at(2 * p + 2);
+    }
+#pragma unroll 1
+    for (int cg = 0; cg < 6; ++cg) {
+        float w0[8], w1[8], w2[8], b[8], sc[8], sh[8];
+#pragma unroll
+        for (int q = 0; q < 2; ++q) {
+            const float4 a0 = __ldg(w4 + cg * 2 + q), a1 = __ldg(w4 + 12 + cg * 2 + q);
+            const float4 a2 = __ldg(w4 + 24 + cg * 2 + q), bb = __ldg(b4 + cg * 2 + q);
+            const float4 ss = __ldg(s4 + cg * 2 + q), hh = __ldg(h4 + cg * 2 + q);
+            w0[4 * q] = a0.x; w0[4 * q + 1] = a0.y; w0[4 * q + 2] = a0.z; w0[4 * q + 3] = a0.w;
+            w1[4 * q] = a1.x; w1[4 * q + 1] = a1.y; w1[4 * q + 2] = a1.z; w1[4 * q + 3] = a1.w;
+            w2[4 * q] = a2.x; w2[4 * q + 1] = a2.y; w2[4 * q + 2] = a2.z; w2[4 * q + 3] = a2.w;
+            b[4 * q] = bb.x; b[4 * q + 1] = bb.y; b[4 * q + 2] = bb.z; b[4 * q + 3] = bb.w;
+            sc[4 * q] = ss.x; sc[4 * q + 1] = ss.y; sc[4 * q + 2] = ss.z; sc[4 * q + 3] = ss.w;
+            sh[4 * q] = hh.x; sh[4 * q + 1] = hh.y; sh[4 * q + 2] = hh.z; sh[4 * q + 3] = hh.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const int p = tid + 256 * j;
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-                const int c = cg * 8 + e;
-                float a = __ldg(b + c);
-                a = fmaf(__ldg(w + c), x0, a);
-                a = fmaf(__ldg(w + 48 + c), x1, a);
-                a = fmaf(__ldg(w + 96 + c), x2, a);
-                v[e] = fmaf(__ldg(sc + c), fmaxf(a, 0.f), __ldg(sh + c));
+                float a = b[e];
+                a = fmaf(w0[e], xs[j][0], a);
+                a = fmaf(w1[e], xs[j][1], a);
+                a = fmaf(w2[e], xs[j][2], a);
+                v[e] = fmaf(sc[e], fmaxf(a, 0.f), sh[e]);
             }
             uint4 hi, lo;
             split8(v, &hi, &lo);
@@ -292,9 +329,8 @@ __device__ void conv1_stage(const TcParams& P, const WindowInput& in, uint32_t a
 // AveragePooling1D(3, stride 1, 'same') with TF's in-range divisor (Appendix B.3): X -> P, both
 // [6][66][8] hi/lo (X at ACT+0, P at ACT+12672).
 __device__ void avgpool_stage(uint32_t act, int tid) {
-    const int p = tid & 63;
-    const float inv = (p == 0 || p == 63) ? 0.5f : (1.0f / 3.0f);
-    for (int cg = (tid >> 6) * 3; cg < (tid >> 6) * 3 + 3; ++cg) {
+    for (int item = tid; item < 6 * 64; item += kEpiThreads) {
+        const int cg = item >> 6, p = item & 63;
         float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 #pragma unroll
         for (int t = 0; t < 3; ++t) {
@@ -304,13 +340,9 @@ __device__ void avgpool_stage(uint32_t act, int tid) {
 #pragma unroll
             for (int e = 0; e < 8; ++e) s[e] += v[e];
         }
-        if (inv == 0.5f) {
+        const float div = (p == 0 || p == 63) ? 2.0f : 3.0f;
 #pragma unroll
-            for (int e = 0; e < 8; ++e) s[e] = s[e] / 2.0f;
-        } else {
-#pragma unroll
-            for (int e = 0; e < 8; ++e) s[e] = s[e] / 3.0f;
-        }
+        for (int e = 0; e < 8; ++e) s[e] = s[e] / div;
         uint4 hi, lo;
         split8(s, &hi, &lo);
         const uint32_t o = act + 12672 + (cg * 66 + p + 1) * 16;
@@ -325,100 +357,122 @@ __device__ void avgpool_stage(uint32_t act, int tid) {
 }
 
 // Epilogue of one job for one window: TMEM accumulators -> bias, ReLU, [pool], [BN], split -> smem.
-__device__ void epilogue(const TcParams& P, const TcJob& J, uint32_t act, uint32_t tmem_win, int tid,
-                         float* probs_out) {
-    const int warp = tid >> 5;
-    const float* bias = P.prm + J.bias_off;
-    const float* bns = J.bn_off >= 0 ? P.prm + J.bn_off : nullptr;
-    const float* bnh = J.bn_off >= 0 ? P.prm + J.bn_off + J.cout : nullptr;
-    const int out_L = J.out_L;
-
-    if (J.mode == EPI_NORMAL) {
-        if (tid < 4 * J.out_ncg) {   // zero halo rows of the output tensor
-            const int cg = tid % J.out_ncg, which = tid / J.out_ncg;
-            const uint32_t a0 = act + J.out_off + (which & 1 ? J.out_lo_delta : 0) +
-                                (cg * J.out_lp + (which & 2 ? out_L + 1 : 0)) * 16;
-            st_shared_v4(a0, make_uint4(0, 0, 0, 0));
+// Warp w handles TMEM lane quadrant (w & 3) and column half (w >> 2): NC columns per warp.
+template <int NC, bool POOL, bool BN, bool PARITY>
+__device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uint32_t prm, uint32_t tmem_win,
+                                               int tid) {
+    const int warp = tid >> 5, lane = tid & 31;
+    const int q = warp & 3, h = warp >> 2;
+    const int row = q * 32 + lane;
+    const int ntiles = J.ntiles, L = J.L;
+    const uint32_t bias_a = prm + (J.bias_off + h * NC) * 4;
+    const uint32_t bn_a = prm + (J.bn_off + h * NC) * 4;
+    const int cg0 = J.out_cg_base + (h * NC) / 8;
+    const uint32_t out_base = act + J.out_off;
+    const int out_lp = J.out_lp, out_lo = J.out_lo_delta;
+    for (int tile = 0; tile < ntiles; ++tile) {
+        const int p = tile * 128 + row;
+        const uint32_t taddr = tmem_win + tile * kTmemTileCols + h * NC + (static_cast<uint32_t>(q * 32) << 16);
+        uint32_t r[NC];
+#pragma unroll
+        for (int g = 0; g < NC / 8; ++g) tmem_ld8(taddr + g * 8, r + g * 8);
+        tmem_wait_ld();
+        const int qpos = POOL ? p >> 1 : p;
+        const bool writer = (p < L) && (!POOL || (p & 1) == 0);
+#pragma unroll
+        for (int g = 0; g < NC / 8; ++g) {
+            float v[8];
+            const float4 b0 = ld_shared_f4(bias_a + g * 32), b1 = ld_shared_f4(bias_a + g * 32 + 16);
+            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(__uint_as_float(r[g * 8 + e]) + bb[e], 0.f);
+            if (POOL) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
+            }
+            if (BN) {
+                const float4 s0 = ld_shared_f4(bn_a + g * 32), s1 = ld_shared_f4(bn_a + g * 32 + 16);
+                const float4 h0 = ld_shared_f4(bn_a + 192 + g * 32), h1 = ld_shared_f4(bn_a + 192 + g * 32 + 16);
+                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
+                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
+            }
+            uint4 hi, lo;
+            split8(v, &hi, &lo);
+            if (writer) {
+                if (PARITY) {   // even/odd pooled positions in separate arrays (input of conv1d_17)
+                    const uint32_t o = act + kYOff + (qpos & 1) * (2 * kYArray) + ((cg0 + g) * 17 + (qpos >> 1)) * 16;
+                    st_shared_v4(o, hi);
+                    st_shared_v4(o + kYArray, lo);
+                } else {
+                    const uint32_t o = out_base + ((cg0 + g) * out_lp + qpos + 1) * 16;
+                    st_shared_v4(o, hi);
+                    st_shared_v4(o + out_lo, lo);
+                }
+            }
         }
-    } else if (J.mode == EPI_PARITY && J.zero_y) {
-        if (tid < 96) {              // zero row 16 of every channel-group of Ye/Yo, hi and lo
+    }
+}
+
+// Head: conv1d_20 accumulators (rows 0..7 = positions, 16 columns) -> ReLU -> global average pool
+// -> softmax (network_architecture.py:89-91).  Warp 0 only.
+__device__ void epilogue_head(const TcJob& J, uint32_t prm, uint32_t tmem_win, int lane, int n_classes,
+                              float* probs_out) {
+    uint32_t r[16];
+    tmem_ld8(tmem_win, r);
+    tmem_ld8(tmem_win + 8, r + 8);
+    tmem_wait_ld();
+    float logit[16];
+#pragma unroll
+    for (int c = 0; c < 16; ++c) {
+        float b;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(prm + (J.bias_off + c) * 4));
+        float s = fmaxf(__uint_as_float(r[c]) + b, 0.f);
+        s += __shfl_xor_sync(0xffffffffu, s, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4);
+        logit[c] = s / 8.0f;
+    }
+    if (lane == 0 && probs_out) {
+        float m = logit[0];
+#pragma unroll
+        for (int c = 1; c < 16; ++c) if (c < n_classes) m = fmaxf(m, logit[c]);
+        float e[16], den = 0.f;
+#pragma unroll
+        for (int c = 0; c < 16; ++c) {
+            e[c] = c < n_classes ? expf(logit[c] - m) : 0.f;
+            den += e[c];
+        }
+#pragma unroll
+        for (int c = 0; c < 16; ++c) if (c < n_classes) probs_out[c] = e[c] / den;
+    }
+}
+
+__device__ void run_epilogue(const TcParams& P, const TcJob& J, uint32_t act, uint32_t prm, uint32_t tmem_win,
+                             int tid, float* probs_out) {
+    if (J.kind == EPI_HEAD) {
+        if (tid < 32) epilogue_head(J, prm, tmem_win, tid, P.n_classes, probs_out);
+        return;
+    }
+    if (J.kind == EPI_PARITY) {
+        if (J.zero_y && tid < 96) {   // zero row 16 of every channel-group of Ye/Yo, hi and lo
             const int cg = tid % 24, arr = tid / 24;
             st_shared_v4(act + kYOff + arr * kYArray + (cg * 17 + 16) * 16, make_uint4(0, 0, 0, 0));
         }
+    } else if (tid < 4 * J.out_ncg) {   // zero halo rows of the output tensor
+        const int cg = tid % J.out_ncg, which = tid / J.out_ncg;
+        const uint32_t a0 = act + J.out_off + (which & 1 ? J.out_lo_delta : 0) +
+                            (cg * J.out_lp + (which & 2 ? J.out_L + 1 : 0)) * 16;
+        st_shared_v4(a0, make_uint4(0, 0, 0, 0));
     }
-
-    for (int tile = 0; tile < J.ntiles; ++tile) {
-        const int p = tile * 128 + tid;                     // position of this thread's row
-        const uint32_t taddr = tmem_win + tile * kTmemTileCols + (static_cast<uint32_t>(warp * 32) << 16);
-        float head_logit[16];
-        for (int chunk = 0; chunk < J.n / 16; ++chunk) {
-            uint32_t r[16];
-            tmem_ld16(taddr + chunk * 16, r);
-            tmem_wait_ld();
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                const int c0 = chunk * 16 + half * 8;
-                float v[8];
-#pragma unroll
-                for (int e = 0; e < 8; ++e) {
-                    const int c = c0 + e;
-                    const float b = c < J.cout ? __ldg(bias + c) : 0.f;
-                    v[e] = fmaxf(__uint_as_float(r[half * 8 + e]) + b, 0.f);
-                }
-                if (J.mode == EPI_HEAD) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) head_logit[half * 8 + e] = v[e];
-                    continue;
-                }
-                if (J.pool) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
-                }
-                if (bns) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = fmaf(__ldg(bns + c0 + e), v[e], __ldg(bnh + c0 + e));
-                }
-                uint4 hi, lo;
-                split8(v, &hi, &lo);
-                const int q = J.pool ? p >> 1 : p;          // output position
-                const bool writer = (p < J.L) && (!J.pool || (p & 1) == 0);
-                if (writer) {
-                    const int cg = J.out_cg_base + (c0 >> 3);
-                    if (J.mode == EPI_NORMAL) {
-                        const uint32_t o = act + J.out_off + (cg * J.out_lp + q + 1) * 16;
-                        st_shared_v4(o, hi);
-                        st_shared_v4(o + J.out_lo_delta, lo);
-                    } else {   // EPI_PARITY: even/odd pooled positions in separate arrays
-                        const uint32_t o = act + kYOff + (q & 1) * (2 * kYArray) + (cg * 17 + (q >> 1)) * 16;
-                        st_shared_v4(o, hi);
-                        st_shared_v4(o + kYArray, lo);
-                    }
-                }
-            }
-        }
-        if (J.mode == EPI_HEAD && warp == 0) {
-            // GlobalAveragePooling1D over the 8 positions (lanes 0..7), then softmax
-            // (network_architecture.py:90-91)
-            float logit[16];
-#pragma unroll
-            for (int c = 0; c < 16; ++c) {
-                float s = head_logit[c];
-                s += __shfl_xor_sync(0xffffffffu, s, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 4);
-                logit[c] = s / 8.0f;
-            }
-            if (tid == 0 && probs_out) {
-                float m = logit[0];
-                for (int c = 1; c < P.n_classes; ++c) m = fmaxf(m, logit[c]);
-                float e[16], den = 0.f;
-                for (int c = 0; c < P.n_classes; ++c) {
-                    e[c] = expf(logit[c] - m);
-                    den += e[c];
-                }
-                for (int c = 0; c < P.n_classes; ++c) probs_out[c] = e[c] / den;
-            }
-        }
+    switch (J.kind) {
+        case EPI_N48: epilogue_tiles<24, false, false, false>(J, act, prm, tmem_win, tid); break;
+        case EPI_N48_POOL_BN: epilogue_tiles<24, true, true, false>(J, act, prm, tmem_win, tid); break;
+        case EPI_N48_BN: epilogue_tiles<24, false, true, false>(J, act, prm, tmem_win, tid); break;
+        case EPI_N16: epilogue_tiles<8, false, false, false>(J, act, prm, tmem_win, tid); break;
+        case EPI_PARITY: epilogue_tiles<24, true, true, true>(J, act, prm, tmem_win, tid); break;
+        default: break;
     }
 }
 
@@ -428,30 +482,35 @@ __device__ void epilogue(const TcParams& P, const TcJob& J, uint32_t act, uint32
 template <bool kCallMode>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_tc_forward(TcParams P, const float* __restrict__ x, const double* __restrict__ xd,
-                 const int16_t* __restrict__ samples,
-                 const int64_t* __restrict__ offsets, int n_reads, int side, int n_windows,
-                 float* __restrict__ probs) {
+                 const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets, int n_reads,
+                 int side, int n_windows, float* __restrict__ probs) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
     const uint32_t wbuf = sbase + kSmemWbuf;
-    const uint32_t bar_wfull = sbase + kSmemBar + 0;
-    const uint32_t bar_wfree = sbase + kSmemBar + 8;
-    const uint32_t bar_mma[2] = {sbase + kSmemBar + 16, sbase + kSmemBar + 24};
-    const uint32_t bar_epi[2] = {sbase + kSmemBar + 32, sbase + kSmemBar + 40};
-    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 64);
+    const uint32_t prm = sbase + kSmemPrm;
+    const uint32_t bar0 = sbase + kSmemBar;
+    const uint32_t bar_whi_full = bar0 + 0, bar_wlo_full = bar0 + 8;
+    const uint32_t bar_whi_free = bar0 + 16, bar_wlo_free = bar0 + 24;
+    const uint32_t bar_mma[2] = {bar0 + 32, bar0 + 40};
+    const uint32_t bar_epi[2] = {bar0 + 48, bar0 + 56};
+    const uint32_t bar_final = bar0 + 64;
+    volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 96);
     const int tid = threadIdx.x;
     const int warp = tid >> 5;
 
     if (tid == 0) {
-        mbar_init(bar_wfull, 1);
-        mbar_init(bar_wfree, 1);
+        mbar_init(bar_whi_full, 1);
+        mbar_init(bar_wlo_full, 1);
+        mbar_init(bar_whi_free, 1);
+        mbar_init(bar_wlo_free, 1);
         mbar_init(bar_mma[0], 1);
         mbar_init(bar_mma[1], 1);
         mbar_init(bar_epi[0], kEpiThreads);
         mbar_init(bar_epi[1], kEpiThreads);
+        mbar_init(bar_final, 1);
         fence_barrier_init();
     }
-    if (warp == 4) tmem_alloc(sbase + kSmemBar + 64, kTmemCols);
+    if (warp == kMmaWarp) tmem_alloc(sbase + kSmemBar + 96, kTmemCols);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -459,8 +518,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     const int njobs = (P.dbg_job >= 0 && P.dbg_job < P.njobs) ? P.dbg_job + 1 : P.njobs;
 
-    if (warp < 4) {
+    if (warp < kEpiWarps) {
         // ================= epilogue / CUDA-core warps =================
+        for (int i = tid; i < P.prm_floats / 4; i += kEpiThreads)
+            reinterpret_cast<float4*>(smem + kSmemPrm)[i] = __ldg(reinterpret_cast<const float4*>(P.prm) + i);
         int win[2];
         bool valid[2];
         for (int w = 0; w < 2; ++w) {
@@ -475,7 +536,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const int64_t off = offsets[read];
                 in.region = samples + off;
                 in.g = window_geometry(static_cast<int>(offsets[read + 1] - off), step, side);
-                // exact integer sums over the slice, reduced over the 128 threads
+                // exact integer sums over the slice, reduced over the 256 threads
                 long long s1 = 0, s2 = 0;
                 for (int i = tid; i < in.g.n; i += kEpiThreads) {
                     const long long v = in.region[in.g.a + i];
@@ -486,12 +547,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     s1 += __shfl_xor_sync(0xffffffffu, s1, o);
                     s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                 }
-                // cross-warp: through the scratch slots behind the barriers
-                long long* red = reinterpret_cast<long long*>(smem + kSmemBar + 128) + w * 8;
-                if ((tid & 31) == 0) { red[warp] = s1; red[4 + warp] = s2; }
+                long long* red = reinterpret_cast<long long*>(smem + kSmemBar + 128);
+                epi_bar_sync();   // previous window's readers are done with the scratch
+                if ((tid & 31) == 0) { red[warp] = s1; red[8 + warp] = s2; }
                 epi_bar_sync();
-                s1 = red[0] + red[1] + red[2] + red[3];
-                s2 = red[4] + red[5] + red[6] + red[7];
+                s1 = 0; s2 = 0;
+                for (int i = 0; i < kEpiWarps; ++i) { s1 += red[i]; s2 += red[8 + i]; }
                 in.mean = 0.0; in.stdev = 0.0;
                 if (in.g.n > 0) zscore_params(s1, s2, in.g.n, &in.mean, &in.stdev);
             } else if (x) {
@@ -503,18 +564,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             fence_proxy_async();
             mbar_arrive(bar_epi[w]);
         }
+        epi_bar_sync();   // parameter block staged by all epilogue threads is now visible
         uint32_t mma_phase[2] = {0, 0};
         for (int j = 0; j < njobs; ++j) {
-            const TcJob J = P.jobs[j];
+            const TcJob& J = c_jobs[j];
             if (!J.last) continue;
             for (int w = 0; w < 2; ++w) {
                 const uint32_t act = sbase + (w ? kSmemAct1 : kSmemAct0);
                 mbar_wait(bar_mma[w], mma_phase[w]);
                 mma_phase[w] ^= 1;
                 tc_fence_after();
-                float* pout = (J.mode == EPI_HEAD && valid[w])
+                float* pout = (J.kind == EPI_HEAD && valid[w])
                                   ? probs + static_cast<size_t>(win[w]) * P.n_classes : nullptr;
-                epilogue(P, J, act, tmem_base + w * kTmemWindowCols, tid, pout);
+                run_epilogue(P, J, act, prm, tmem_base + w * kTmemWindowCols, tid, pout);
                 if (J.avgpool_after) {
                     epi_bar_sync();
                     avgpool_stage(act, tid);
@@ -525,73 +587,97 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
         }
         if (P.dbg_job >= 0) {   // debug: dump both ACT regions after the last processed job
+            mbar_wait(bar_final, 0);
             epi_bar_sync();
             if (blockIdx.x == 0)
                 for (int i = tid; i < 2 * kActBytes / 16; i += kEpiThreads)
                     reinterpret_cast<uint4*>(P.dbg_out)[i] = reinterpret_cast<const uint4*>(smem)[i];
         }
-    } else if (tid == 128) {
-        // ================= weight loader + MMA issuer (one thread) =================
-        uint32_t wfull_phase = 0, wfree_phase = 0, epi_phase[2] = {0, 0};
+    } else if (tid == kMmaWarp * 32) {
+        // ================= MMA issuer (one thread) =================
+        uint32_t wfull_phase = 0, epi_phase[2] = {0, 0};
         for (int j = 0; j < njobs; ++j) {
-            const TcJob J = P.jobs[j];
-            if (j > 0) {   // weight buffer is free once every MMA of the previous job has completed
-                mbar_wait(bar_wfree, wfree_phase);
-                wfree_phase ^= 1;
-            }
-            mbar_expect_tx(bar_wfull, J.w_bytes);
-            bulk_g2s(wbuf, P.w + J.w_goff, J.w_bytes, bar_wfull);
-            mbar_wait(bar_wfull, wfull_phase);
-            wfull_phase ^= 1;
+            const TcJob& J = c_jobs[j];
             const uint32_t idesc = make_idesc(128, J.n);
-            const uint32_t blk_bytes = 2u * J.n * 16u;           // one K=16 block of B
-            const int nkb = J.ntaps * J.ncb;                     // K blocks per term in this job
+            const uint32_t blk16 = 2u * J.n;                 // one K=16 block of B, in 16-byte units
+            const uint32_t lp = J.lp, ntaps = J.ntaps, ncb = J.ncb, ntiles = J.ntiles;
+            const uint32_t lo16 = J.lo_delta >> 4;
+            const uint32_t whi16 = wbuf >> 4, wlo16 = (wbuf + kWHalf) >> 4;
             for (int w = 0; w < 2; ++w) {
                 if (J.first) {   // input written and previous accumulators drained
                     mbar_wait(bar_epi[w], epi_phase[w]);
                     epi_phase[w] ^= 1;
                 }
                 tc_fence_after();
-                const uint32_t act = sbase + (w ? kSmemAct1 : kSmemAct0);
-                for (int tile = 0; tile < J.ntiles; ++tile) {
-                    const uint32_t d = tmem_base + w * kTmemWindowCols + tile * kTmemTileCols;
+                const uint32_t act16 = (sbase + (w ? kSmemAct1 : kSmemAct0)) >> 4;
+                const uint32_t dwin = tmem_base + w * kTmemWindowCols;
+                // ---- phase 1: A_hi x W_lo (lets the loader refill W_lo early) ----
+                if (w == 0) mbar_wait(bar_wlo_full, wfull_phase);
+                for (uint32_t tile = 0; tile < ntiles; ++tile) {
                     uint32_t acc = J.first ? 0u : 1u;
-                    for (int term = 0; term < 3; ++term) {
-                        const uint32_t a_lo = term == 1 ? J.lo_delta : 0;
-                        const uint32_t b_lo = term == 2 ? nkb * blk_bytes : 0;
-                        for (int t = 0; t < J.ntaps; ++t) {
-                            for (int cb = 0; cb < J.ncb; ++cb) {
-                                const uint32_t a = act + J.tap_off[t] + a_lo +
-                                                   (2 * (J.cb0 + cb) * J.lp + tile * 128) * 16;
-                                const uint32_t b = wbuf + b_lo + (t * J.ncb + cb) * blk_bytes;
-                                tc_mma(d, make_desc(a, J.lp * 16, 128), make_desc(b, J.n * 16, 128),
-                                       idesc, acc);
-                                acc = 1u;
-                            }
+                    for (uint32_t t = 0; t < ntaps; ++t) {
+                        const uint32_t a_row = act16 + (J.tap_off[t] >> 4) + tile * 128;
+                        for (uint32_t cb = 0; cb < ncb; ++cb) {
+                            const uint32_t a = a_row + 2 * (J.cb0 + cb) * lp;
+                            const uint32_t b = wlo16 + (t * ncb + cb) * blk16;
+                            tc_mma(dwin + tile * kTmemTileCols, make_desc16(a, lp), make_desc16(b, J.n), idesc, acc);
+                            acc = 1u;
+                        }
+                    }
+                }
+                if (w == 1) tc_commit(bar_wlo_free);
+                // ---- phase 2: (A_hi + A_lo) x W_hi ----
+                if (w == 0) mbar_wait(bar_whi_full, wfull_phase);
+                for (uint32_t tile = 0; tile < ntiles; ++tile) {
+                    for (uint32_t t = 0; t < ntaps; ++t) {
+                        const uint32_t a_row = act16 + (J.tap_off[t] >> 4) + tile * 128;
+                        for (uint32_t cb = 0; cb < ncb; ++cb) {
+                            const uint32_t a = a_row + 2 * (J.cb0 + cb) * lp;
+                            const uint32_t b = whi16 + (t * ncb + cb) * blk16;
+                            const uint64_t bd = make_desc16(b, J.n);
+                            tc_mma(dwin + tile * kTmemTileCols, make_desc16(a, lp), bd, idesc, 1u);
+                            tc_mma(dwin + tile * kTmemTileCols, make_desc16(a + lo16, lp), bd, idesc, 1u);
                         }
                     }
                 }
                 if (J.last) tc_commit(bar_mma[w]);
+                if (w == 1) tc_commit(bar_whi_free);
             }
-            tc_commit(bar_wfree);
+            wfull_phase ^= 1;
         }
-        // drain: the last wfree commit covers every MMA issued by this thread
-        mbar_wait(bar_wfree, wfree_phase);
+        tc_commit(bar_final);
+        mbar_wait(bar_final, 0);
+    } else if (tid == kLoadWarp * 32) {
+        // ================= weight loader (one thread) =================
+        uint32_t free_phase = 0;
+        for (int j = 0; j < njobs; ++j) {
+            const TcJob& J = c_jobs[j];
+            const unsigned char* src = P.w + J.w_goff;
+            if (j > 0) mbar_wait(bar_wlo_free, free_phase);
+            mbar_expect_tx(bar_wlo_full, J.w_half);
+            bulk_g2s(wbuf + kWHalf, src + J.w_half, J.w_half, bar_wlo_full);
+            if (j > 0) {
+                mbar_wait(bar_whi_free, free_phase);
+                free_phase ^= 1;
+            }
+            mbar_expect_tx(bar_whi_full, J.w_half);
+            bulk_g2s(wbuf, src, J.w_half, bar_whi_full);
+        }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 4) tmem_dealloc(tmem_base, kTmemCols);
+    if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
 struct TcEngine {
-    TcJob* d_jobs = nullptr;
     unsigned char* d_w = nullptr;
     float* d_prm = nullptr;
     TcParams params{};
     int njobs = 0;
+    std::vector<TcJob> jobs;   // uploaded to constant memory (identical for every model of this topology)
 };
 
 static uint16_t bf16_rn(float f) {
@@ -612,26 +698,11 @@ struct JobBuilder {
     const Blob& blob;
     std::vector<TcJob> jobs;
     std::vector<unsigned char> w;
-    std::vector<float> prm;
-    int bias_off[21];
-    int bn_off[8];
+    std::vector<float> prm;        // smem-resident block: per job bias[n] (+ scale[48] shift[48])
+    std::vector<float> bn_scale[8], bn_shift[8];
 
     explicit JobBuilder(const Blob& b) : blob(b) {
-        for (int i = 1; i <= 20; ++i) {
-            const BlobTensor* t = blob.find("conv1d_" + std::to_string(i) + "/bias");
-            while (prm.size() % 4) prm.push_back(0.f);
-            bias_off[i] = static_cast<int>(prm.size());
-            prm.insert(prm.end(), t->data, t->data + t->count);
-            for (int k = 0; k < 16; ++k) prm.push_back(0.f);   // padding for N-padded reads
-        }
-        for (int i = 1; i <= 7; ++i) {
-            std::vector<float> sc, sh;
-            fold_bn(blob, i, &sc, &sh);
-            while (prm.size() % 4) prm.push_back(0.f);
-            bn_off[i] = static_cast<int>(prm.size());
-            prm.insert(prm.end(), sc.begin(), sc.end());   // scale[C] then shift[C]
-            prm.insert(prm.end(), sh.begin(), sh.end());
-        }
+        for (int i = 1; i <= 7; ++i) fold_bn(blob, i, &bn_scale[i], &bn_shift[i]);
     }
 
     // pack W[tap][cin][cout] -> [hi | lo][tap][cb in job][2 chunks][n rows][8] bf16
@@ -643,7 +714,7 @@ struct JobBuilder {
         const size_t blk = static_cast<size_t>(2) * n * 8;   // bf16 elements per K block
         while (w.size() % 128) w.push_back(0);
         J->w_goff = static_cast<int>(w.size());
-        J->w_bytes = static_cast<int>(2 * nkb * blk * 2);
+        J->w_half = static_cast<int>(nkb * blk * 2);
         std::vector<uint16_t> buf(2 * nkb * blk, 0);
         for (int t = 0; t < s.k; ++t)
             for (int cb = 0; cb < ncb; ++cb)
@@ -663,11 +734,25 @@ struct JobBuilder {
         w.insert(w.end(), p, p + buf.size() * 2);
     }
 
+    // bias (padded to n) and, if bn > 0, the folded scale/shift of channels [ch0, ch0+48) of BN `bn`
+    void pack_params(int layer, int n, int bn, int ch0, TcJob* J) {
+        const BlobTensor* t = blob.find("conv1d_" + std::to_string(layer) + "/bias");
+        J->bias_off = static_cast<int>(prm.size());
+        for (int c = 0; c < n; ++c) prm.push_back(c < static_cast<int>(t->count) ? t->data[c] : 0.f);
+        J->bn_off = 0;
+        if (bn > 0) {
+            J->bn_off = static_cast<int>(prm.size());
+            for (int c = 0; c < 48; ++c) prm.push_back(bn_scale[bn][ch0 + c]);
+            for (int c = 0; c < 48; ++c) prm.push_back(bn_shift[bn][ch0 + c]);
+        }
+    }
+
     // generic conv job; in_* describe the input tensor, out_* the output tensor
-    TcJob& add(int layer, int L, int in_off, int in_lp, int in_lo_delta, int mode, int pool, int bn,
-               int out_off, int out_cg_base) {
+    TcJob& add(int layer, int L, int in_off, int in_lp, int in_lo_delta, int kind, int bn, int out_off,
+               int out_cg_base) {
         const ConvSpec& s = kConvSpecs[layer];
         const int cout = s.cout ? s.cout : blob.n_classes;
+        const bool pool = kind == EPI_N48_POOL_BN || kind == EPI_PARITY;
         TcJob J{};
         J.n = (cout + 15) / 16 * 16;
         J.cout = cout;
@@ -680,10 +765,7 @@ struct JobBuilder {
         J.ncb = s.cin / 16;
         J.cb0 = 0;
         J.first = J.last = 1;
-        J.mode = mode;
-        J.pool = pool;
-        J.bias_off = bias_off[layer];
-        J.bn_off = bn > 0 ? bn_off[bn] : -1;
+        J.kind = kind;
         J.out_L = pool ? L / 2 : L;
         J.out_off = out_off;
         J.out_lp = J.out_L + 2;
@@ -691,6 +773,7 @@ struct JobBuilder {
         J.out_lo_delta = J.out_ncg * J.out_lp * 16;
         J.out_cg_base = out_cg_base;
         pack_weights(layer, J.n, 0, J.ncb, &J);
+        pack_params(layer, J.n, bn, kind == EPI_PARITY ? out_cg_base * 8 : 0, &J);
         jobs.push_back(J);
         return jobs.back();
     }
@@ -699,27 +782,23 @@ struct JobBuilder {
 static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     if (blob.n_classes > 16) return false;
     // T1 (BN1 output) is written by conv1_stage: [6][514][8], lo at +49344
-    B->add(2, 512, 0, 514, 49344, EPI_NORMAL, 0, 0, 0, 0);
-    B->add(3, 512, 0, 514, 49344, EPI_NORMAL, 0, 0, 0, 0);
-    B->add(4, 512, 0, 514, 49344, EPI_NORMAL, 1, 2, 0, 0);          // -> [6][258][8], lo +24768
-    B->add(5, 256, 0, 258, 24768, EPI_NORMAL, 0, 0, 0, 0);          // -> [2][258][8], lo +8256
-    B->add(6, 256, 0, 258, 8256, EPI_NORMAL, 0, 0, 0, 0);           // -> [6][258][8]
-    B->add(7, 256, 0, 258, 24768, EPI_NORMAL, 1, 3, 0, 0);          // -> [6][130][8], lo +12480
-    B->add(8, 128, 0, 130, 12480, EPI_NORMAL, 0, 0, 0, 0);
-    B->add(9, 128, 0, 130, 12480, EPI_NORMAL, 1, 4, 0, 0).avgpool_after = 1;   // X [6][66][8], lo +6336
-    // inception block: X @0, P @12672, T12 @25344, T14 @29568, T15 @33792, Y (parity split) @72576
-    B->add(10, 64, 12672, 66, 6336, EPI_PARITY, 1, 5, 0, 0).zero_y = 1;
-    B->add(11, 64, 0, 66, 6336, EPI_PARITY, 1, 5, 0, 6);
-    B->add(12, 64, 0, 66, 6336, EPI_NORMAL, 0, 0, 25344, 0);
-    B->add(13, 64, 25344, 66, 2112, EPI_PARITY, 1, 5, 0, 12);
-    B->add(14, 64, 0, 66, 6336, EPI_NORMAL, 0, 0, 29568, 0);
-    B->add(15, 64, 29568, 66, 2112, EPI_NORMAL, 0, 0, 33792, 0);
-    B->add(16, 64, 33792, 66, 6336, EPI_PARITY, 1, 5, 0, 18);
-    // BN5 parameters are per concatenated channel: offset the folded scale/shift per branch
-    {
-        const int base = B->bn_off[5];
-        (void)base;
-    }
+    B->add(2, 512, 0, 514, 49344, EPI_N48, 0, 0, 0);
+    B->add(3, 512, 0, 514, 49344, EPI_N48, 0, 0, 0);
+    B->add(4, 512, 0, 514, 49344, EPI_N48_POOL_BN, 2, 0, 0);      // -> [6][258][8], lo +24768
+    B->add(5, 256, 0, 258, 24768, EPI_N16, 0, 0, 0);              // -> [2][258][8], lo +8256
+    B->add(6, 256, 0, 258, 8256, EPI_N48, 0, 0, 0);               // -> [6][258][8]
+    B->add(7, 256, 0, 258, 24768, EPI_N48_POOL_BN, 3, 0, 0);      // -> [6][130][8], lo +12480
+    B->add(8, 128, 0, 130, 12480, EPI_N48, 0, 0, 0);
+    B->add(9, 128, 0, 130, 12480, EPI_N48_POOL_BN, 4, 0, 0).avgpool_after = 1;   // X [6][66][8], lo +6336
+    // inception block: X @0, P @12672, T12 @25344, T14 @29568, T15 @33792, Y (parity split) @72576;
+    // concat order [conv10, conv11, conv13, conv16] (network_architecture.py:68), BN5 per channel
+    B->add(10, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 0).zero_y = 1;
+    B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6);
+    B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 25344, 0);
+    B->add(13, 64, 25344, 66, 2112, EPI_PARITY, 5, 0, 12);
+    B->add(14, 64, 0, 66, 6336, EPI_N16, 0, 29568, 0);
+    B->add(15, 64, 29568, 66, 2112, EPI_N48, 0, 33792, 0);
+    B->add(16, 64, 33792, 66, 6336, EPI_PARITY, 5, 0, 18);
     // conv1d_17: stride 2 on the parity-split Y (tap0 = Ye[i], tap1 = Yo[i], tap2 = Ye[i+1]),
     // K = 3 x 192 split in 4 jobs of 3 channel blocks so each weight chunk fits the buffer
     for (int s = 0; s < 4; ++s) {
@@ -728,17 +807,24 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
         J.tap_off[0] = kYOff; J.tap_off[1] = kYOff + 2 * kYArray; J.tap_off[2] = kYOff + 16;
         J.lo_delta = kYArray; J.ncb = 3; J.cb0 = 3 * s;
         J.first = (s == 0); J.last = (s == 3);
-        J.mode = EPI_NORMAL; J.pool = 0; J.bias_off = B->bias_off[17]; J.bn_off = B->bn_off[6];
+        J.kind = EPI_N48_BN;
         J.out_L = 16; J.out_off = 0; J.out_lp = 18; J.out_ncg = 6; J.out_lo_delta = 6 * 18 * 16;
         J.out_cg_base = 0;
         B->pack_weights(17, 48, 3 * s, 3, &J);
+        if (J.last) B->pack_params(17, 48, 6, 0, &J);
         B->jobs.push_back(J);
     }
-    B->add(18, 16, 0, 18, 1728, EPI_NORMAL, 0, 0, 0, 0);
-    B->add(19, 16, 0, 18, 1728, EPI_NORMAL, 1, 7, 0, 0);            // -> [6][10][8], lo +960
-    B->add(20, 8, 0, 10, 960, EPI_HEAD, 0, 0, 0, 0);
+    B->add(18, 16, 0, 18, 1728, EPI_N48, 0, 0, 0);
+    B->add(19, 16, 0, 18, 1728, EPI_N48_POOL_BN, 7, 0, 0);        // -> [6][10][8], lo +960
+    B->add(20, 8, 0, 10, 960, EPI_HEAD, 0, 0, 0);
+    if (B->prm.size() > static_cast<size_t>(kPrmFloats) || B->jobs.size() > static_cast<size_t>(kMaxJobs))
+        return false;
+    for (const TcJob& J : B->jobs)
+        if (J.w_half > kWHalf) return false;
+    while (B->prm.size() % 4) B->prm.push_back(0.f);
+    P->prm_floats = static_cast<int>(B->prm.size());
 
-    // conv1 parameters
+    // conv1 parameters live behind the smem block in the global parameter buffer
     auto push = [&](const float* p, size_t n) {
         while (B->prm.size() % 4) B->prm.push_back(0.f);
         const int off = static_cast<int>(B->prm.size());
@@ -746,9 +832,9 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
         return off;
     };
     P->conv1_w = push(blob.find("conv1d_1/kernel")->data, 144);
-    P->conv1_b = B->bias_off[1];
-    P->bn1_s = B->bn_off[1];
-    P->bn1_h = B->bn_off[1] + 48;
+    P->conv1_b = push(blob.find("conv1d_1/bias")->data, 48);
+    P->bn1_s = push(B->bn_scale[1].data(), 48);
+    P->bn1_h = push(B->bn_shift[1].data(), 48);
     P->n_classes = blob.n_classes;
     return true;
 }
@@ -758,25 +844,10 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
     JobBuilder B(blob);
     TcParams P{};
     if (!build_jobs(blob, &B, &P)) return nullptr;
-    // BN5 covers the 192 concatenated channels: each branch's job reads scale at bn_off + cg_base*8
-    // and shift at bn_off + 192 + cg_base*8 -> handled by giving those jobs cout-relative offsets
-    for (TcJob& J : B.jobs)
-        if (J.mode == EPI_PARITY) {
-            // scale[c] at bn_off + c, shift[c] at bn_off + J.cout + c inside epilogue(); for the
-            // concat we need scale at base + 8*cg_base + c and shift at base + 192 + 8*cg_base + c.
-            // Re-pack a private [scale48 | shift48] pair for the branch.
-            const int base = B.bn_off[5], ch0 = J.out_cg_base * 8;
-            while (B.prm.size() % 4) B.prm.push_back(0.f);
-            const int off = static_cast<int>(B.prm.size());
-            for (int c = 0; c < 48; ++c) B.prm.push_back(B.prm[base + ch0 + c]);
-            for (int c = 0; c < 48; ++c) B.prm.push_back(B.prm[base + 192 + ch0 + c]);
-            J.bn_off = off;
-        }
     TcEngine* e = new TcEngine();
-    bool ok = cudaMalloc(&e->d_jobs, B.jobs.size() * sizeof(TcJob)) == cudaSuccess &&
-              cudaMalloc(&e->d_w, B.w.size()) == cudaSuccess &&
+    e->jobs = B.jobs;
+    bool ok = cudaMalloc(&e->d_w, B.w.size()) == cudaSuccess &&
               cudaMalloc(&e->d_prm, B.prm.size() * sizeof(float)) == cudaSuccess &&
-              cudaMemcpy(e->d_jobs, B.jobs.data(), B.jobs.size() * sizeof(TcJob), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(e->d_w, B.w.data(), B.w.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(e->d_prm, B.prm.data(), B.prm.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaFuncSetAttribute(k_tc_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
@@ -787,7 +858,6 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
         return nullptr;
     }
     e->njobs = static_cast<int>(B.jobs.size());
-    P.jobs = e->d_jobs;
     P.njobs = e->njobs;
     P.w = e->d_w;
     P.prm = e->d_prm;
@@ -799,14 +869,30 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
 
 void tc_destroy(TcEngine* e) {
     if (!e) return;
-    cudaFree(e->d_jobs);
     cudaFree(e->d_w);
     cudaFree(e->d_prm);
     delete e;
 }
 
+// The job table lives in constant memory.  It depends only on the topology and the class count, so
+// every model of a process normally shares one table; if a model with a different table shows up,
+// drain the device before replacing it (kernels of the previous model may still be reading it).
+static std::vector<TcJob> g_uploaded_jobs;
+static int sync_jobs(TcEngine* e) {
+    const size_t bytes = e->jobs.size() * sizeof(TcJob);
+    if (g_uploaded_jobs.size() == e->jobs.size() &&
+        std::memcmp(g_uploaded_jobs.data(), e->jobs.data(), bytes) == 0)
+        return 0;
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpyToSymbol(c_jobs, e->jobs.data(), bytes) != cudaSuccess)
+        return fail(DBN_ECUDA, "uploading the tcgen05 job table failed");
+    g_uploaded_jobs = e->jobs;
+    return 0;
+}
+
 int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, float* d_probs,
                cudaStream_t st) {
+    if (int rc = sync_jobs(e)) return rc;
     const int grid = static_cast<int>((n + 1) / 2);
     k_tc_forward<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(e->params, d_x, d_xd, nullptr, nullptr,
                                                                0, 0, static_cast<int>(n), d_probs);
@@ -817,6 +903,7 @@ int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, flo
 
 int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offsets, int n_reads,
                     int side, int steps, float* d_step_probs, cudaStream_t st) {
+    if (int rc = sync_jobs(e)) return rc;
     const int n = n_reads * steps;
     k_tc_forward<true><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(e->params, nullptr, nullptr, d_samples,
                                                                       d_offsets, n_reads, side, n,
@@ -830,6 +917,7 @@ int tc_num_jobs(const TcEngine* e) { return e ? e->njobs : 0; }
 
 // Debug: run windows d_x[0..1] up to and including job `job`, dump both ACT regions (2*98688 B).
 int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, cudaStream_t st) {
+    if (int rc = sync_jobs(e)) return rc;
     TcParams P = e->params;
     P.dbg_job = job;
     P.dbg_out = d_out;
