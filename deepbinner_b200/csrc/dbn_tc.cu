@@ -166,7 +166,9 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
                  : "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.
+// D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.  Issued by the one elected lane of
+// the MMA warp from a warp-uniform region, so ptxas keeps the descriptor arithmetic on the uniform
+// datapath (UTCHMMA takes uniform registers; no R2UR waterfall per instruction).
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
     asm volatile(
@@ -175,6 +177,15 @@ __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t
         "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
+}
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile(
+        "{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\t"
+        "elect.sync rx|px, 0xffffffff;\n\t"
+        "@px mov.s32 %0, 1;\n\t}"
+        : "+r"(pred));
+    return pred;
 }
 __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
     asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
@@ -357,7 +368,15 @@ __device__ void avgpool_stage(uint32_t act, int tid) {
 }
 
 // Epilogue of one job for one window: TMEM accumulators -> bias, ReLU, [pool], [BN], split -> smem.
-// Warp w handles TMEM lane quadrant (w & 3) and column half (w >> 2): NC columns per warp.
+// Warp w handles TMEM lane quadrant (w & 3) and column half (w >> 2): NC columns per warp.  The
+// per-channel parameters of the warp's columns are hoisted into registers once per job and the
+// TMEM load of the next tile is issued before the current tile is processed.
+template <int NC>
+__device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&r)[NC]) {
+#pragma unroll
+    for (int g = 0; g < NC / 8; ++g) tmem_ld8(taddr + g * 8, &r[g * 8]);
+}
+
 template <int NC, bool POOL, bool BN, bool PARITY>
 __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uint32_t prm, uint32_t tmem_win,
                                                int tid) {
@@ -365,38 +384,51 @@ __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uin
     const int q = warp & 3, h = warp >> 2;
     const int row = q * 32 + lane;
     const int ntiles = J.ntiles, L = J.L;
-    const uint32_t bias_a = prm + (J.bias_off + h * NC) * 4;
-    const uint32_t bn_a = prm + (J.bn_off + h * NC) * 4;
     const int cg0 = J.out_cg_base + (h * NC) / 8;
     const uint32_t out_base = act + J.out_off;
     const int out_lp = J.out_lp, out_lo = J.out_lo_delta;
+    float bias[NC], sc[BN ? NC : 1], sh[BN ? NC : 1];
+    {
+        const uint32_t bias_a = prm + (J.bias_off + h * NC) * 4;
+#pragma unroll
+        for (int g = 0; g < NC / 4; ++g) {
+            const float4 b = ld_shared_f4(bias_a + g * 16);
+            bias[4 * g] = b.x; bias[4 * g + 1] = b.y; bias[4 * g + 2] = b.z; bias[4 * g + 3] = b.w;
+        }
+        if (BN) {
+            const uint32_t bn_a = prm + (J.bn_off + h * NC) * 4;
+#pragma unroll
+            for (int g = 0; g < NC / 4; ++g) {
+                const float4 a = ld_shared_f4(bn_a + g * 16), b = ld_shared_f4(bn_a + 192 + g * 16);
+                sc[4 * g] = a.x; sc[4 * g + 1] = a.y; sc[4 * g + 2] = a.z; sc[4 * g + 3] = a.w;
+                sh[4 * g] = b.x; sh[4 * g + 1] = b.y; sh[4 * g + 2] = b.z; sh[4 * g + 3] = b.w;
+            }
+        }
+    }
+    const uint32_t taddr0 = tmem_win + h * NC + (static_cast<uint32_t>(q * 32) << 16);
+    uint32_t r[NC];
+    tmem_load_cols<NC>(taddr0, r);
     for (int tile = 0; tile < ntiles; ++tile) {
         const int p = tile * 128 + row;
-        const uint32_t taddr = tmem_win + tile * kTmemTileCols + h * NC + (static_cast<uint32_t>(q * 32) << 16);
-        uint32_t r[NC];
-#pragma unroll
-        for (int g = 0; g < NC / 8; ++g) tmem_ld8(taddr + g * 8, r + g * 8);
         tmem_wait_ld();
+        float acc[NC];
+#pragma unroll
+        for (int c = 0; c < NC; ++c) acc[c] = __uint_as_float(r[c]);
+        if (tile + 1 < ntiles) tmem_load_cols<NC>(taddr0 + (tile + 1) * kTmemTileCols, r);
         const int qpos = POOL ? p >> 1 : p;
         const bool writer = (p < L) && (!POOL || (p & 1) == 0);
 #pragma unroll
         for (int g = 0; g < NC / 8; ++g) {
             float v[8];
-            const float4 b0 = ld_shared_f4(bias_a + g * 32), b1 = ld_shared_f4(bias_a + g * 32 + 16);
-            const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(__uint_as_float(r[g * 8 + e]) + bb[e], 0.f);
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(acc[g * 8 + e] + bias[g * 8 + e], 0.f);
             if (POOL) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
             }
             if (BN) {
-                const float4 s0 = ld_shared_f4(bn_a + g * 32), s1 = ld_shared_f4(bn_a + g * 32 + 16);
-                const float4 h0 = ld_shared_f4(bn_a + 192 + g * 32), h1 = ld_shared_f4(bn_a + 192 + g * 32 + 16);
-                const float sc[8] = {s0.x, s0.y, s0.z, s0.w, s1.x, s1.y, s1.z, s1.w};
-                const float sh[8] = {h0.x, h0.y, h0.z, h0.w, h1.x, h1.y, h1.z, h1.w};
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[g * 8 + e], v[e], sh[g * 8 + e]);
             }
             uint4 hi, lo;
             split8(v, &hi, &lo);
@@ -476,6 +508,46 @@ __device__ void run_epilogue(const TcParams& P, const TcJob& J, uint32_t act, ui
     }
 }
 
+// One accumulation phase of a job for one window: for every tile, NT taps x NCB channel blocks of
+// K=16, each as NTERM MMAs (term 0: A_hi, term 1: A_lo) against the same B block.  Fully unrolled.
+template <int NT, int NCB, int NTERM>
+__device__ __forceinline__ void issue_phase(uint32_t dwin, uint32_t ntiles, uint32_t a16,
+                                            const uint32_t (&tap16)[3], uint32_t cb_first, uint32_t lp,
+                                            uint32_t lo16, uint32_t b16, uint32_t blk16, uint32_t n,
+                                            uint32_t idesc, bool zero_first) {
+    const uint64_t a_hi_word = (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(lp & 0x3FFF) << 16);
+    const uint64_t b_hi_word = (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(n & 0x3FFF) << 16);
+    for (uint32_t tile = 0; tile < ntiles; ++tile) {
+        const uint32_t d = dwin + tile * kTmemTileCols;
+        const uint32_t a_tile = a16 + tile * 128 + 2 * cb_first * lp;
+        uint32_t acc = zero_first ? 0u : 1u;
+#pragma unroll
+        for (int t = 0; t < NT; ++t) {
+#pragma unroll
+            for (int cb = 0; cb < NCB; ++cb) {
+                const uint32_t a = a_tile + tap16[t] + 2 * cb * lp;
+                const uint64_t bd = b_hi_word | ((b16 + (t * NCB + cb) * blk16) & 0x3FFF);
+                tc_mma(d, a_hi_word | (a & 0x3FFF), bd, idesc, acc);
+                acc = 1u;
+                if (NTERM == 2) tc_mma(d, a_hi_word | ((a + lo16) & 0x3FFF), bd, idesc, 1u);
+            }
+        }
+    }
+}
+
+template <int NTERM>
+__device__ __forceinline__ void issue_job_phase(int ntaps, int ncb, uint32_t dwin,
+                                                uint32_t ntiles, uint32_t a16, const uint32_t (&tap16)[3],
+                                                uint32_t cb_first, uint32_t lp, uint32_t lo16, uint32_t b16,
+                                                uint32_t blk16, uint32_t n, uint32_t idesc, bool zero_first) {
+    if (ntaps == 3 && ncb == 3)
+        issue_phase<3, 3, NTERM>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+    else if (ntaps == 1 && ncb == 3)
+        issue_phase<1, 3, NTERM>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+    else
+        issue_phase<3, 1, NTERM>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+}
+
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -496,7 +568,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t bar_final = bar0 + 64;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 96);
     const int tid = threadIdx.x;
-    const int warp = tid >> 5;
+    // warp index via shfl: tells the compiler it is warp-uniform, so the role branches below are
+    // convergent regions and the MMA issuer's address arithmetic can use the uniform datapath
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
     if (tid == 0) {
         mbar_init(bar_whi_full, 1);
@@ -593,62 +667,52 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int i = tid; i < 2 * kActBytes / 16; i += kEpiThreads)
                     reinterpret_cast<uint4*>(P.dbg_out)[i] = reinterpret_cast<const uint4*>(smem)[i];
         }
-    } else if (tid == kMmaWarp * 32) {
-        // ================= MMA issuer (one thread) =================
-        uint32_t wfull_phase = 0, epi_phase[2] = {0, 0};
-        for (int j = 0; j < njobs; ++j) {
-            const TcJob& J = c_jobs[j];
-            const uint32_t idesc = make_idesc(128, J.n);
-            const uint32_t blk16 = 2u * J.n;                 // one K=16 block of B, in 16-byte units
-            const uint32_t lp = J.lp, ntaps = J.ntaps, ncb = J.ncb, ntiles = J.ntiles;
-            const uint32_t lo16 = J.lo_delta >> 4;
-            const uint32_t whi16 = wbuf >> 4, wlo16 = (wbuf + kWHalf) >> 4;
-            for (int w = 0; w < 2; ++w) {
-                if (J.first) {   // input written and previous accumulators drained
-                    mbar_wait(bar_epi[w], epi_phase[w]);
-                    epi_phase[w] ^= 1;
-                }
-                tc_fence_after();
-                const uint32_t act16 = (sbase + (w ? kSmemAct1 : kSmemAct0)) >> 4;
-                const uint32_t dwin = tmem_base + w * kTmemWindowCols;
-                // ---- phase 1: A_hi x W_lo (lets the loader refill W_lo early) ----
-                if (w == 0) mbar_wait(bar_wlo_full, wfull_phase);
-                for (uint32_t tile = 0; tile < ntiles; ++tile) {
-                    uint32_t acc = J.first ? 0u : 1u;
-                    for (uint32_t t = 0; t < ntaps; ++t) {
-                        const uint32_t a_row = act16 + (J.tap_off[t] >> 4) + tile * 128;
-                        for (uint32_t cb = 0; cb < ncb; ++cb) {
-                            const uint32_t a = a_row + 2 * (J.cb0 + cb) * lp;
-                            const uint32_t b = wlo16 + (t * ncb + cb) * blk16;
-                            tc_mma(dwin + tile * kTmemTileCols, make_desc16(a, lp), make_desc16(b, J.n), idesc, acc);
-                            acc = 1u;
-                        }
+    } else if (warp == kMmaWarp) {
+        // ================= MMA issuer (one elected lane of a converged warp) =================
+        // A full 512-column allocation by the only CTA on the SM starts at TMEM address 0; using
+        // the literal keeps every MMA operand derived from uniform sources.
+        if (tmem_base != 0) __trap();
+        if (elect_one()) {
+            uint32_t wfull_phase = 0, epi_phase[2] = {0, 0};
+            for (int j = 0; j < njobs; ++j) {
+                const TcJob& J = c_jobs[j];
+                const int ntaps = J.ntaps, ncb = J.ncb;
+                const uint32_t n = J.n, lp = J.lp, ntiles = J.ntiles, cb0 = J.cb0;
+                const uint32_t idesc = make_idesc(128, n);
+                const uint32_t blk16 = 2u * n;                   // one K=16 block of B, in 16-byte units
+                const uint32_t lo16 = J.lo_delta >> 4;
+                const uint32_t tap16[3] = {static_cast<uint32_t>(J.tap_off[0]) >> 4,
+                                           static_cast<uint32_t>(J.tap_off[1]) >> 4,
+                                           static_cast<uint32_t>(J.tap_off[2]) >> 4};
+                const bool first = J.first != 0, last = J.last != 0;
+                const uint32_t whi16 = wbuf >> 4, wlo16 = (wbuf + kWHalf) >> 4;
+                for (int w = 0; w < 2; ++w) {
+                    if (first) {   // input written and previous accumulators drained
+                        mbar_wait(bar_epi[w], epi_phase[w]);
+                        epi_phase[w] ^= 1;
                     }
+                    tc_fence_after();
+                    const uint32_t act16 = (sbase + (w ? kSmemAct1 : kSmemAct0)) >> 4;
+                    const uint32_t dwin = w * kTmemWindowCols;
+                    // ---- phase 1: A_hi x W_lo (lets the loader refill W_lo early) ----
+                    if (w == 0) mbar_wait(bar_wlo_full, wfull_phase);
+                    issue_job_phase<1>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, wlo16, blk16, n,
+                                       idesc, first);
+                    if (w == 1) tc_commit(bar_wlo_free);
+                    // ---- phase 2: (A_hi + A_lo) x W_hi ----
+                    if (w == 0) mbar_wait(bar_whi_full, wfull_phase);
+                    issue_job_phase<2>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, whi16, blk16, n,
+                                       idesc, false);
+                    if (last) tc_commit(bar_mma[w]);
+                    if (w == 1) tc_commit(bar_whi_free);
                 }
-                if (w == 1) tc_commit(bar_wlo_free);
-                // ---- phase 2: (A_hi + A_lo) x W_hi ----
-                if (w == 0) mbar_wait(bar_whi_full, wfull_phase);
-                for (uint32_t tile = 0; tile < ntiles; ++tile) {
-                    for (uint32_t t = 0; t < ntaps; ++t) {
-                        const uint32_t a_row = act16 + (J.tap_off[t] >> 4) + tile * 128;
-                        for (uint32_t cb = 0; cb < ncb; ++cb) {
-                            const uint32_t a = a_row + 2 * (J.cb0 + cb) * lp;
-                            const uint32_t b = whi16 + (t * ncb + cb) * blk16;
-                            const uint64_t bd = make_desc16(b, J.n);
-                            tc_mma(dwin + tile * kTmemTileCols, make_desc16(a, lp), bd, idesc, 1u);
-                            tc_mma(dwin + tile * kTmemTileCols, make_desc16(a + lo16, lp), bd, idesc, 1u);
-                        }
-                    }
-                }
-                if (J.last) tc_commit(bar_mma[w]);
-                if (w == 1) tc_commit(bar_whi_free);
+                wfull_phase ^= 1;
             }
-            wfull_phase ^= 1;
+            tc_commit(bar_final);
+            mbar_wait(bar_final, 0);
         }
-        tc_commit(bar_final);
-        mbar_wait(bar_final, 0);
-    } else if (tid == kLoadWarp * 32) {
-        // ================= weight loader (one thread) =================
+    } else if (warp == kLoadWarp && elect_one()) {
+        // ================= weight loader (one elected lane) =================
         uint32_t free_phase = 0;
         for (int j = 0; j < njobs; ++j) {
             const TcJob& J = c_jobs[j];
