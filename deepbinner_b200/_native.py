@@ -69,6 +69,8 @@ def load_library():
         'db_tc_num_jobs': (ctypes.c_int, [ctypes.c_void_p]),
         'db_tc_debug_dump': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_void_p]),
+        'db_tc_trace': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
+                                       ctypes.c_void_p]),
         'db_last_gpu_ms': (ctypes.c_float, [ctypes.c_void_p]),
         'db_kernel_launches': (ctypes.c_int64, [ctypes.c_void_p]),
     }
@@ -86,7 +88,7 @@ EXPORTED_SYMBOLS = ['db_abi_version', 'db_last_error', 'db_create', 'db_destroy'
                     'db_set_engine', 'db_get_engine', 'db_predict_windows',
                     'db_predict_windows_f64', 'db_predict_windows_device', 'db_call_batch',
                     'db_call_batch_device', 'db_last_gpu_ms', 'db_kernel_launches',
-                    'db_tc_num_jobs', 'db_tc_debug_dump']
+                    'db_tc_num_jobs', 'db_tc_debug_dump', 'db_tc_trace']
 
 
 def check(rc, what):

@@ -22,6 +22,7 @@ int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offs
                     int side, int steps, float* d_step_probs, cudaStream_t st);
 
 int tc_num_jobs(const TcEngine* e);
+int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st);
 // Debug: run windows d_x[0..1] through jobs 0..job and dump both activation regions.
 int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, cudaStream_t st);
 

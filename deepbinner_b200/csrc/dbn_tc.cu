@@ -36,21 +36,22 @@ namespace dbn {
 // ---------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------
-constexpr int kEpiWarps = 8;
-constexpr int kEpiThreads = kEpiWarps * 32;     // warps 0-7: epilogue / CUDA-core stages
-constexpr int kMmaWarp = 8;                     // warp 8: TMEM allocator + MMA issuer
-constexpr int kLoadWarp = 9;                    // warp 9: weight loader
-constexpr int kTcThreads = 320;
+constexpr int kEpiWarps = 12;
+constexpr int kEpiThreads = kEpiWarps * 32;     // warps 0-11: epilogue / CUDA-core stages
+constexpr int kMmaWarp = 12;                    // warp 12: TMEM allocator + MMA issuer
+constexpr int kLoadWarp = 13;                   // warp 13: weight loader
+constexpr int kTcThreads = 448;
 constexpr int kActBytes = 98688;                // 2 x [6][514][8] bf16
-constexpr int kWHalf = 13824;                   // bf16 hi (or lo) part of a 48->48 k=3 layer
-constexpr int kWbufBytes = 2 * kWHalf;
+constexpr int kWPart0 = 15360;                  // weight part 0: up to 5 K blocks x (hi + lo) x 1536 B
+constexpr int kWPart1 = 12288;                  // weight part 1: up to 4 K blocks
+constexpr int kWbufBytes = kWPart0 + kWPart1;   // == hi+lo bf16 of a 48->48 k=3 layer
 constexpr int kPrmFloats = 1664;                // per-job bias / folded BN, resident in smem
 constexpr int kSmemAct0 = 0;
 constexpr int kSmemAct1 = kActBytes;
 constexpr int kSmemWbuf = 2 * kActBytes;
 constexpr int kSmemPrm = kSmemWbuf + kWbufBytes;
 constexpr int kSmemBar = kSmemPrm + kPrmFloats * 4;   // mbarriers, tmem pointer, reduction scratch
-constexpr int kTcSmemBytes = kSmemBar + 256;
+constexpr int kTcSmemBytes = kSmemBar + 384;
 static_assert(kTcSmemBytes <= 232448, "shared memory budget");
 constexpr int kTmemCols = 512;
 constexpr int kTmemWindowCols = 256;
@@ -80,8 +81,9 @@ struct TcJob {
     int lo_delta;     // bytes from hi array to lo array of the input
     int ncb;          // 16-channel K blocks per tap handled by this job
     int cb0;          // first K block (conv1d_17 is split in 4 jobs)
-    int w_goff;       // byte offset of this job's packed weights in global memory ([hi | lo])
-    int w_half;       // bytes of the hi part (== bytes of the lo part)
+    int w_goff;       // byte offset of this job's packed weights in global memory ([part 0 | part 1])
+    int kb_split;     // K blocks [0, kb_split) are weight part 0, [kb_split, ntaps*ncb) part 1
+    int w_part[2];    // bytes of each part; a part is [hi blocks | lo blocks] of its K-block range
     int first, last;  // first: zero the accumulators; last: run the epilogue
     // epilogue
     int kind, bias_off, bn_off;  // float offsets into the smem parameter block
@@ -100,6 +102,7 @@ struct TcParams {
     int n_classes;
     int dbg_job;              // >= 0: stop after this job's epilogue and dump ACT of both windows
     unsigned char* dbg_out;
+    long long* trace;         // optional timeline of CTA 0: [job][window][4] clock64 stamps
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -169,14 +172,32 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.  Issued by the one elected lane of
 // the MMA warp from a warp-uniform region, so ptxas keeps the descriptor arithmetic on the uniform
 // datapath (UTCHMMA takes uniform registers; no R2UR waterfall per instruction).
+// COLL: 0 = default, 1 = collector::a::fill (keep A in the collector buffer), 2 = collector::a::lastuse
+// (take A from the collector buffer instead of re-reading shared memory).
+template <int COLL>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                        uint32_t accumulate) {
-    asm volatile(
-        "{\n\t.reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-        ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (COLL == 1)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else if (COLL == 2)
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 __device__ __forceinline__ uint32_t elect_one() {
     uint32_t pred = 0;
@@ -197,8 +218,8 @@ __device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
 __device__ __forceinline__ void tmem_wait_ld() {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void epi_bar_sync() {   // the 256 epilogue threads only
-    asm volatile("bar.sync 1, 256;" ::: "memory");
+__device__ __forceinline__ void epi_bar_sync() {   // the 384 epilogue threads only
+    asm volatile("bar.sync 1, 384;" ::: "memory");
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
     asm volatile("st.shared.v4.b32 [%0], {%1,%2,%3,%4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z),
@@ -238,14 +259,17 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
     return r;
 }
+// hi is rounded to nearest (one F2FP per pair on the XU pipe); lo is the TRUNCATED upper half of
+// the exact remainder x - hi (one PRMT per pair).  The remainder's sign is symmetric around zero,
+// so truncating it toward zero is unbiased with respect to x; |x - hi - lo| <= 2^-16 |x|.
 __device__ __forceinline__ void split8(const float (&v)[8], uint4* hi, uint4* lo) {
     uint32_t h[4], l[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
-        const float h0 = __uint_as_float(h[i] << 16);
-        const float h1 = __uint_as_float(h[i] & 0xFFFF0000u);
-        l[i] = pack_bf16x2(v[2 * i] - h0, v[2 * i + 1] - h1);
+        const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
+        const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
+        l[i] = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x7632);
     }
     *hi = make_uint4(h[0], h[1], h[2], h[3]);
     *lo = make_uint4(l[0], l[1], l[2], l[3]);
@@ -283,15 +307,17 @@ struct WindowInput {
 };
 
 // conv1d_1 (1 -> 48, k=3, stride 2, pad right) + ReLU + BatchNorm_1 -> T1 [6][514][8] hi/lo.
+// 384 threads: thread t handles positions t and (t < 128) t + 384.
 __device__ void conv1_stage(const TcParams& P, const WindowInput& in, uint32_t act, int tid) {
     const float4* w4 = reinterpret_cast<const float4*>(P.prm + P.conv1_w);   // [3][48]
     const float4* b4 = reinterpret_cast<const float4*>(P.prm + P.conv1_b);
     const float4* s4 = reinterpret_cast<const float4*>(P.prm + P.bn1_s);
     const float4* h4 = reinterpret_cast<const float4*>(P.prm + P.bn1_h);
+    const int npos = tid < 128 ? 2 : 1;
     float xs[2][3];
 #pragma unroll
     for (int j = 0; j < 2; ++j) {
-        const int p = tid + 256 * j;
+        const int p = tid + kEpiThreads * j;
         xs[j][0] = in.at(2 * p);
         xs[j][1] = in.at(2 * p + 1);
         xs[j][2] = in.at(2 * p + 2);
@@ -311,9 +337,8 @@ __device__ void conv1_stage(const TcParams& P, const WindowInput& in, uint32_t a
             sc[4 * q] = ss.x; sc[4 * q + 1] = ss.y; sc[4 * q + 2] = ss.z; sc[4 * q + 3] = ss.w;
             sh[4 * q] = hh.x; sh[4 * q + 1] = hh.y; sh[4 * q + 2] = hh.z; sh[4 * q + 3] = hh.w;
         }
-#pragma unroll
-        for (int j = 0; j < 2; ++j) {
-            const int p = tid + 256 * j;
+        for (int j = 0; j < npos; ++j) {
+            const int p = tid + kEpiThreads * j;
             float v[8];
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
@@ -368,7 +393,8 @@ __device__ void avgpool_stage(uint32_t act, int tid) {
 }
 
 // Epilogue of one job for one window: TMEM accumulators -> bias, ReLU, [pool], [BN], split -> smem.
-// Warp w handles TMEM lane quadrant (w & 3) and column half (w >> 2): NC columns per warp.  The
+// Warp w handles TMEM lane quadrant (w & 3) and column group (w >> 2): NC = 16 columns per warp
+// (three groups for N = 48; for N = 16 only group 0 has work).  The
 // per-channel parameters of the warp's columns are hoisted into registers once per job and the
 // TMEM load of the next tile is issued before the current tile is processed.
 template <int NC>
@@ -382,6 +408,7 @@ __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uin
                                                int tid) {
     const int warp = tid >> 5, lane = tid & 31;
     const int q = warp & 3, h = warp >> 2;
+    if (h * NC >= J.n) return;
     const int row = q * 32 + lane;
     const int ntiles = J.ntiles, L = J.L;
     const int cg0 = J.out_cg_base + (h * NC) / 8;
@@ -448,7 +475,7 @@ __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uin
 }
 
 // Head: conv1d_20 accumulators (rows 0..7 = positions, 16 columns) -> ReLU -> global average pool
-// -> softmax (network_architecture.py:89-91).  Warp 0 only.
+// -> softmax (network_architecture.py:89-91).  Warp 0 only; lane l < 8 finishes classes l and l + 8.
 __device__ void epilogue_head(const TcJob& J, uint32_t prm, uint32_t tmem_win, int lane, int n_classes,
                               float* probs_out) {
     uint32_t r[16];
@@ -464,20 +491,24 @@ __device__ void epilogue_head(const TcJob& J, uint32_t prm, uint32_t tmem_win, i
         s += __shfl_xor_sync(0xffffffffu, s, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4);
-        logit[c] = s / 8.0f;
+        logit[c] = s / 8.0f;     // lanes 0..7 now all hold the mean over the 8 positions
     }
-    if (lane == 0 && probs_out) {
-        float m = logit[0];
+    float m = logit[0], mine0 = 0.f, mine1 = 0.f;
 #pragma unroll
-        for (int c = 1; c < 16; ++c) if (c < n_classes) m = fmaxf(m, logit[c]);
-        float e[16], den = 0.f;
-#pragma unroll
-        for (int c = 0; c < 16; ++c) {
-            e[c] = c < n_classes ? expf(logit[c] - m) : 0.f;
-            den += e[c];
-        }
-#pragma unroll
-        for (int c = 0; c < 16; ++c) if (c < n_classes) probs_out[c] = e[c] / den;
+    for (int c = 0; c < 16; ++c) {
+        if (c < n_classes) m = fmaxf(m, logit[c]);
+        if (c == lane) mine0 = logit[c];
+        if (c == lane + 8) mine1 = logit[c];
+    }
+    const float e0 = lane < n_classes ? expf(mine0 - m) : 0.f;
+    const float e1 = lane + 8 < n_classes ? expf(mine1 - m) : 0.f;
+    float den = e0 + e1;
+    den += __shfl_xor_sync(0xffffffffu, den, 1);
+    den += __shfl_xor_sync(0xffffffffu, den, 2);
+    den += __shfl_xor_sync(0xffffffffu, den, 4);
+    if (lane < 8 && probs_out) {
+        if (lane < n_classes) probs_out[lane] = e0 / den;
+        if (lane + 8 < n_classes) probs_out[lane + 8] = e1 / den;
     }
 }
 
@@ -499,53 +530,60 @@ __device__ void run_epilogue(const TcParams& P, const TcJob& J, uint32_t act, ui
         st_shared_v4(a0, make_uint4(0, 0, 0, 0));
     }
     switch (J.kind) {
-        case EPI_N48: epilogue_tiles<24, false, false, false>(J, act, prm, tmem_win, tid); break;
-        case EPI_N48_POOL_BN: epilogue_tiles<24, true, true, false>(J, act, prm, tmem_win, tid); break;
-        case EPI_N48_BN: epilogue_tiles<24, false, true, false>(J, act, prm, tmem_win, tid); break;
-        case EPI_N16: epilogue_tiles<8, false, false, false>(J, act, prm, tmem_win, tid); break;
-        case EPI_PARITY: epilogue_tiles<24, true, true, true>(J, act, prm, tmem_win, tid); break;
+        case EPI_N48: epilogue_tiles<16, false, false, false>(J, act, prm, tmem_win, tid); break;
+        case EPI_N48_POOL_BN: epilogue_tiles<16, true, true, false>(J, act, prm, tmem_win, tid); break;
+        case EPI_N48_BN: epilogue_tiles<16, false, true, false>(J, act, prm, tmem_win, tid); break;
+        case EPI_N16: epilogue_tiles<16, false, false, false>(J, act, prm, tmem_win, tid); break;
+        case EPI_PARITY: epilogue_tiles<16, true, true, true>(J, act, prm, tmem_win, tid); break;
         default: break;
     }
 }
 
-// One accumulation phase of a job for one window: for every tile, NT taps x NCB channel blocks of
-// K=16, each as NTERM MMAs (term 0: A_hi, term 1: A_lo) against the same B block.  Fully unrolled.
-template <int NT, int NCB, int NTERM>
-__device__ __forceinline__ void issue_phase(uint32_t dwin, uint32_t ntiles, uint32_t a16,
-                                            const uint32_t (&tap16)[3], uint32_t cb_first, uint32_t lp,
-                                            uint32_t lo16, uint32_t b16, uint32_t blk16, uint32_t n,
-                                            uint32_t idesc, bool zero_first) {
+// One weight part of a job for one window: for every tile, the K blocks [KB0, KB1) of the job
+// (block kb = tap kb / NCB, channel block kb % NCB), each as three MMAs
+//   A_hi x W_hi (A kept in the collector), A_hi x W_lo (A reused from the collector), A_lo x W_hi.
+// Fully unrolled; all operands warp-uniform.
+template <int NCB, int KB0, int KB1>
+__device__ __forceinline__ void issue_part(uint32_t dwin, uint32_t ntiles, uint32_t a16, const uint32_t (&tap16)[3],
+                                           uint32_t cb_first, uint32_t lp, uint32_t lo16, uint32_t b16,
+                                           uint32_t blk16, uint32_t n, uint32_t idesc, bool zero_first) {
     const uint64_t a_hi_word = (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(lp & 0x3FFF) << 16);
     const uint64_t b_hi_word = (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(n & 0x3FFF) << 16);
+    constexpr int NKB = KB1 - KB0;
     for (uint32_t tile = 0; tile < ntiles; ++tile) {
         const uint32_t d = dwin + tile * kTmemTileCols;
         const uint32_t a_tile = a16 + tile * 128 + 2 * cb_first * lp;
         uint32_t acc = zero_first ? 0u : 1u;
 #pragma unroll
-        for (int t = 0; t < NT; ++t) {
-#pragma unroll
-            for (int cb = 0; cb < NCB; ++cb) {
-                const uint32_t a = a_tile + tap16[t] + 2 * cb * lp;
-                const uint64_t bd = b_hi_word | ((b16 + (t * NCB + cb) * blk16) & 0x3FFF);
-                tc_mma(d, a_hi_word | (a & 0x3FFF), bd, idesc, acc);
-                acc = 1u;
-                if (NTERM == 2) tc_mma(d, a_hi_word | ((a + lo16) & 0x3FFF), bd, idesc, 1u);
-            }
+        for (int kb = KB0; kb < KB1; ++kb) {
+            const int t = kb / NCB, cb = kb % NCB;
+            const uint32_t a = a_tile + tap16[t] + 2 * cb * lp;
+            const uint64_t ad = a_hi_word | (a & 0x3FFF);
+            const uint64_t bd_hi = b_hi_word | ((b16 + (kb - KB0) * blk16) & 0x3FFF);
+            const uint64_t bd_lo = b_hi_word | ((b16 + (NKB + kb - KB0) * blk16) & 0x3FFF);
+            tc_mma<1>(d, ad, bd_hi, idesc, acc);
+            tc_mma<2>(d, ad, bd_lo, idesc, 1u);
+            tc_mma<0>(d, a_hi_word | ((a + lo16) & 0x3FFF), bd_hi, idesc, 1u);
+            acc = 1u;
         }
     }
 }
 
-template <int NTERM>
-__device__ __forceinline__ void issue_job_phase(int ntaps, int ncb, uint32_t dwin,
-                                                uint32_t ntiles, uint32_t a16, const uint32_t (&tap16)[3],
-                                                uint32_t cb_first, uint32_t lp, uint32_t lo16, uint32_t b16,
-                                                uint32_t blk16, uint32_t n, uint32_t idesc, bool zero_first) {
-    if (ntaps == 3 && ncb == 3)
-        issue_phase<3, 3, NTERM>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
-    else if (ntaps == 1 && ncb == 3)
-        issue_phase<1, 3, NTERM>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
-    else
-        issue_phase<3, 1, NTERM>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+template <int PART>
+__device__ __forceinline__ void issue_job_part(int ntaps, int ncb, uint32_t dwin, uint32_t ntiles, uint32_t a16,
+                                               const uint32_t (&tap16)[3], uint32_t cb_first, uint32_t lp,
+                                               uint32_t lo16, uint32_t b16, uint32_t blk16, uint32_t n,
+                                               uint32_t idesc, bool zero_first) {
+    if (ntaps == 3 && ncb == 3) {          // 9 K blocks: 5 + 4
+        if (PART == 0) issue_part<3, 0, 5>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+        else issue_part<3, 5, 9>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+    } else if (ntaps == 1) {               // 1x1 conv over 48 channels: 3 K blocks: 2 + 1
+        if (PART == 0) issue_part<3, 0, 2>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+        else issue_part<3, 2, 3>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+    } else {                               // k=3 conv over 16 channels: 3 K blocks (one per tap): 2 + 1
+        if (PART == 0) issue_part<1, 0, 2>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+        else issue_part<1, 2, 3>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+    }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -561,8 +599,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t wbuf = sbase + kSmemWbuf;
     const uint32_t prm = sbase + kSmemPrm;
     const uint32_t bar0 = sbase + kSmemBar;
-    const uint32_t bar_whi_full = bar0 + 0, bar_wlo_full = bar0 + 8;
-    const uint32_t bar_whi_free = bar0 + 16, bar_wlo_free = bar0 + 24;
+    const uint32_t bar_wfull[2] = {bar0 + 0, bar0 + 8};     // weight part p landed in smem
+    const uint32_t bar_wfree[2] = {bar0 + 16, bar0 + 24};   // every MMA reading weight part p completed
     const uint32_t bar_mma[2] = {bar0 + 32, bar0 + 40};
     const uint32_t bar_epi[2] = {bar0 + 48, bar0 + 56};
     const uint32_t bar_final = bar0 + 64;
@@ -573,10 +611,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
     if (tid == 0) {
-        mbar_init(bar_whi_full, 1);
-        mbar_init(bar_wlo_full, 1);
-        mbar_init(bar_whi_free, 1);
-        mbar_init(bar_wlo_free, 1);
+        mbar_init(bar_wfull[0], 1);
+        mbar_init(bar_wfull[1], 1);
+        mbar_init(bar_wfree[0], 1);
+        mbar_init(bar_wfree[1], 1);
         mbar_init(bar_mma[0], 1);
         mbar_init(bar_mma[1], 1);
         mbar_init(bar_epi[0], kEpiThreads);
@@ -594,6 +632,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     if (warp < kEpiWarps) {
         // ================= epilogue / CUDA-core warps =================
+        if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[31 * 8 + 0] = clock64();
         for (int i = tid; i < P.prm_floats / 4; i += kEpiThreads)
             reinterpret_cast<float4*>(smem + kSmemPrm)[i] = __ldg(reinterpret_cast<const float4*>(P.prm) + i);
         int win[2];
@@ -610,7 +649,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const int64_t off = offsets[read];
                 in.region = samples + off;
                 in.g = window_geometry(static_cast<int>(offsets[read + 1] - off), step, side);
-                // exact integer sums over the slice, reduced over the 256 threads
+                // exact integer sums over the slice, reduced over the 384 threads
                 long long s1 = 0, s2 = 0;
                 for (int i = tid; i < in.g.n; i += kEpiThreads) {
                     const long long v = in.region[in.g.a + i];
@@ -623,10 +662,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 }
                 long long* red = reinterpret_cast<long long*>(smem + kSmemBar + 128);
                 epi_bar_sync();   // previous window's readers are done with the scratch
-                if ((tid & 31) == 0) { red[warp] = s1; red[8 + warp] = s2; }
+                if ((tid & 31) == 0) { red[warp] = s1; red[12 + warp] = s2; }
                 epi_bar_sync();
                 s1 = 0; s2 = 0;
-                for (int i = 0; i < kEpiWarps; ++i) { s1 += red[i]; s2 += red[8 + i]; }
+                for (int i = 0; i < kEpiWarps; ++i) { s1 += red[i]; s2 += red[12 + i]; }
                 in.mean = 0.0; in.stdev = 0.0;
                 if (in.g.n > 0) zscore_params(s1, s2, in.g.n, &in.mean, &in.stdev);
             } else if (x) {
@@ -637,6 +676,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             conv1_stage(P, in, sbase + (w ? kSmemAct1 : kSmemAct0), tid);
             fence_proxy_async();
             mbar_arrive(bar_epi[w]);
+            if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[31 * 8 + 1 + w] = clock64();
         }
         epi_bar_sync();   // parameter block staged by all epilogue threads is now visible
         uint32_t mma_phase[2] = {0, 0};
@@ -648,6 +688,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 mbar_wait(bar_mma[w], mma_phase[w]);
                 mma_phase[w] ^= 1;
                 tc_fence_after();
+                if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[(j * 2 + w) * 4 + 2] = clock64();
                 float* pout = (J.kind == EPI_HEAD && valid[w])
                                   ? probs + static_cast<size_t>(win[w]) * P.n_classes : nullptr;
                 run_epilogue(P, J, act, prm, tmem_base + w * kTmemWindowCols, tid, pout);
@@ -658,6 +699,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 fence_proxy_async();
                 tc_fence_before();
                 mbar_arrive(bar_epi[w]);
+                if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[(j * 2 + w) * 4 + 3] = clock64();
             }
         }
         if (P.dbg_job >= 0) {   // debug: dump both ACT regions after the last processed job
@@ -685,26 +727,28 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                                            static_cast<uint32_t>(J.tap_off[1]) >> 4,
                                            static_cast<uint32_t>(J.tap_off[2]) >> 4};
                 const bool first = J.first != 0, last = J.last != 0;
-                const uint32_t whi16 = wbuf >> 4, wlo16 = (wbuf + kWHalf) >> 4;
+                const uint32_t wp16[2] = {wbuf >> 4, (wbuf + kWPart0) >> 4};
                 for (int w = 0; w < 2; ++w) {
                     if (first) {   // input written and previous accumulators drained
                         mbar_wait(bar_epi[w], epi_phase[w]);
                         epi_phase[w] ^= 1;
                     }
                     tc_fence_after();
+                    if (P.trace && blockIdx.x == 0) P.trace[(j * 2 + w) * 4 + 0] = clock64();
                     const uint32_t act16 = (sbase + (w ? kSmemAct1 : kSmemAct0)) >> 4;
                     const uint32_t dwin = w * kTmemWindowCols;
-                    // ---- phase 1: A_hi x W_lo (lets the loader refill W_lo early) ----
-                    if (w == 0) mbar_wait(bar_wlo_full, wfull_phase);
-                    issue_job_phase<1>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, wlo16, blk16, n,
-                                       idesc, first);
-                    if (w == 1) tc_commit(bar_wlo_free);
-                    // ---- phase 2: (A_hi + A_lo) x W_hi ----
-                    if (w == 0) mbar_wait(bar_whi_full, wfull_phase);
-                    issue_job_phase<2>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, whi16, blk16, n,
-                                       idesc, false);
+                    // ---- weight part 0 (first K blocks); freed early so the loader can refill it ----
+                    if (w == 0) mbar_wait(bar_wfull[0], wfull_phase);
+                    issue_job_part<0>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, wp16[0], blk16, n,
+                                      idesc, first);
+                    if (w == 1) tc_commit(bar_wfree[0]);
+                    // ---- weight part 1 (remaining K blocks) ----
+                    if (w == 0) mbar_wait(bar_wfull[1], wfull_phase);
+                    issue_job_part<1>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, wp16[1], blk16, n,
+                                      idesc, false);
                     if (last) tc_commit(bar_mma[w]);
-                    if (w == 1) tc_commit(bar_whi_free);
+                    if (w == 1) tc_commit(bar_wfree[1]);
+                    if (P.trace && blockIdx.x == 0) P.trace[(j * 2 + w) * 4 + 1] = clock64();
                 }
                 wfull_phase ^= 1;
             }
@@ -717,15 +761,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int j = 0; j < njobs; ++j) {
             const TcJob& J = c_jobs[j];
             const unsigned char* src = P.w + J.w_goff;
-            if (j > 0) mbar_wait(bar_wlo_free, free_phase);
-            mbar_expect_tx(bar_wlo_full, J.w_half);
-            bulk_g2s(wbuf + kWHalf, src + J.w_half, J.w_half, bar_wlo_full);
+            if (j > 0) mbar_wait(bar_wfree[0], free_phase);
+            mbar_expect_tx(bar_wfull[0], J.w_part[0]);
+            bulk_g2s(wbuf, src, J.w_part[0], bar_wfull[0]);
             if (j > 0) {
-                mbar_wait(bar_whi_free, free_phase);
+                mbar_wait(bar_wfree[1], free_phase);
                 free_phase ^= 1;
             }
-            mbar_expect_tx(bar_whi_full, J.w_half);
-            bulk_g2s(wbuf, src, J.w_half, bar_whi_full);
+            mbar_expect_tx(bar_wfull[1], J.w_part[1]);
+            bulk_g2s(wbuf + kWPart0, src + J.w_part[0], J.w_part[1], bar_wfull[1]);
         }
     }
     tc_fence_before();
@@ -769,19 +813,24 @@ struct JobBuilder {
         for (int i = 1; i <= 7; ++i) fold_bn(blob, i, &bn_scale[i], &bn_shift[i]);
     }
 
-    // pack W[tap][cin][cout] -> [hi | lo][tap][cb in job][2 chunks][n rows][8] bf16
+    // pack W[tap][cin][cout] -> two parts (K blocks [0, split) and [split, nkb), block kb = tap kb / ncb,
+    // channel block kb % ncb), each part [hi blocks | lo blocks], block = [2 chunks][n rows][8] bf16
     void pack_weights(int layer, int n, int cb0, int ncb, TcJob* J) {
         const ConvSpec& s = kConvSpecs[layer];
         const int cout = s.cout ? s.cout : blob.n_classes;
         const float* k = blob.find("conv1d_" + std::to_string(layer) + "/kernel")->data;
         const int nkb = s.k * ncb;
+        const int split = nkb == 9 ? 5 : 2;
         const size_t blk = static_cast<size_t>(2) * n * 8;   // bf16 elements per K block
         while (w.size() % 128) w.push_back(0);
         J->w_goff = static_cast<int>(w.size());
-        J->w_half = static_cast<int>(nkb * blk * 2);
-        std::vector<uint16_t> buf(2 * nkb * blk, 0);
-        for (int t = 0; t < s.k; ++t)
-            for (int cb = 0; cb < ncb; ++cb)
+        J->kb_split = split;
+        const int range[3] = {0, split, nkb};
+        for (int part = 0; part < 2; ++part) {
+            const int kb0 = range[part], kb1 = range[part + 1], cnt = kb1 - kb0;
+            std::vector<uint16_t> buf(2 * cnt * blk, 0);
+            for (int kb = kb0; kb < kb1; ++kb) {
+                const int t = kb / ncb, cb = kb % ncb;
                 for (int j = 0; j < 2; ++j)
                     for (int row = 0; row < n; ++row)
                         for (int e = 0; e < 8; ++e) {
@@ -790,12 +839,15 @@ struct JobBuilder {
                             if (row < cout && cin < s.cin) v = k[(t * s.cin + cin) * cout + row];
                             const uint16_t hi = bf16_rn(v);
                             const uint16_t lo = bf16_rn(v - bf16_to_float(hi));
-                            const size_t idx = (static_cast<size_t>(t * ncb + cb) * 2 + j) * n * 8 + row * 8 + e;
+                            const size_t idx = (static_cast<size_t>(kb - kb0) * 2 + j) * n * 8 + row * 8 + e;
                             buf[idx] = hi;
-                            buf[nkb * blk + idx] = lo;
+                            buf[cnt * blk + idx] = lo;
                         }
-        const unsigned char* p = reinterpret_cast<const unsigned char*>(buf.data());
-        w.insert(w.end(), p, p + buf.size() * 2);
+            }
+            J->w_part[part] = static_cast<int>(buf.size() * 2);
+            const unsigned char* p = reinterpret_cast<const unsigned char*>(buf.data());
+            w.insert(w.end(), p, p + buf.size() * 2);
+        }
     }
 
     // bias (padded to n) and, if bn > 0, the folded scale/shift of channels [ch0, ch0+48) of BN `bn`
@@ -884,7 +936,7 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     if (B->prm.size() > static_cast<size_t>(kPrmFloats) || B->jobs.size() > static_cast<size_t>(kMaxJobs))
         return false;
     for (const TcJob& J : B->jobs)
-        if (J.w_half > kWHalf) return false;
+        if (J.w_part[0] > kWPart0 || J.w_part[1] > kWPart1) return false;
     while (B->prm.size() % 4) B->prm.push_back(0.f);
     P->prm_floats = static_cast<int>(B->prm.size());
 
@@ -927,6 +979,7 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
     P.prm = e->d_prm;
     P.dbg_job = -1;
     P.dbg_out = nullptr;
+    P.trace = nullptr;
     e->params = P;
     return e;
 }
@@ -978,6 +1031,19 @@ int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offs
 }
 
 int tc_num_jobs(const TcEngine* e) { return e ? e->njobs : 0; }
+
+// Diagnostics: run `n` windows with CTA 0 recording clock64 stamps per (job, window):
+// [0] MMA issue start, [1] MMA issue end, [2] epilogue start (accumulators ready), [3] epilogue end.
+int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st) {
+    if (int rc = sync_jobs(e)) return rc;
+    TcParams P = e->params;
+    P.trace = d_trace;
+    k_tc_forward<false><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0,
+                                                                      n, d_probs);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(DBN_ECUDA, "tcgen05 trace launch failed: %s", cudaGetErrorString(err));
+    return 0;
+}
 
 // Debug: run windows d_x[0..1] up to and including job `job`, dump both ACT regions (2*98688 B).
 int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, cudaStream_t st) {

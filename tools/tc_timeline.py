@@ -1,0 +1,45 @@
+#!/usr/bin/env python3
+"""Print the per-job timeline of CTA 0 of the tcgen05 kernel (clock64 stamps), run on a B200."""
+import ctypes
+import pathlib
+import sys
+
+import numpy as np
+import torch
+
+ROOT = pathlib.Path(__file__).resolve().parents[1]
+sys.path.insert(0, str(ROOT))
+from deepbinner_b200.model import B200Model, tc_num_jobs  # noqa: E402
+from deepbinner_b200 import _native  # noqa: E402
+
+NAMES = ['conv2', 'conv3', 'conv4', 'conv5', 'conv6', 'conv7', 'conv8', 'conv9', 'conv10', 'conv11',
+         'conv12', 'conv13', 'conv14', 'conv15', 'conv16', 'c17a', 'c17b', 'c17c', 'c17d', 'conv18',
+         'conv19', 'conv20']
+
+
+def main():
+    n = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+    m = B200Model(str(ROOT / 'deepbinner_b200/models/EXP-NBD103_read_starts.dbnw'))
+    m.set_engine('tcgen05')
+    x = torch.randn(n, 1024, device='cuda')
+    p = torch.zeros(n, 13, device='cuda')
+    trace = np.zeros((32, 2, 4), dtype=np.int64)
+    for _ in range(3):
+        rc = m._lib.db_tc_trace(m._handle, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(p.data_ptr()),
+                                _native.as_ptr(trace))
+        _native.check(rc, 'db_tc_trace')
+    nj = tc_num_jobs(m)
+    misc = trace[31].reshape(-1)
+    t0 = misc[0] if misc[0] > 0 else trace[:nj][trace[:nj] > 0].min()
+    print('kernel start 0 | conv1 w0 done {} | conv1 w1 done {}'.format(int(misc[1] - t0), int(misc[2] - t0)))
+    print('job      win | mma_issue_start issue_end | epi_start epi_end | issue_dur epi_dur  (cycles rel. to first stamp)')
+    for j in range(nj):
+        for w in range(2):
+            a, b, c, d = [int(v - t0) if v > 0 else -1 for v in trace[j, w]]
+            print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d}'.format(
+                NAMES[j], w, a, b, c, d, b - a, (d - c) if c >= 0 else -1))
+    print('total', int(trace[:nj].max() - t0))
+
+
+if __name__ == '__main__':
+    main()
