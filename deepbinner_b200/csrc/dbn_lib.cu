@@ -522,7 +522,7 @@ int db_tc_debug_dump(db_model* m, const float* x, int job, unsigned char* out) {
 int db_tc_trace(db_model* m, const float* d_x, int n, float* d_probs, int64_t* trace) {
     if (!m || !m->tc) return fail(DBN_EINVAL, "tcgen05 engine not available");
     DBN_CUDA(cudaSetDevice(m->device));
-    const size_t bytes = 32 * 2 * 4 * sizeof(long long);
+    const size_t bytes = 32 * 2 * 16 * sizeof(long long);
     int rc = grow(&m->d_step, &m->d_step_bytes, bytes);
     if (rc) return rc;
     cudaStream_t st = m->streams[0];

@@ -138,8 +138,8 @@ DBN_API int64_t db_kernel_launches(const db_model *model);
  */
 DBN_API int db_tc_num_jobs(const db_model *model);
 DBN_API int db_tc_debug_dump(db_model *model, const float *x, int job, unsigned char *out);
-/* Timeline of CTA 0 for n device-resident windows: trace[job][window][4] SM-clock stamps (MMA issue
- * start/end, epilogue start/end); host buffer of 32*2*4 int64. */
+/* Timeline of CTA 0 for n device-resident windows: trace[job][window][8] SM-clock stamps (MMA issue
+ * start/end, epilogue start/end, then epilogue internals); host buffer of 32*2*8 int64. */
 DBN_API int db_tc_trace(db_model *model, const float *d_x, int n, float *d_probs, int64_t *trace);
 
 #ifdef __cplusplus

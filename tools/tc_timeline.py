@@ -23,7 +23,7 @@ def main():
     m.set_engine('tcgen05')
     x = torch.randn(n, 1024, device='cuda')
     p = torch.zeros(n, 13, device='cuda')
-    trace = np.zeros((32, 2, 4), dtype=np.int64)
+    trace = np.zeros((32, 2, 16), dtype=np.int64)
     for _ in range(3):
         rc = m._lib.db_tc_trace(m._handle, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(p.data_ptr()),
                                 _native.as_ptr(trace))
@@ -32,12 +32,14 @@ def main():
     misc = trace[31].reshape(-1)
     t0 = misc[0] if misc[0] > 0 else trace[:nj][trace[:nj] > 0].min()
     print('kernel start 0 | conv1 w0 done {} | conv1 w1 done {}'.format(int(misc[1] - t0), int(misc[2] - t0)))
-    print('job      win | mma_issue_start issue_end | epi_start epi_end | issue_dur epi_dur  (cycles rel. to first stamp)')
+    print('job      win | mma_issue_start issue_end | epi_start epi_end | issue_dur epi_dur | epi: params tmem compute fence')
     for j in range(nj):
         for w in range(2):
-            a, b, c, d = [int(v - t0) if v > 0 else -1 for v in trace[j, w]]
-            print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d}'.format(
-                NAMES[j], w, a, b, c, d, b - a, (d - c) if c >= 0 else -1))
+            a, b, c, d, e4, e5, e6, e7 = [int(v - t0) if v > 0 else -1 for v in trace[j, w][:8]]
+            x8, x9, x10 = [int(v - t0) if v > 0 else -1 for v in trace[j, w][8:11]]
+            print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d} | {:5d} {:5d} {:5d} {:5d} {:5d}'.format(
+                NAMES[j], w, a, b, c, d, b - a, (d - c) if c >= 0 else -1,
+                e4 - c, e5 - e4, e6 - e5, e7 - e6, d - e7) + '  || enter {} halo {} switch {} prm {}'.format(x8 - c, x9 - x8, x10 - x9, e4 - x10))
     print('total', int(trace[:nj].max() - t0))
 
 
