@@ -357,6 +357,8 @@ def main():
             line['cpu_baseline'] = cpu
         print(json.dumps(line), flush=True)
     parallel.barrier()
+    if world_size > 1:
+        torch.distributed.destroy_process_group()
 
 
 if __name__ == '__main__':

@@ -59,9 +59,16 @@ static_assert(kTcSmemBytes <= 232448, "shared memory budget");
 constexpr int kTmemCols = 512;
 constexpr int kTmemWindowCols = 256;
 constexpr int kTmemTileCols = 64;
-constexpr int kYOff = 72576;               // parity-split concat buffer (top of the ACT region)
-constexpr int kYArray = 6528;              // 24 cg x 17 rows x 16 B
-static_assert(kYOff + 4 * kYArray == kActBytes, "Y buffer placement");
+// Parity-split concat buffer (input of conv1d_17) for BOTH windows of the CTA, in window 0's ACT
+// region: 4 arrays (Ye_hi, Ye_lo, Yo_hi, Yo_lo) of [24 cg][36 rows][8]; window w occupies rows
+// 18w .. 18w+15, rows 18w+16/17 are zero.  From conv1d_17 on the two windows are STACKED in one
+// M=128 tile (row = 18 w + position): the L=16 tail then needs one MMA pass and one epilogue pass
+// per layer for both windows.  Pitch 18 keeps max-pool pairs even-aligned.
+constexpr int kStackPitch = 18;
+constexpr int kYRows = 2 * kStackPitch;    // 36
+constexpr int kYArray = 24 * kYRows * 16;  // 13824
+constexpr int kYOff = kActBytes - 4 * kYArray;   // 43392
+static_assert(kYOff >= 33792, "Y buffer overlaps the inception scratch tensors");
 constexpr int kMaxJobs = 32;
 
 enum EpiKind {
@@ -92,6 +99,7 @@ struct alignas(128) TcJob {
     int kind, bias_off, bn_off;  // float offsets into the smem parameter block
     int out_off, out_lp, out_lo_delta, out_cg_base, out_ncg, out_L;
     int avgpool_after, zero_y;
+    int stack;        // 1: both windows stacked in one tile (single pass); 2: first such job (joins windows)
 };
 
 __constant__ TcJob c_jobs[kMaxJobs];
@@ -422,8 +430,8 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&r)[NC]
 }
 
 template <int NC, bool POOL, bool BN, bool PARITY>
-__device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uint32_t prm, uint32_t tmem_win,
-                                               int tid, long long* tr) {
+__device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uint32_t act0, int w, uint32_t prm,
+                                               uint32_t tmem_win, int tid, long long* tr) {
     // tid is epilogue-relative (0..383); hardware warp = tid / 32 + kEpiWarp0 decides the TMEM lane
     // quadrant it may access (warp % 4); each run of 4 consecutive warps covers all quadrants
     const int lane = tid & 31;
@@ -431,6 +439,7 @@ __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uin
     if (h * NC >= J.n) return;
     const int row = q * 32 + lane;
     const int ntiles = J.ntiles, L = J.L;
+    const bool stack = J.stack != 0;
     const int cg0 = J.out_cg_base + (h * NC) / 8;
     const uint32_t out_base = act + J.out_off;
     const int out_lp = J.out_lp, out_lo = J.out_lo_delta;
@@ -466,7 +475,9 @@ __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uin
         for (int c = 0; c < NC; ++c) acc[c] = __uint_as_float(r[c]);
         if (tile + 1 < ntiles) tmem_load_cols<NC>(taddr0 + (tile + 1) * kTmemTileCols, r);
         const int qpos = POOL ? p >> 1 : p;
-        const bool writer = (p < L) && (!POOL || (p & 1) == 0);
+        // stacked tail: rows 18 w + i, i < 16 are positions; the other rows below L are separators
+        const bool valid = stack ? (p < L && (p % kStackPitch) < 16) : (p < L);
+        const bool writer = (stack && !POOL) ? (p < L) : (valid && (!POOL || (p & 1) == 0));
 #pragma unroll
         for (int g = 0; g < NC / 8; ++g) {
             float v[8];
@@ -482,9 +493,14 @@ __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uin
             }
             uint4 hi, lo;
             split8(v, &hi, &lo);
+            if (stack && !POOL && !valid) {   // separator rows of a stacked tensor are zero padding
+                hi = make_uint4(0, 0, 0, 0);
+                lo = make_uint4(0, 0, 0, 0);
+            }
             if (writer) {
                 if (PARITY) {   // even/odd pooled positions in separate arrays (input of conv1d_17)
-                    const uint32_t o = act + kYOff + (qpos & 1) * (2 * kYArray) + ((cg0 + g) * 17 + (qpos >> 1)) * 16;
+                    const uint32_t o = act0 + kYOff + (qpos & 1) * (2 * kYArray) +
+                                       ((cg0 + g) * kYRows + w * kStackPitch + (qpos >> 1)) * 16;
                     st_shared_v4(o, hi);
                     st_shared_v4(o + kYArray, lo);
                 } else {
@@ -497,56 +513,64 @@ __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uin
     }
 }
 
-// Head: conv1d_20 accumulators (rows 0..7 = positions, 16 columns) -> ReLU -> global average pool
-// -> softmax (network_architecture.py:89-91).  Warp 0 only; lane l < 8 finishes classes l and l + 8.
-__device__ void epilogue_head(const TcJob& J, uint32_t prm, uint32_t tmem_win, int lane, int n_classes,
-                              float* probs_out) {
+// Head for the two stacked windows: conv1d_20 accumulators (row 9 w + k = position k of window w, 16
+// columns) -> ReLU -> global average pool -> softmax (network_architecture.py:89-91).  One warp
+// (TMEM lane quadrant 0); `scratch` = 32 x 16 floats of free shared memory.  Lanes 0-15 finish
+// window 0 (class = lane), lanes 16-31 window 1.
+__device__ void epilogue_head(const TcJob& J, uint32_t prm, uint32_t tmem_win, uint32_t scratch, int lane,
+                              int n_classes, float* probs0, float* probs1) {
     uint32_t r[16];
     tmem_ld8(tmem_win, r);
     tmem_ld8(tmem_win + 8, r + 8);
     tmem_wait_ld();
-    float logit[16];
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        float b;
-        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(b) : "r"(prm + (J.bias_off + c) * 4));
-        float s = fmaxf(__uint_as_float(r[c]) + b, 0.f);
-        s += __shfl_xor_sync(0xffffffffu, s, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4);
-        logit[c] = s / 8.0f;     // lanes 0..7 now all hold the mean over the 8 positions
+    for (int g = 0; g < 4; ++g) {
+        const float4 b = ld_shared_f4(prm + (J.bias_off + 4 * g) * 4);
+        float4 v;
+        v.x = fmaxf(__uint_as_float(r[4 * g + 0]) + b.x, 0.f);
+        v.y = fmaxf(__uint_as_float(r[4 * g + 1]) + b.y, 0.f);
+        v.z = fmaxf(__uint_as_float(r[4 * g + 2]) + b.z, 0.f);
+        v.w = fmaxf(__uint_as_float(r[4 * g + 3]) + b.w, 0.f);
+        asm volatile("st.shared.v4.f32 [%0], {%1,%2,%3,%4};" ::"r"(scratch + (lane * 16 + 4 * g) * 4), "f"(v.x),
+                     "f"(v.y), "f"(v.z), "f"(v.w)
+                     : "memory");
     }
-    float m = logit[0], mine0 = 0.f, mine1 = 0.f;
+    __syncwarp();
+    const int w = lane >> 4, c = lane & 15;
+    float s = 0.f;
 #pragma unroll
-    for (int c = 0; c < 16; ++c) {
-        if (c < n_classes) m = fmaxf(m, logit[c]);
-        if (c == lane) mine0 = logit[c];
-        if (c == lane + 8) mine1 = logit[c];
+    for (int k = 0; k < 8; ++k) {
+        float t;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(t) : "r"(scratch + ((w * 9 + k) * 16 + c) * 4));
+        s += t;
     }
-    const float e0 = lane < n_classes ? expf(mine0 - m) : 0.f;
-    const float e1 = lane + 8 < n_classes ? expf(mine1 - m) : 0.f;
-    float den = e0 + e1;
-    den += __shfl_xor_sync(0xffffffffu, den, 1);
-    den += __shfl_xor_sync(0xffffffffu, den, 2);
-    den += __shfl_xor_sync(0xffffffffu, den, 4);
-    if (lane < 8 && probs_out) {
-        if (lane < n_classes) probs_out[lane] = e0 / den;
-        if (lane + 8 < n_classes) probs_out[lane + 8] = e1 / den;
-    }
+    const float logit = s / 8.0f;
+    float m = c < n_classes ? logit : -3.0e38f;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+    const float e = c < n_classes ? expf(logit - m) : 0.f;
+    float den = e;
+#pragma unroll
+    for (int o = 8; o > 0; o >>= 1) den += __shfl_xor_sync(0xffffffffu, den, o);
+    float* out = w ? probs1 : probs0;
+    if (out && c < n_classes) out[c] = e / den;
 }
 
-__device__ void run_epilogue(const TcParams& P, const TcJob& J, uint32_t act, uint32_t prm, uint32_t tmem_win,
-                             int tid, float* probs_out, long long* tr) {
+__device__ void run_epilogue(const TcParams& P, const TcJob& J, uint32_t act, uint32_t act0, int w, uint32_t prm,
+                             uint32_t tmem_win, int tid, float* probs0, float* probs1, long long* tr) {
     if (tr) tr[8] = clock64();
     if (J.kind == EPI_HEAD) {
-        // rows 0..7 live in TMEM lane quadrant 0: hardware warp 4 = epilogue-relative warp 2
-        if ((tid >> 5) == 2) epilogue_head(J, prm, tmem_win, tid & 31, P.n_classes, probs_out);
+        // rows 0..16 live in TMEM lane quadrant 0: hardware warp 4 = epilogue-relative warp 2;
+        // scratch: 2 KB of window 0's ACT region behind the (tiny) conv1d_19 output
+        if ((tid >> 5) == 2)
+            epilogue_head(J, prm, tmem_win, act0 + 8192, tid & 31, P.n_classes, probs0, probs1);
         return;
     }
     if (J.kind == EPI_PARITY) {
-        if (J.zero_y && tid < 96) {   // zero row 16 of every channel-group of Ye/Yo, hi and lo
-            const int cg = tid % 24, arr = tid / 24;
-            st_shared_v4(act + kYOff + arr * kYArray + (cg * 17 + 16) * 16, make_uint4(0, 0, 0, 0));
+        if (J.zero_y && tid < 192) {   // zero rows 16, 17 of this window in every array / channel-group
+            const int cg = tid % 24, rest = tid / 24, arr = rest >> 1, rrow = rest & 1;
+            st_shared_v4(act0 + kYOff + arr * kYArray + (cg * kYRows + w * kStackPitch + 16 + rrow) * 16,
+                         make_uint4(0, 0, 0, 0));
         }
     } else if (tid < 32 && (tid & 7) < J.out_ncg) {   // zero halo rows of the output tensor
         const int cg = tid & 7, which = tid >> 3;     // (no runtime division on this critical path)
@@ -556,11 +580,11 @@ __device__ void run_epilogue(const TcParams& P, const TcJob& J, uint32_t act, ui
     }
     if (tr) tr[9] = clock64();
     switch (J.kind) {
-        case EPI_N48: epilogue_tiles<16, false, false, false>(J, act, prm, tmem_win, tid, tr); break;
-        case EPI_N48_POOL_BN: epilogue_tiles<16, true, true, false>(J, act, prm, tmem_win, tid, tr); break;
-        case EPI_N48_BN: epilogue_tiles<16, false, true, false>(J, act, prm, tmem_win, tid, tr); break;
-        case EPI_N16: epilogue_tiles<16, false, false, false>(J, act, prm, tmem_win, tid, tr); break;
-        case EPI_PARITY: epilogue_tiles<16, true, true, true>(J, act, prm, tmem_win, tid, tr); break;
+        case EPI_N48: epilogue_tiles<16, false, false, false>(J, act, act0, w, prm, tmem_win, tid, tr); break;
+        case EPI_N48_POOL_BN: epilogue_tiles<16, true, true, false>(J, act, act0, w, prm, tmem_win, tid, tr); break;
+        case EPI_N48_BN: epilogue_tiles<16, false, true, false>(J, act, act0, w, prm, tmem_win, tid, tr); break;
+        case EPI_N16: epilogue_tiles<16, false, false, false>(J, act, act0, w, prm, tmem_win, tid, tr); break;
+        case EPI_PARITY: epilogue_tiles<16, true, true, true>(J, act, act0, w, prm, tmem_win, tid, tr); break;
         default: break;
     }
 }
@@ -712,16 +736,18 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const TcJob& J = c_jobs[j];
             if ((tid & 31) == 0) prefetch_job(j + 1);
             if (!J.last) continue;
-            for (int w = 0; w < 2; ++w) {
+            const int nw = J.stack ? 1 : 2;   // stacked tail jobs: one pass serves both windows
+            for (int w = 0; w < nw; ++w) {
                 const uint32_t act = sbase + (w ? kSmemAct1 : kSmemAct0);
                 mbar_wait(bar_mma[w], mma_phase[w]);
                 mma_phase[w] ^= 1;
                 tc_fence_after();
                 if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[(j * 2 + w) * 16 + 2] = clock64();
-                float* pout = (J.kind == EPI_HEAD && valid[w])
-                                  ? probs + static_cast<size_t>(win[w]) * P.n_classes : nullptr;
+                const bool head = J.kind == EPI_HEAD;
+                float* p0 = (head && valid[0]) ? probs + static_cast<size_t>(win[0]) * P.n_classes : nullptr;
+                float* p1 = (head && valid[1]) ? probs + static_cast<size_t>(win[1]) * P.n_classes : nullptr;
                 long long* tr = (P.trace && blockIdx.x == 0 && tid == 0) ? P.trace + (j * 2 + w) * 16 : nullptr;
-                run_epilogue(P, J, act, prm, tmem_base + w * kTmemWindowCols, tid, pout, tr);
+                run_epilogue(P, J, act, sbase + kSmemAct0, w, prm, tmem_base + w * kTmemWindowCols, tid, p0, p1, tr);
                 if (tr) tr[6] = clock64();
                 if (J.avgpool_after) {
                     epi_bar_sync();
@@ -761,10 +787,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                                            static_cast<uint32_t>(J.tap_off[2]) >> 4};
                 const bool first = J.first != 0, last = J.last != 0;
                 const uint32_t wp16[2] = {wbuf >> 4, (wbuf + kWPart0) >> 4};
-                for (int w = 0; w < 2; ++w) {
+                const int nw = J.stack ? 1 : 2;
+                for (int w = 0; w < nw; ++w) {
                     if (first) {   // input written and previous accumulators drained
                         mbar_wait(bar_epi[w], epi_phase[w]);
                         epi_phase[w] ^= 1;
+                        if (J.stack == 2) {   // first stacked job: window 1's last epilogue must be done too
+                            mbar_wait(bar_epi[1], epi_phase[1]);
+                            epi_phase[1] ^= 1;
+                        }
                     }
                     tc_fence_after();
                     if (P.trace && blockIdx.x == 0) P.trace[(j * 2 + w) * 16 + 0] = clock64();
@@ -774,13 +805,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     if (w == 0) mbar_wait(bar_wfull[0], wfull_phase);
                     issue_job_part<0>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, wp16[0], blk16, n,
                                       idesc, first);
-                    if (w == 1) tc_commit(bar_wfree[0]);
+                    if (w == nw - 1) tc_commit(bar_wfree[0]);
                     // ---- weight part 1 (remaining K blocks) ----
                     if (w == 0) mbar_wait(bar_wfull[1], wfull_phase);
                     issue_job_part<1>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, wp16[1], blk16, n,
                                       idesc, false);
                     if (last) tc_commit(bar_mma[w]);
-                    if (w == 1) tc_commit(bar_wfree[1]);
+                    if (w == nw - 1) tc_commit(bar_wfree[1]);
                     if (P.trace && blockIdx.x == 0) P.trace[(j * 2 + w) * 16 + 1] = clock64();
                 }
                 wfull_phase ^= 1;
@@ -939,33 +970,36 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     B->add(7, 256, 0, 258, 24768, EPI_N48_POOL_BN, 3, 0, 0);      // -> [6][130][8], lo +12480
     B->add(8, 128, 0, 130, 12480, EPI_N48, 0, 0, 0);
     B->add(9, 128, 0, 130, 12480, EPI_N48_POOL_BN, 4, 0, 0).avgpool_after = 1;   // X [6][66][8], lo +6336
-    // inception block: X @0, P @12672, T12 @25344, T14 @29568, T15 @33792, Y (parity split) @72576;
+    // inception block: X @0, P @12672 (later T15), T12 @25344, T14 @29568; Y (parity split, both
+    // windows) in window 0's region @43392;
     // concat order [conv10, conv11, conv13, conv16] (network_architecture.py:68), BN5 per channel
     B->add(10, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 0).zero_y = 1;
     B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6);
     B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 25344, 0);
     B->add(13, 64, 25344, 66, 2112, EPI_PARITY, 5, 0, 12);
     B->add(14, 64, 0, 66, 6336, EPI_N16, 0, 29568, 0);
-    B->add(15, 64, 29568, 66, 2112, EPI_N48, 0, 33792, 0);
-    B->add(16, 64, 33792, 66, 6336, EPI_PARITY, 5, 0, 18);
+    B->add(15, 64, 29568, 66, 2112, EPI_N48, 0, 12672, 0);     // T15 reuses P's slot (P is dead)
+    B->add(16, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 18);
+    // conv1d_17 .. conv1d_20 run on BOTH windows stacked in one tile (row = 18 w + position).
     // conv1d_17: stride 2 on the parity-split Y (tap0 = Ye[i], tap1 = Yo[i], tap2 = Ye[i+1]),
     // K = 3 x 192 split in 4 jobs of 3 channel blocks so each weight chunk fits the buffer
     for (int s = 0; s < 4; ++s) {
         TcJob J{};
-        J.n = 48; J.cout = 48; J.ntiles = 1; J.L = 16; J.lp = 17; J.ntaps = 3;
+        J.n = 48; J.cout = 48; J.ntiles = 1; J.L = 34; J.lp = kYRows; J.ntaps = 3;
         J.tap_off[0] = kYOff; J.tap_off[1] = kYOff + 2 * kYArray; J.tap_off[2] = kYOff + 16;
         J.lo_delta = kYArray; J.ncb = 3; J.cb0 = 3 * s;
         J.first = (s == 0); J.last = (s == 3);
+        J.stack = s == 0 ? 2 : 1;
         J.kind = EPI_N48_BN;
-        J.out_L = 16; J.out_off = 0; J.out_lp = 18; J.out_ncg = 6; J.out_lo_delta = 6 * 18 * 16;
+        J.out_L = 34; J.out_off = 0; J.out_lp = 36; J.out_ncg = 6; J.out_lo_delta = 6 * 36 * 16;
         J.out_cg_base = 0;
         B->pack_weights(17, 48, 3 * s, 3, &J);
         if (J.last) B->pack_params(17, 48, 6, 0, &J);
         B->jobs.push_back(J);
     }
-    B->add(18, 16, 0, 18, 1728, EPI_N48, 0, 0, 0);
-    B->add(19, 16, 0, 18, 1728, EPI_N48_POOL_BN, 7, 0, 0);        // -> [6][10][8], lo +960
-    B->add(20, 8, 0, 10, 960, EPI_HEAD, 0, 0, 0);
+    B->add(18, 34, 0, 36, 3456, EPI_N48, 0, 0, 0).stack = 1;
+    B->add(19, 34, 0, 36, 3456, EPI_N48_POOL_BN, 7, 0, 0).stack = 1;   // -> [6][19][8], lo +1824
+    B->add(20, 17, 0, 19, 1824, EPI_HEAD, 0, 0, 0).stack = 1;
     if (B->prm.size() > static_cast<size_t>(kPrmFloats) || B->jobs.size() > static_cast<size_t>(kMaxJobs))
         return false;
     for (const TcJob& J : B->jobs)

@@ -23,39 +23,56 @@ def decode(region, off, ncg, lp, length, lo_delta):
     return t, full[:, 0, :], full[:, length + 1, :]
 
 
-def decode_parity(region, cg0, ncg):
-    off, arr_bytes = 72576, 6528
+def decode_parity(act0, w, cg0, ncg):
+    """Parity-split concat buffer of both windows in window 0's region: 4 arrays [24][36][8]; window w
+    uses rows 18w .. 18w+15, rows 18w+16/17 must be zero."""
+    arr_bytes = 24 * 36 * 16
+    off = 98688 - 4 * arr_bytes
     def arr(o):
-        return bf16_to_f32(region[o:o + 24 * 17 * 16].view(np.uint16).reshape(24, 17, 8))
+        return bf16_to_f32(act0[o:o + arr_bytes].view(np.uint16).reshape(24, 36, 8))
     ye = arr(off) + arr(off + arr_bytes)
     yo = arr(off + 2 * arr_bytes) + arr(off + 3 * arr_bytes)
+    r0 = 18 * w
     y = np.zeros((32, ncg * 8), np.float32)
-    y[0::2] = ye[cg0:cg0 + ncg, :16].transpose(1, 0, 2).reshape(16, ncg * 8)
-    y[1::2] = yo[cg0:cg0 + ncg, :16].transpose(1, 0, 2).reshape(16, ncg * 8)
-    return y, ye[:, 16, :], None
+    y[0::2] = ye[cg0:cg0 + ncg, r0:r0 + 16].transpose(1, 0, 2).reshape(16, ncg * 8)
+    y[1::2] = yo[cg0:cg0 + ncg, r0:r0 + 16].transpose(1, 0, 2).reshape(16, ncg * 8)
+    return y, ye[:, r0 + 16:r0 + 18, :], None
 
 
-# job index -> (oracle tap, decoder)
+def decode_stacked(act0, w, lp, length, pitch, lo_delta):
+    """Stacked tail tensors (both windows in window 0's region): [6][lp][8] hi/lo, window w at rows
+    1 + pitch*w + i; returns (tensor, halo rows, separator rows)."""
+    def arr(o):
+        return bf16_to_f32(act0[o:o + 6 * lp * 16].view(np.uint16).reshape(6, lp, 8))
+    full = arr(0) + arr(lo_delta)
+    r0 = 1 + pitch * w
+    t = full[:, r0:r0 + length, :].transpose(1, 0, 2).reshape(length, 48)
+    halos = np.stack([full[:, 0, :], full[:, lp - 1, :]])
+    sep = full[:, 1 + length:1 + pitch, :] if (pitch > length and length == 16) else None
+    return t, halos, sep
+
+
+# job index -> (oracle tap, decoder(dump, w)); dump[w] = raw bytes of window w's activation region
 JOBS = [
-    (0, 'conv2', lambda r: decode(r, 0, 6, 514, 512, 49344)),
-    (1, 'conv3', lambda r: decode(r, 0, 6, 514, 512, 49344)),
-    (2, 'bn2', lambda r: decode(r, 0, 6, 258, 256, 24768)),
-    (3, 'conv5', lambda r: decode(r, 0, 2, 258, 256, 8256)),
-    (4, 'conv6', lambda r: decode(r, 0, 6, 258, 256, 24768)),
-    (5, 'bn3', lambda r: decode(r, 0, 6, 130, 128, 12480)),
-    (6, 'conv8', lambda r: decode(r, 0, 6, 130, 128, 12480)),
-    (7, 'bn4', lambda r: decode(r, 0, 6, 66, 64, 6336)),
-    (7, 'avgpool', lambda r: decode(r, 12672, 6, 66, 64, 6336)),
-    (8, 'bn5:0', lambda r: decode_parity(r, 0, 6)),
-    (9, 'bn5:48', lambda r: decode_parity(r, 6, 6)),
-    (10, 'conv12', lambda r: decode(r, 25344, 2, 66, 64, 2112)),
-    (11, 'bn5:96', lambda r: decode_parity(r, 12, 6)),
-    (12, 'conv14', lambda r: decode(r, 29568, 2, 66, 64, 2112)),
-    (13, 'conv15', lambda r: decode(r, 33792, 6, 66, 64, 6336)),
-    (14, 'bn5:144', lambda r: decode_parity(r, 18, 6)),
-    (18, 'bn6', lambda r: decode(r, 0, 6, 18, 16, 1728)),
-    (19, 'conv18', lambda r: decode(r, 0, 6, 18, 16, 1728)),
-    (20, 'bn7', lambda r: decode(r, 0, 6, 10, 8, 960)),
+    (0, 'conv2', lambda d, w: decode(d[w], 0, 6, 514, 512, 49344)),
+    (1, 'conv3', lambda d, w: decode(d[w], 0, 6, 514, 512, 49344)),
+    (2, 'bn2', lambda d, w: decode(d[w], 0, 6, 258, 256, 24768)),
+    (3, 'conv5', lambda d, w: decode(d[w], 0, 2, 258, 256, 8256)),
+    (4, 'conv6', lambda d, w: decode(d[w], 0, 6, 258, 256, 24768)),
+    (5, 'bn3', lambda d, w: decode(d[w], 0, 6, 130, 128, 12480)),
+    (6, 'conv8', lambda d, w: decode(d[w], 0, 6, 130, 128, 12480)),
+    (7, 'bn4', lambda d, w: decode(d[w], 0, 6, 66, 64, 6336)),
+    (7, 'avgpool', lambda d, w: decode(d[w], 12672, 6, 66, 64, 6336)),
+    (8, 'bn5:0', lambda d, w: decode_parity(d[0], w, 0, 6)),
+    (9, 'bn5:48', lambda d, w: decode_parity(d[0], w, 6, 6)),
+    (10, 'conv12', lambda d, w: decode(d[w], 25344, 2, 66, 64, 2112)),
+    (11, 'bn5:96', lambda d, w: decode_parity(d[0], w, 12, 6)),
+    (12, 'conv14', lambda d, w: decode(d[w], 29568, 2, 66, 64, 2112)),
+    (13, 'conv15', lambda d, w: decode(d[w], 12672, 6, 66, 64, 6336)),
+    (14, 'bn5:144', lambda d, w: decode_parity(d[0], w, 18, 6)),
+    (18, 'bn6', lambda d, w: decode_stacked(d[0], w, 36, 16, 18, 3456)),
+    (19, 'conv18', lambda d, w: decode_stacked(d[0], w, 36, 16, 18, 3456)),
+    (20, 'bn7', lambda d, w: decode_stacked(d[0], w, 19, 8, 9, 1824)),
 ]
 
 
@@ -76,7 +93,7 @@ def test_every_job_against_oracle(fixture_reads):
     for job, tap, dec in JOBS:
         dump = tc_debug_dump(model, x, job)
         for w in range(2):
-            got, halo_a, halo_b = dec(dump[w])
+            got, halo_a, halo_b = dec(dump, w)
             if tap.startswith('bn5:'):
                 c0 = int(tap.split(':')[1])
                 ref = taps['bn5'][w][:, c0:c0 + 48]
