@@ -429,34 +429,73 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&r)[NC]
     for (int g = 0; g < NC / 8; ++g) tmem_ld8(taddr + g * 8, &r[g * 8]);
 }
 
+// Everything a pass needs from the job descriptor, fetched into registers BEFORE waiting for the
+// accumulators (the wait has slack; the constant/shared loads would otherwise sit on the critical path).
+struct EpiArgs {
+    int kind, n, ntiles, L, stack, zero_y;
+    int bias_off, bn_off;
+    int out_off, out_lp, out_lo_delta, out_cg_base, out_ncg, out_L;
+};
+__device__ __forceinline__ EpiArgs load_epi_args(const TcJob& J) {
+    EpiArgs a;
+    a.kind = J.kind; a.n = J.n; a.ntiles = J.ntiles; a.L = J.L; a.stack = J.stack; a.zero_y = J.zero_y;
+    a.bias_off = J.bias_off; a.bn_off = J.bn_off;
+    a.out_off = J.out_off; a.out_lp = J.out_lp; a.out_lo_delta = J.out_lo_delta;
+    a.out_cg_base = J.out_cg_base; a.out_ncg = J.out_ncg; a.out_L = J.out_L;
+    return a;
+}
+
+// Wait until the MMAs of this (job, window) have completed.  Every epilogue thread waits every pass
+// (a thread may never run more than one mbarrier phase ahead).
+__device__ __forceinline__ void wait_accumulators(uint32_t bar, uint32_t parity, long long* tr) {
+    mbar_wait(bar, parity);
+    tc_fence_after();
+    if (tr) tr[2] = clock64();
+}
+
+// Zero padding rows written by each pass (after the wait: the output may alias the layer's input).
+__device__ __forceinline__ void zero_padding_rows(const EpiArgs& A, uint32_t act, uint32_t act0, int w, int tid) {
+    if (A.kind == EPI_PARITY) {
+        if (A.zero_y && tid < 192) {   // rows 16, 17 of this window in every array / channel-group
+            const int cg = tid % 24, rest = tid / 24, arr = rest >> 1, rrow = rest & 1;
+            st_shared_v4(act0 + kYOff + arr * kYArray + (cg * kYRows + w * kStackPitch + 16 + rrow) * 16,
+                         make_uint4(0, 0, 0, 0));
+        }
+    } else if (tid < 32 && (tid & 7) < A.out_ncg) {   // halo rows 0 and out_L + 1 of the output tensor
+        const int cg = tid & 7, which = tid >> 3;
+        const uint32_t a0 = act + A.out_off + (which & 1 ? A.out_lo_delta : 0) +
+                            (cg * A.out_lp + (which & 2 ? A.out_L + 1 : 0)) * 16;
+        st_shared_v4(a0, make_uint4(0, 0, 0, 0));
+    }
+}
+
 template <int NC, bool POOL, bool BN, bool PARITY>
-__device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uint32_t act0, int w, uint32_t prm,
-                                               uint32_t tmem_win, int tid, long long* tr) {
+__device__ __forceinline__ void epilogue_tiles(const EpiArgs& A, uint32_t act, uint32_t act0, int w, uint32_t prm,
+                                               uint32_t tmem_win, int tid, uint32_t bar, uint32_t parity,
+                                               long long* tr) {
     // tid is epilogue-relative (0..383); hardware warp = tid / 32 + kEpiWarp0 decides the TMEM lane
     // quadrant it may access (warp % 4); each run of 4 consecutive warps covers all quadrants
     const int lane = tid & 31;
     const int q = ((tid >> 5) + kEpiWarp0) & 3, h = tid >> 7;
-    if (h * NC >= J.n) return;
+    const bool active = h * NC < A.n;
     const int row = q * 32 + lane;
-    const int ntiles = J.ntiles, L = J.L;
-    const bool stack = J.stack != 0;
-    const int cg0 = J.out_cg_base + (h * NC) / 8;
-    const uint32_t out_base = act + J.out_off;
-    const int out_lp = J.out_lp, out_lo = J.out_lo_delta;
+    const int ntiles = A.ntiles, L = A.L;
+    const bool stack = A.stack != 0;
+    const int cg0 = A.out_cg_base + (h * NC) / 8;
+    const uint32_t out_base = act + A.out_off;
+    const int out_lp = A.out_lp, out_lo = A.out_lo_delta;
     const uint32_t taddr0 = tmem_win + h * NC + (static_cast<uint32_t>(q * 32) << 16);
-    uint32_t r[NC];
-    tmem_load_cols<NC>(taddr0, r);   // in flight while the per-channel parameters are fetched
     float bias[NC], sc[BN ? NC : 1], sh[BN ? NC : 1];
-    if (tr) tr[10] = clock64();
-    {
-        const uint32_t bias_a = prm + (J.bias_off + h * NC) * 4;
+    {   // unconditional (inactive warps read neighbouring parameters they never use) so that the
+        // arrays stay in registers
+        const uint32_t bias_a = prm + (A.bias_off + h * NC) * 4;
 #pragma unroll
         for (int g = 0; g < NC / 4; ++g) {
             const float4 b = ld_shared_f4(bias_a + g * 16);
             bias[4 * g] = b.x; bias[4 * g + 1] = b.y; bias[4 * g + 2] = b.z; bias[4 * g + 3] = b.w;
         }
         if (BN) {
-            const uint32_t bn_a = prm + (J.bn_off + h * NC) * 4;
+            const uint32_t bn_a = prm + (A.bn_off + h * NC) * 4;
 #pragma unroll
             for (int g = 0; g < NC / 4; ++g) {
                 const float4 a = ld_shared_f4(bn_a + g * 16), b = ld_shared_f4(bn_a + 192 + g * 16);
@@ -465,6 +504,14 @@ __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uin
             }
         }
     }
+    wait_accumulators(bar, parity, tr);
+    if (!active) {
+        zero_padding_rows(A, act, act0, w, tid);
+        return;
+    }
+    uint32_t r[NC];
+    tmem_load_cols<NC>(taddr0, r);
+    zero_padding_rows(A, act, act0, w, tid);
     if (tr) tr[4] = clock64();
     for (int tile = 0; tile < ntiles; ++tile) {
         const int p = tile * 128 + row;
@@ -517,7 +564,7 @@ __device__ __forceinline__ void epilogue_tiles(const TcJob& J, uint32_t act, uin
 // columns) -> ReLU -> global average pool -> softmax (network_architecture.py:89-91).  One warp
 // (TMEM lane quadrant 0); `scratch` = 32 x 16 floats of free shared memory.  Lanes 0-15 finish
 // window 0 (class = lane), lanes 16-31 window 1.
-__device__ void epilogue_head(const TcJob& J, uint32_t prm, uint32_t tmem_win, uint32_t scratch, int lane,
+__device__ void epilogue_head(int bias_off, uint32_t prm, uint32_t tmem_win, uint32_t scratch, int lane,
                               int n_classes, float* probs0, float* probs1) {
     uint32_t r[16];
     tmem_ld8(tmem_win, r);
@@ -525,7 +572,7 @@ __device__ void epilogue_head(const TcJob& J, uint32_t prm, uint32_t tmem_win, u
     tmem_wait_ld();
 #pragma unroll
     for (int g = 0; g < 4; ++g) {
-        const float4 b = ld_shared_f4(prm + (J.bias_off + 4 * g) * 4);
+        const float4 b = ld_shared_f4(prm + (bias_off + 4 * g) * 4);
         float4 v;
         v.x = fmaxf(__uint_as_float(r[4 * g + 0]) + b.x, 0.f);
         v.y = fmaxf(__uint_as_float(r[4 * g + 1]) + b.y, 0.f);
@@ -556,36 +603,26 @@ __device__ void epilogue_head(const TcJob& J, uint32_t prm, uint32_t tmem_win, u
     if (out && c < n_classes) out[c] = e / den;
 }
 
+// One epilogue pass: fetch the descriptor, dispatch on the kind, (inside) wait for the accumulators,
+// drain them.
 __device__ void run_epilogue(const TcParams& P, const TcJob& J, uint32_t act, uint32_t act0, int w, uint32_t prm,
-                             uint32_t tmem_win, int tid, float* probs0, float* probs1, long long* tr) {
-    if (tr) tr[8] = clock64();
-    if (J.kind == EPI_HEAD) {
+                             uint32_t tmem_win, int tid, uint32_t bar, uint32_t parity, float* probs0,
+                             float* probs1, long long* tr) {
+    const EpiArgs A = load_epi_args(J);
+    if (A.kind == EPI_N48 || A.kind == EPI_N16) {
+        epilogue_tiles<16, false, false, false>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+    } else if (A.kind == EPI_N48_POOL_BN) {
+        epilogue_tiles<16, true, true, false>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+    } else if (A.kind == EPI_PARITY) {
+        epilogue_tiles<16, true, true, true>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+    } else if (A.kind == EPI_N48_BN) {
+        epilogue_tiles<16, false, true, false>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+    } else {   // EPI_HEAD
+        wait_accumulators(bar, parity, tr);
         // rows 0..16 live in TMEM lane quadrant 0: hardware warp 4 = epilogue-relative warp 2;
         // scratch: 2 KB of window 0's ACT region behind the (tiny) conv1d_19 output
         if ((tid >> 5) == 2)
-            epilogue_head(J, prm, tmem_win, act0 + 8192, tid & 31, P.n_classes, probs0, probs1);
-        return;
-    }
-    if (J.kind == EPI_PARITY) {
-        if (J.zero_y && tid < 192) {   // zero rows 16, 17 of this window in every array / channel-group
-            const int cg = tid % 24, rest = tid / 24, arr = rest >> 1, rrow = rest & 1;
-            st_shared_v4(act0 + kYOff + arr * kYArray + (cg * kYRows + w * kStackPitch + 16 + rrow) * 16,
-                         make_uint4(0, 0, 0, 0));
-        }
-    } else if (tid < 32 && (tid & 7) < J.out_ncg) {   // zero halo rows of the output tensor
-        const int cg = tid & 7, which = tid >> 3;     // (no runtime division on this critical path)
-        const uint32_t a0 = act + J.out_off + (which & 1 ? J.out_lo_delta : 0) +
-                            (cg * J.out_lp + (which & 2 ? J.out_L + 1 : 0)) * 16;
-        st_shared_v4(a0, make_uint4(0, 0, 0, 0));
-    }
-    if (tr) tr[9] = clock64();
-    switch (J.kind) {
-        case EPI_N48: epilogue_tiles<16, false, false, false>(J, act, act0, w, prm, tmem_win, tid, tr); break;
-        case EPI_N48_POOL_BN: epilogue_tiles<16, true, true, false>(J, act, act0, w, prm, tmem_win, tid, tr); break;
-        case EPI_N48_BN: epilogue_tiles<16, false, true, false>(J, act, act0, w, prm, tmem_win, tid, tr); break;
-        case EPI_N16: epilogue_tiles<16, false, false, false>(J, act, act0, w, prm, tmem_win, tid, tr); break;
-        case EPI_PARITY: epilogue_tiles<16, true, true, true>(J, act, act0, w, prm, tmem_win, tid, tr); break;
-        default: break;
+            epilogue_head(A.bias_off, prm, tmem_win, act0 + 8192, tid & 31, P.n_classes, probs0, probs1);
     }
 }
 
@@ -739,15 +776,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const int nw = J.stack ? 1 : 2;   // stacked tail jobs: one pass serves both windows
             for (int w = 0; w < nw; ++w) {
                 const uint32_t act = sbase + (w ? kSmemAct1 : kSmemAct0);
-                mbar_wait(bar_mma[w], mma_phase[w]);
-                mma_phase[w] ^= 1;
-                tc_fence_after();
-                if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[(j * 2 + w) * 16 + 2] = clock64();
-                const bool head = J.kind == EPI_HEAD;
-                float* p0 = (head && valid[0]) ? probs + static_cast<size_t>(win[0]) * P.n_classes : nullptr;
-                float* p1 = (head && valid[1]) ? probs + static_cast<size_t>(win[1]) * P.n_classes : nullptr;
+                float* p0 = valid[0] ? probs + static_cast<size_t>(win[0]) * P.n_classes : nullptr;
+                float* p1 = valid[1] ? probs + static_cast<size_t>(win[1]) * P.n_classes : nullptr;
                 long long* tr = (P.trace && blockIdx.x == 0 && tid == 0) ? P.trace + (j * 2 + w) * 16 : nullptr;
-                run_epilogue(P, J, act, sbase + kSmemAct0, w, prm, tmem_base + w * kTmemWindowCols, tid, p0, p1, tr);
+                run_epilogue(P, J, act, sbase + kSmemAct0, w, prm, tmem_base + w * kTmemWindowCols, tid,
+                             bar_mma[w], mma_phase[w], p0, p1, tr);
+                mma_phase[w] ^= 1;
                 if (tr) tr[6] = clock64();
                 if (J.avgpool_after) {
                     epi_bar_sync();

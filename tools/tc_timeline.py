@@ -39,7 +39,7 @@ def main():
             x8, x9, x10 = [int(v - t0) if v > 0 else -1 for v in trace[j, w][8:11]]
             print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d} | {:5d} {:5d} {:5d} {:5d} {:5d}'.format(
                 NAMES[j], w, a, b, c, d, b - a, (d - c) if c >= 0 else -1,
-                e4 - c, e5 - e4, e6 - e5, e7 - e6, d - e7) + '  || enter {} halo {} switch {} prm {}'.format(x8 - c, x9 - x8, x10 - x9, e4 - x10))
+                e4 - c, e5 - e4, e6 - e5, e7 - e6, d - e7))
     print('total', int(trace[:nj].max() - t0))
 
 
