@@ -135,6 +135,9 @@ struct db_model {
     // streams / events
     cudaStream_t streams[2] = {nullptr, nullptr};
     cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+    cudaEvent_t ev_slot[2] = {nullptr, nullptr};
+    float* h_out[2] = {nullptr, nullptr};   // pinned result staging of the pipelined host predict
+    size_t h_out_bytes[2] = {0, 0};
     float last_ms = 0.f;
     int64_t launches = 0;
     // device scratch (grown on demand)
@@ -264,6 +267,10 @@ void db_destroy(db_model* m) {
     cudaFree(m->d_calls);
     if (m->h_samples) cudaFreeHost(m->h_samples);
     if (m->h_offsets) cudaFreeHost(m->h_offsets);
+    for (int i = 0; i < 2; ++i) {
+        if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
+        if (m->h_out[i]) cudaFreeHost(m->h_out[i]);
+    }
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     if (m->ev_stop) cudaEventDestroy(m->ev_stop);
     delete m;
@@ -311,6 +318,10 @@ int db_create(const void* weights_blob, size_t blob_bytes, int device, db_model*
             DBN_CUDA(cudaStreamCreateWithFlags(&m->streams[i], cudaStreamNonBlocking));
         DBN_CUDA(cudaEventCreate(&m->ev_start));
         DBN_CUDA(cudaEventCreate(&m->ev_stop));
+        for (int i = 0; i < 2; ++i) {
+            DBN_CUDA(cudaEventCreateWithFlags(&m->ev_slot[i], cudaEventDisableTiming));
+            DBN_CUDA(cudaEventRecord(m->ev_slot[i], m->streams[i]));   // so that a first wait never blocks
+        }
         return 0;
     }();
     if (rc) {
@@ -349,6 +360,10 @@ int db_set_engine(db_model* m, int engine) {
 
 int db_get_engine(const db_model* m) { return m ? m->engine : DBN_EINVAL; }
 
+// Host-buffer predict: the windows are processed in chunks on two streams so that the H2D copy of
+// chunk i+1 overlaps the kernel of chunk i.  Results go D2H into pinned staging (a copy into the
+// caller's pageable array would block the host and serialise the pipeline) and are copied out when
+// the slot is reused / at the end.
 static int predict_host(db_model* m, const void* x, bool is_f64, int64_t n, float* probs) {
     if (!m) return fail(DBN_EINVAL, "predict: model is NULL");
     if (n < 0) return fail(DBN_EINVAL, "predict: n < 0");
@@ -356,41 +371,52 @@ static int predict_host(db_model* m, const void* x, bool is_f64, int64_t n, floa
     if (!x || !probs) return fail(DBN_EINVAL, "predict: NULL buffer");
     DBN_CUDA(cudaSetDevice(m->device));
     const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
-    const int64_t kChunk = 16384;  // windows per pipelined chunk (64 MiB of fp32 input)
+    const int64_t kChunk = 8192;   // windows per pipelined chunk (32 MiB of fp32 input)
     const size_t row_in = static_cast<size_t>(m->input_size) * esz;
     const size_t row_out = static_cast<size_t>(m->n_classes) * sizeof(float);
     DBN_CUDA(cudaEventRecord(m->ev_start, m->streams[0]));
+    DBN_CUDA(cudaStreamWaitEvent(m->streams[1], m->ev_start, 0));
     int64_t done = 0;
+    int64_t pending_off[2] = {-1, -1}, pending_cnt[2] = {0, 0};
+    auto drain = [&](int slot) -> int {
+        if (pending_off[slot] < 0) return 0;
+        DBN_CUDA(cudaEventSynchronize(m->ev_slot[slot]));
+        std::memcpy(reinterpret_cast<char*>(probs) + pending_off[slot] * row_out, m->h_out[slot],
+                    pending_cnt[slot] * row_out);
+        pending_off[slot] = -1;
+        return 0;
+    };
     int slot = 0;
     while (done < n) {
         const int64_t cnt = std::min(kChunk, n - done);
         cudaStream_t st = m->streams[slot];
-        if (slot == 1 && done == kChunk)  // first use of stream 1: order it after the start event
-            DBN_CUDA(cudaStreamWaitEvent(st, m->ev_start, 0));
-        int rc = grow(&m->d_in[slot], &m->d_in_bytes[slot], cnt * row_in);
+        int rc = drain(slot);
+        if (rc) return rc;
+        rc = grow(&m->d_in[slot], &m->d_in_bytes[slot], cnt * row_in);
         if (rc) return rc;
         rc = grow(&m->d_out[slot], &m->d_out_bytes[slot], cnt * row_out);
+        if (rc) return rc;
+        rc = grow_host(&m->h_out[slot], &m->h_out_bytes[slot], cnt * row_out);
         if (rc) return rc;
         DBN_CUDA(cudaMemcpyAsync(m->d_in[slot], static_cast<const char*>(x) + done * row_in,
                                  cnt * row_in, cudaMemcpyHostToDevice, st));
         rc = launch_predict(m, m->d_in[slot], is_f64, cnt, m->d_out[slot], st);
         if (rc) return rc;
-        DBN_CUDA(cudaMemcpyAsync(reinterpret_cast<char*>(probs) + done * row_out, m->d_out[slot],
-                                 cnt * row_out, cudaMemcpyDeviceToHost, st));
+        DBN_CUDA(cudaMemcpyAsync(m->h_out[slot], m->d_out[slot], cnt * row_out, cudaMemcpyDeviceToHost, st));
+        DBN_CUDA(cudaEventRecord(m->ev_slot[slot], st));
+        pending_off[slot] = done;
+        pending_cnt[slot] = cnt;
         done += cnt;
         slot ^= 1;
     }
-    if (n > kChunk) {
-        // join stream 1 into stream 0 before the stop event
-        cudaEvent_t join;
-        DBN_CUDA(cudaEventCreateWithFlags(&join, cudaEventDisableTiming));
-        DBN_CUDA(cudaEventRecord(join, m->streams[1]));
-        DBN_CUDA(cudaStreamWaitEvent(m->streams[0], join, 0));
-        DBN_CUDA(cudaEventDestroy(join));
-    }
+    // join stream 1 into stream 0 before the stop event, then drain both slots
+    DBN_CUDA(cudaStreamWaitEvent(m->streams[0], m->ev_slot[1], 0));
     DBN_CUDA(cudaEventRecord(m->ev_stop, m->streams[0]));
+    for (int sl = 0; sl < 2; ++sl) {
+        int rc = drain(sl);
+        if (rc) return rc;
+    }
     DBN_CUDA(cudaEventSynchronize(m->ev_stop));
-    DBN_CUDA(cudaStreamSynchronize(m->streams[1]));
     DBN_CUDA(cudaEventElapsedTime(&m->last_ms, m->ev_start, m->ev_stop));
     return DBN_OK;
 }
