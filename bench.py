@@ -302,6 +302,38 @@ def main():
     parallel.barrier()
     e2e_value = world_size * shard * e2e_steps / e2e_s
 
+    # ---- informational: BASELINE configs[1] (EXP-NBD103 start+end models, batch 256, default scan
+    # 6144 => 12 windows per read per model) through the fused call_batch entry with host buffers ----
+    native = None
+    if rank == 0:
+        try:
+            from deepbinner_b200 import classify as cls
+            import types
+            end_model = B200Model(str(ROOT / 'deepbinner_b200' / 'models' / 'EXP-NBD103_read_ends.dbnw'),
+                                  device=local_rank, engine=args.engine)
+            rng = np.random.RandomState(7)
+            reads = [np.clip(rng.normal(rng.uniform(300, 600), rng.uniform(10, 500), rng.randint(3000, 20000)),
+                             -32768, 32767).astype(np.int16) for _ in range(BATCH)]
+            ids = ['r%d' % i for i in range(BATCH)]
+            a = types.SimpleNamespace(scan_size=6144.0, batch_size=BATCH, score_diff=0.5, require_either=True,
+                                      require_start=False, require_both=False)
+            def native_step():
+                sc, _ = cls.call_batch(1024, model.n_classes, ids, reads, model, a, 'start')
+                ec, _ = cls.call_batch(1024, model.n_classes, ids, reads, end_model, a, 'end')
+                return [cls.combine_calls(x, y, a) for x, y in zip(sc, ec)]
+            native_step()
+            t0 = time.perf_counter()
+            reps = 10
+            for _ in range(reps):
+                native_step()
+            dt = time.perf_counter() - t0
+            native = {'reads_per_s': reps * BATCH / dt, 'windows_per_s': reps * BATCH * 24 / dt,
+                      'what': 'classify.call_batch x2 + combine_calls on 256 host reads (fused GPU entry, '
+                              'H2D/D2H and Python packing included)'}
+            end_model.close()
+        except Exception as e:  # noqa: BLE001
+            native = {'error': str(e)}
+
     # ---- parity statistic of the metric: softmax max-abs-err vs the CPU reference ----
     parity = None
     cpu = None
@@ -339,6 +371,7 @@ def main():
                 'batch': BATCH, 'reads_per_step_per_gpu': shard, 'engine': model.engine,
                 'l2': 'inputs per step (256 MiB) exceed L2; no flush needed',
                 'large_batch_reads_per_s': shard / (big_ms * 1e-3),
+                'native_preset_batch256': native,
                 'windows_per_read': 1},
             'clocks': clocks,
             'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': shard * 4096,
