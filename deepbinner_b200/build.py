@@ -10,7 +10,7 @@ import sys
 PKG = pathlib.Path(__file__).resolve().parent
 CSRC = PKG / 'csrc'
 LIB = PKG / 'libdeepbinner_b200.so'
-SOURCES = ['dbn_lib.cu', 'dbn_tc.cu']
+SOURCES = ['dbn_lib.cu', 'dbn_tc.cu', 'dbn_fast5.cpp']
 NVCC_FLAGS = ['-gencode', 'arch=compute_100a,code=sm_100a', '-lineinfo', '-O3', '-std=c++17',
               '--use_fast_math=false', '-Xcompiler', '-fPIC', '-Xcompiler', '-fvisibility=hidden',
               '-shared', '-cudart', 'static']
@@ -37,7 +37,7 @@ def build_library(force=False, verbose=False):
     cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != '--use_fast_math=false']
     if verbose:
         cmd += ['-Xptxas', '-v']
-    cmd += [str(CSRC / s) for s in SOURCES] + ['-o', str(LIB)]
+    cmd += [str(CSRC / s) for s in SOURCES] + ['-lz', '-o', str(LIB)]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout)

@@ -18,7 +18,8 @@ import sys
 import numpy as np
 
 from . import hdf5_lite, weights
-from .load_fast5s import find_all_fast5s, get_read_id_and_signal, determine_single_or_multi_fast5s
+from .load_fast5s import (find_all_fast5s, get_read_id_and_signal, determine_single_or_multi_fast5s,
+                          read_fast5_batch)
 from .misc import print_summary_table
 from .model import B200Model, signals_fit_int16
 from .trim_signal import normalise
@@ -105,11 +106,15 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
     if full_output:
         print_output_header(args.verbose, use_start, use_end, output_size)
 
+    input_size = start_input_size if use_start else end_input_size
+    keep = int(args.scan_size) + input_size // 2
     classifications, read_id_to_fast5_file = {}, {}
     for batch in chunker(fast5_files, args.batch_size):
         read_ids, signals = [], []
-        for fast5_file in batch:
-            read_id, signal = get_read_id_and_signal(fast5_file)
+        # the whole batch is parsed on native host threads; only the samples call_batch can look at
+        # (first / last scan_size + input_size/2) are kept, which gives identical calls
+        loaded = load_batch(batch, keep)
+        for fast5_file, (read_id, signal) in zip(batch, loaded):
             if signal is None:       # unreadable file: skipped, as in the reference (:135-136)
                 continue
             read_id_to_fast5_file[read_id] = fast5_file
@@ -152,6 +157,16 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
         if summary_table:
             print_summary_table(classifications)
     return classifications, read_id_to_fast5_file
+
+
+def load_batch(fast5_batch, keep):
+    """[(read_id, signal)] for a batch of files.  Indirection point: tests substitute the loader."""
+    if get_read_id_and_signal is not _DEFAULT_SINGLE_LOADER:    # a test / caller patched the loader
+        return [get_read_id_and_signal(f) for f in fast5_batch]
+    return read_fast5_batch(fast5_batch, keep=keep)
+
+
+_DEFAULT_SINGLE_LOADER = get_read_id_and_signal
 
 
 def classify_training_data(input_file, start_model, start_input_size, end_model, end_input_size,

@@ -4,15 +4,79 @@ fast5 discovery and raw-signal extraction with the semantics of reference `load_
 :67-90, `get_root_level_keys` :93-98), on top of the built-in HDF5 subset reader (no h5py here).
 """
 
+import ctypes
 import os
 import random
 import sys
 
+import numpy as np
+
 from . import hdf5_lite
+
+
+def _native_lib():
+    """The C-ABI library's fast5 entry points (csrc/dbn_fast5.cpp), or None if the library cannot be
+    loaded (then the pure-Python reader below is used; both give identical results)."""
+    try:
+        from . import _native
+        return _native.load_library()
+    except Exception:  # noqa: BLE001
+        return None
+
+
+def read_fast5_batch(fast5_files, keep=0, threads=None):
+    """Parse many single-read fast5 files on native host threads.
+    -> list of (read_id, int16 signal) or (None, None) per file, in input order.  If keep > 0 only the
+    first and last `keep` samples of longer signals are returned (concatenated) - everything
+    call_batch can ever look at when keep >= scan_size + input_size/2."""
+    lib = _native_lib()
+    files = [str(f) for f in fast5_files]
+    if lib is None:
+        out = []
+        for f in files:
+            rid, sig = get_read_id_and_signal_python(f)
+            if sig is not None and keep > 0 and len(sig) > 2 * keep:
+                sig = np.concatenate([sig[:keep], sig[-keep:]])
+            out.append((rid, sig))
+        return out
+    n = len(files)
+    if n == 0:
+        return []
+    arr = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(f) for f in files])
+    handle = ctypes.c_void_p()
+    threads = threads or min(16, os.cpu_count() or 1)
+    if lib.db_fast5_batch_read(arr, n, int(threads), int(keep), ctypes.byref(handle)) != 0:
+        raise RuntimeError('db_fast5_batch_read failed')
+    try:
+        ptrs = [ctypes.c_void_p() for _ in range(5)]
+        lib.db_fast5_batch_get(handle, *[ctypes.byref(p) for p in ptrs])
+        offsets = np.ctypeslib.as_array(ctypes.cast(ptrs[1], ctypes.POINTER(ctypes.c_int64)), (n + 1,)).copy()
+        total = int(offsets[-1])
+        samples = np.ctypeslib.as_array(ctypes.cast(ptrs[0], ctypes.POINTER(ctypes.c_int16)),
+                                        (max(total, 1),))[:total].copy()
+        ids = ctypes.string_at(ptrs[3], n * 64)
+        status = np.ctypeslib.as_array(ctypes.cast(ptrs[4], ctypes.POINTER(ctypes.c_int32)), (max(n, 1),))[:n].copy()
+    finally:
+        lib.db_fast5_batch_free(handle)
+    out = []
+    for i in range(n):
+        if status[i] == 2:
+            sys.exit('Error: Deepbinner does not (yet) support multi-read fast5 files')
+        if status[i] != 0:
+            out.append((None, None))
+            continue
+        rid = ids[i * 64:(i + 1) * 64].split(b'\x00')[0].decode()
+        out.append((rid, samples[offsets[i]:offsets[i + 1]]))
+    return out
 
 
 def get_read_id_and_signal(fast5_file):
     """-> (read_id str, int16 signal) or (None, None) if the file cannot be read."""
+    return read_fast5_batch([fast5_file], threads=1)[0]
+
+
+def get_read_id_and_signal_python(fast5_file):
+    """Pure-Python twin of the native reader (hdf5_lite); kept as the cross-check."""
     try:
         with hdf5_lite.open_file(fast5_file) as h:
             keys = h.keys()
@@ -48,6 +112,17 @@ def find_all_fast5s(directory, verbose=False):
 
 
 def get_root_level_keys(fast5_file):
+    lib = _native_lib()
+    if lib is not None:
+        buf = ctypes.create_string_buffer(1 << 20)
+        count = ctypes.c_int()
+        if lib.db_fast5_list_root(os.fsencode(str(fast5_file)), buf, len(buf), ctypes.byref(count)) != 0:
+            return []
+        return [x.decode() for x in buf.raw.split(b'\x00')[:count.value]]
+    return get_root_level_keys_python(fast5_file)
+
+
+def get_root_level_keys_python(fast5_file):
     try:
         with hdf5_lite.open_file(fast5_file) as h:
             return h.keys()

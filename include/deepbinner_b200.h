@@ -132,6 +132,33 @@ DBN_API float db_last_gpu_ms(const db_model *model);
 DBN_API int64_t db_kernel_launches(const db_model *model);
 
 /*
+ * Native fast5 reader (host only, no GPU needed) - replaces h5py in load_fast5s.py:25-49
+ * get_read_id_and_signal and :93-98 get_root_level_keys.  Return value / status: 0 = ok,
+ * 1 = unreadable or not a single-read fast5 (the reference returns (None, None)), 2 = multi-read
+ * file (the reference exits with "does not (yet) support multi-read fast5 files").
+ *
+ * db_fast5_read: read_id (64-byte NUL-padded buffer) and the int16 Signal of one file; *length
+ *   receives the signal length; samples are copied only if capacity >= *length (call with
+ *   signal = NULL / capacity = 0 to query the length).
+ * db_fast5_list_root: NUL-separated names of the root group's members (hdf5_file.keys()).
+ * db_fast5_batch_read: parse n files on `threads` host threads; if keep > 0 only the first and last
+ *   `keep` samples of longer signals are retained (all call_batch ever slices when
+ *   keep >= scan_size + input_size/2).  db_fast5_batch_get exposes the packed result: samples,
+ *   offsets[n+1], full (untruncated) lengths[n], read ids [n][64], status[n]; the pointers stay
+ *   valid until db_fast5_batch_free.
+ */
+typedef struct db_fast5_batch db_fast5_batch;
+DBN_API int db_fast5_read(const char *path, char *read_id, int16_t *signal, int64_t capacity,
+                          int64_t *length);
+DBN_API int db_fast5_list_root(const char *path, char *names, int64_t capacity, int *count);
+DBN_API int db_fast5_batch_read(const char *const *paths, int n, int threads, int64_t keep,
+                                db_fast5_batch **out);
+DBN_API int db_fast5_batch_get(const db_fast5_batch *batch, const int16_t **samples,
+                               const int64_t **offsets, const int64_t **full_length,
+                               const char **read_ids, const int32_t **status);
+DBN_API void db_fast5_batch_free(db_fast5_batch *batch);
+
+/*
  * Diagnostics of the tcgen05 engine (used by tests/test_gpu_tc_layers.py): number of MMA jobs, and a
  * dump of the two shared-memory activation regions (2 x 98688 bytes, split-bf16 layout documented in
  * csrc/dbn_tc.cu) after running host windows x[0..1] through jobs 0..job.

@@ -77,3 +77,14 @@ def synthetic_signals(n_reads, seed=0, length=1024):
     lens = [length] * n_reads if np.isscalar(length) else list(length)
     return [np.clip(rng.normal(means[i], sds[i], lens[i]), -32768, 32767).astype(np.int16)
             for i in range(n_reads)]
+
+
+@pytest.fixture(scope='session')
+def fast5_dir(tmp_path_factory):
+    """The reference's fast5 test files (7 single-read + 1 multi-read), unpacked from the committed
+    archive tests/golden/fast5_fixtures.tar.gz."""
+    import tarfile
+    d = tmp_path_factory.mktemp('fast5')
+    with tarfile.open(GOLDEN / 'fast5_fixtures.tar.gz') as t:
+        t.extractall(d, filter='data')
+    return d

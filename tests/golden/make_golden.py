@@ -13,6 +13,10 @@ Outputs
                            tests/test_combine_calls.py:27-51, tests/test_load_fast5s.py:42-72
   oracle_outputs.npz       fp64-oracle outputs on those reads for the three shipped models:
                            per-step softmax rows, merged per-read probabilities and calls
+  fast5_fixtures.tar.gz    the reference's 7 single-read fast5 test files + one multi-read file,
+                           re-packed (`tar czf` of tests/fast5_files and one file of
+                           tests/multi_read_fast5_files) so the fast5 readers can be tested where
+                           /root/reference does not exist
   refcode_call_batch.json  outputs of the REFERENCE'S OWN call_batch (imported from
                            /root/reference with h5py/keras/tensorflow stubbed) driven by the
                            oracle's forward pass as `model.predict`
@@ -79,6 +83,10 @@ def main():
     for i, k in enumerate(sorted(multi)):
         arrays['multi_signal_{}'.format(i)] = multi[k]
     np.savez_compressed(HERE / 'fixture_reads.npz', **arrays)
+    import subprocess
+    subprocess.check_call(['tar', 'czf', str(HERE / 'fast5_fixtures.tar.gz'), 'fast5_files',
+                           'multi_read_fast5_files/FAK33493_2dac03b8dc7b3757bdcf3b4fed263b60fa5da102_1002.fast5'],
+                          cwd=str(REF / 'tests'))
 
     goldens = {
         'source': 'reference tests/test_classify.py, tests/test_combine_calls.py, tests/test_load_fast5s.py',

@@ -1,0 +1,60 @@
+"""fast5 readers: the native C++ reader behind the C ABI and its pure-Python twin
+against the reference's goldens (tests/test_load_fast5s.py:32-85) and against each other."""
+import numpy as np
+import pytest
+
+from deepbinner_b200 import load_fast5s as lf
+
+
+def singles(fast5_dir):
+    return sorted(str(p) for p in (fast5_dir / 'fast5_files').glob('*.fast5'))
+
+
+def test_native_reader_is_loaded():
+    assert lf._native_lib() is not None
+
+
+def test_goldens_of_the_reference_tests(fast5_dir, fixture_reads, reference_goldens, capsys):
+    ids, sigs, names = fixture_reads
+    files = lf.find_all_fast5s(fast5_dir / 'fast5_files', verbose=True)
+    assert len(files) == 7 and '7 fast5s found' in capsys.readouterr().err
+    for rid, sig, name in zip(ids, sigs, names):
+        for reader in (lf.get_read_id_and_signal, lf.get_read_id_and_signal_python):
+            r, s = reader(fast5_dir / 'fast5_files' / name)
+            assert r == rid and s.dtype == np.int16 and np.array_equal(s, sig)
+    for rid, g in reference_goldens['load_fast5'].items():
+        s = sigs[ids.index(rid)]
+        assert len(s) == g['len'] and all(s[int(k)] == v for k, v in g['samples'].items())
+    for reader in (lf.get_read_id_and_signal, lf.get_read_id_and_signal_python):
+        assert reader(fast5_dir / 'fast5_files' / 'not_a_real_file.fast5') == (None, None)
+        assert reader(__file__) == (None, None)
+
+
+def test_single_and_multi_detection(fast5_dir):
+    files = singles(fast5_dir)
+    multi = [str(p) for p in (fast5_dir / 'multi_read_fast5_files').glob('*.fast5')]
+    assert lf.determine_single_or_multi_fast5s(files) == 'single'
+    assert lf.determine_single_or_multi_fast5s(multi) == 'multi'
+    native, python = lf.get_root_level_keys(multi[0]), lf.get_root_level_keys_python(multi[0])
+    assert sorted(native) == sorted(python) and len(native) == 10
+    assert all(k.startswith('read_') for k in native)
+    assert lf.get_root_level_keys(files[0]) == lf.get_root_level_keys_python(files[0])
+    assert lf.get_root_level_keys(__file__) == []
+    with pytest.raises(SystemExit):          # load_fast5s.py:36-38
+        lf.get_read_id_and_signal(multi[0])
+
+
+def test_batch_reader_truncation_keeps_the_scan_regions(fast5_dir, fixture_reads):
+    ids, sigs, names = fixture_reads
+    files = [str(fast5_dir / 'fast5_files' / n) for n in names] + [str(fast5_dir / 'nope.fast5')]
+    keep = 6144 + 512
+    for threads in (1, 4):
+        got = lf.read_fast5_batch(files, keep=keep, threads=threads)
+        assert got[-1] == (None, None)
+        for (rid, s), ref_id, ref in zip(got, ids, sigs):
+            assert rid == ref_id
+            assert np.array_equal(s[:keep], ref[:keep]) and np.array_equal(s[-keep:], ref[-keep:])
+            assert len(s) == min(len(ref), 2 * keep)
+    full = lf.read_fast5_batch(files[:-1], keep=0)
+    assert all(np.array_equal(s, ref) for (_, s), ref in zip(full, sigs))
+    assert lf.read_fast5_batch([]) == []

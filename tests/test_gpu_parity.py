@@ -254,3 +254,51 @@ def test_errors_are_loud(models):
     with pytest.raises(ValueError):
         model.predict(np.zeros((2, 1000, 1)))
     assert model.kernel_launches > 0
+
+
+def test_cli_classify_on_real_fast5_files(fast5_dir, reference_goldens, capsys):
+    """`deepbinner classify --native <dir>` end to end: native fast5 reader -> fused GPU call_batch ->
+    TSV on stdout; calls equal the reference's both-models goldens (tests/test_classify.py:154-160)
+    and the README expectation for the sample reads (2 reads each of barcodes 1, 2, 3)."""
+    from deepbinner_b200 import deepbinner as cli
+    cli.main(['classify', '--native', str(fast5_dir / 'fast5_files')])
+    out = capsys.readouterr()
+    lines = out.out.strip().splitlines()
+    assert lines[0] == 'read_ID\tbarcode_call' and len(lines) == 8
+    got = dict(l.split('\t') for l in lines[1:])
+    assert got == reference_goldens['both_require_either']
+    assert '7 fast5s found' in out.err      # (the summary table goes to the stderr bound at import time)
+    # a single file, verbose, start model only (TSV row pinned at tests/test_classify.py:213-217)
+    g = reference_goldens['verbose_row_177c3867']
+    one = [p for p in (fast5_dir / 'fast5_files').glob('*read_11206*')][0]
+    cli.main(['classify', '-s', cli.find_native_start_model(), '--verbose', str(one)])
+    lines = capsys.readouterr().out.strip().splitlines()
+    assert lines[1] == '\t'.join([g['read_id'], '3'] + g['start'])
+    with pytest.raises(SystemExit) as e:     # multi-read input is rejected like the reference does
+        cli.main(['classify', '--native', str(fast5_dir / 'multi_read_fast5_files')])
+    assert 'one-read-per-file' in str(e.value)
+
+
+def test_realtime_on_real_fast5_files(fast5_dir, tmp_path, capsys):
+    """`deepbinner realtime --stop`: files are classified on the GPU and moved into barcodeNN/."""
+    import shutil
+    from deepbinner_b200 import deepbinner as cli
+    from deepbinner_b200 import realtime as rt
+    in_dir, out_dir = tmp_path / 'in', tmp_path / 'out'
+    shutil.copytree(fast5_dir / 'fast5_files', in_dir)
+    args = ['realtime', '--in_dir', str(in_dir), '--out_dir', str(out_dir), '--native', '--stop']
+    orig = rt.POLL_SECONDS
+    rt.POLL_SECONDS = 0
+    try:
+        import argparse
+        p = argparse.ArgumentParser()
+        sub = p.add_subparsers(dest='subparser_name')
+        cli.realtime_subparser(sub)
+        a = p.parse_args(args)
+        cli.check_classify_and_realtime_arguments(a)
+        rt.realtime(a, poll_seconds=0)
+    finally:
+        rt.POLL_SECONDS = orig
+    moved = {d.name: sorted(f.name for f in d.iterdir()) for d in out_dir.iterdir()}
+    assert {k: len(v) for k, v in moved.items()} == {'barcode01': 2, 'barcode02': 2, 'barcode03': 2, 'barcode12': 1}
+    assert list(in_dir.glob('*.fast5')) == []
