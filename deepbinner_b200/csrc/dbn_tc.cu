@@ -913,10 +913,14 @@ struct JobBuilder {
 
     // pack W[tap][cin][cout] -> two parts (K blocks [0, split) and [split, nkb), block kb = tap kb / ncb,
     // channel block kb % ncb), each part [hi blocks | lo blocks], block = [2 chunks][n rows][8] bf16
-    void pack_weights(int layer, int n, int cb0, int ncb, TcJob* J) {
+    // `layer2` (optional): a second conv with the same input and kernel size whose output channels
+    // are appended along N (rows cout .. cout + cout2 - 1): one MMA job computes both.
+    void pack_weights(int layer, int n, int cb0, int ncb, TcJob* J, int layer2 = 0) {
         const ConvSpec& s = kConvSpecs[layer];
         const int cout = s.cout ? s.cout : blob.n_classes;
         const float* k = blob.find("conv1d_" + std::to_string(layer) + "/kernel")->data;
+        const int cout2 = layer2 ? kConvSpecs[layer2].cout : 0;
+        const float* k2 = layer2 ? blob.find("conv1d_" + std::to_string(layer2) + "/kernel")->data : nullptr;
         const int nkb = s.k * ncb;
         const int split = nkb == 9 ? 5 : 2;
         const size_t blk = static_cast<size_t>(2) * n * 8;   // bf16 elements per K block
@@ -935,6 +939,7 @@ struct JobBuilder {
                             const int cin = (cb0 + cb) * 16 + j * 8 + e;
                             float v = 0.f;
                             if (row < cout && cin < s.cin) v = k[(t * s.cin + cin) * cout + row];
+                            else if (row < cout + cout2 && cin < s.cin) v = k2[(t * s.cin + cin) * cout2 + row - cout];
                             const uint16_t hi = bf16_rn(v);
                             const uint16_t lo = bf16_rn(v - bf16_to_float(hi));
                             const size_t idx = (static_cast<size_t>(kb - kb0) * 2 + j) * n * 8 + row * 8 + e;
@@ -949,10 +954,13 @@ struct JobBuilder {
     }
 
     // bias (padded to n) and, if bn > 0, the folded scale/shift of channels [ch0, ch0+48) of BN `bn`
-    void pack_params(int layer, int n, int bn, int ch0, TcJob* J) {
+    void pack_params(int layer, int n, int bn, int ch0, TcJob* J, int layer2 = 0) {
         const BlobTensor* t = blob.find("conv1d_" + std::to_string(layer) + "/bias");
+        const BlobTensor* t2 = layer2 ? blob.find("conv1d_" + std::to_string(layer2) + "/bias") : nullptr;
+        const int c1 = static_cast<int>(t->count);
         J->bias_off = static_cast<int>(prm.size());
-        for (int c = 0; c < n; ++c) prm.push_back(c < static_cast<int>(t->count) ? t->data[c] : 0.f);
+        for (int c = 0; c < n; ++c)
+            prm.push_back(c < c1 ? t->data[c] : (t2 && c - c1 < static_cast<int>(t2->count) ? t2->data[c - c1] : 0.f));
         J->bn_off = 0;
         if (bn > 0) {
             J->bn_off = static_cast<int>(prm.size());
@@ -963,9 +971,9 @@ struct JobBuilder {
 
     // generic conv job; in_* describe the input tensor, out_* the output tensor
     TcJob& add(int layer, int L, int in_off, int in_lp, int in_lo_delta, int kind, int bn, int out_off,
-               int out_cg_base) {
+               int out_cg_base, int layer2 = 0) {
         const ConvSpec& s = kConvSpecs[layer];
-        const int cout = s.cout ? s.cout : blob.n_classes;
+        const int cout = (s.cout ? s.cout : blob.n_classes) + (layer2 ? kConvSpecs[layer2].cout : 0);
         const bool pool = kind == EPI_N48_POOL_BN || kind == EPI_PARITY;
         TcJob J{};
         J.n = (cout + 15) / 16 * 16;
@@ -986,8 +994,8 @@ struct JobBuilder {
         J.out_ncg = cout / 8;
         J.out_lo_delta = J.out_ncg * J.out_lp * 16;
         J.out_cg_base = out_cg_base;
-        pack_weights(layer, J.n, 0, J.ncb, &J);
-        pack_params(layer, J.n, bn, kind == EPI_PARITY ? out_cg_base * 8 : 0, &J);
+        pack_weights(layer, J.n, 0, J.ncb, &J, layer2);
+        pack_params(layer, J.n, bn, kind == EPI_PARITY ? out_cg_base * 8 : 0, &J, layer2);
         jobs.push_back(J);
         return jobs.back();
     }
@@ -1004,15 +1012,15 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     B->add(7, 256, 0, 258, 24768, EPI_N48_POOL_BN, 3, 0, 0);      // -> [6][130][8], lo +12480
     B->add(8, 128, 0, 130, 12480, EPI_N48, 0, 0, 0);
     B->add(9, 128, 0, 130, 12480, EPI_N48_POOL_BN, 4, 0, 0).avgpool_after = 1;   // X [6][66][8], lo +6336
-    // inception block: X @0, P @12672 (later T15), T12 @25344, T14 @29568; Y (parity split, both
-    // windows) in window 0's region @43392;
+    // inception block: X @0, P @12672 (later T15), T1214 @25344 (conv1d_12 | conv1d_14 outputs as
+    // one 32-channel tensor: both are 1x1 convs of X, so ONE MMA job with N = 32 computes them); Y
+    // (parity split, both windows) in window 0's region @43392;
     // concat order [conv10, conv11, conv13, conv16] (network_architecture.py:68), BN5 per channel
     B->add(10, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 0).zero_y = 1;
     B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6);
-    B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 25344, 0);
-    B->add(13, 64, 25344, 66, 2112, EPI_PARITY, 5, 0, 12);
-    B->add(14, 64, 0, 66, 6336, EPI_N16, 0, 29568, 0);
-    B->add(15, 64, 29568, 66, 2112, EPI_N48, 0, 12672, 0);     // T15 reuses P's slot (P is dead)
+    B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 25344, 0, 14);      // -> [4][66][8], lo +4224
+    B->add(13, 64, 25344, 66, 4224, EPI_PARITY, 5, 0, 12);       // reads channel-groups 0-1 (conv1d_12)
+    B->add(15, 64, 25344 + 2 * 66 * 16, 66, 4224, EPI_N48, 0, 12672, 0);   // groups 2-3 (conv1d_14); T15 in P's slot
     B->add(16, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 18);
     // conv1d_17 .. conv1d_20 run on BOTH windows stacked in one tile (row = 18 w + position).
     // conv1d_17: stride 2 on the parity-split Y (tap0 = Ye[i], tap1 = Yo[i], tap2 = Ye[i+1]),
