@@ -302,3 +302,36 @@ def test_realtime_on_real_fast5_files(fast5_dir, tmp_path, capsys):
     moved = {d.name: sorted(f.name for f in d.iterdir()) for d in out_dir.iterdir()}
     assert {k: len(v) for k, v in moved.items()} == {'barcode01': 2, 'barcode02': 2, 'barcode03': 2, 'barcode12': 1}
     assert list(in_dir.glob('*.fast5')) == []
+
+
+def test_randomised_ragged_reads_against_oracle(models, oracle_weights, fixture_reads, multi_reads):
+    """Property-style sweep: reads of random length (0 .. 3 scan sizes) cut from real signals or drawn
+    from the synthetic recipe, both sides, several scan sizes and thresholds, odd batch sizes - calls
+    identical to the oracle and probabilities within 1e-3."""
+    _, sigs, _ = fixture_reads
+    _, msigs = multi_reads
+    pool = sigs + msigs
+    rng = np.random.RandomState(2024)
+    for trial, (name, side, scan, thr, n) in enumerate([
+            ('EXP-NBD103_read_starts', 'start', 6144, 0.5, 37), ('EXP-NBD103_read_ends', 'end', 6144, 0.5, 37),
+            ('SQK-RBK004_read_starts', 'start', 3072, 0.2, 21), ('EXP-NBD103_read_ends', 'end', 512, 0.9, 64),
+            ('EXP-NBD103_read_starts', 'end', 1536, 0.01, 19), ('SQK-RBK004_read_starts', 'start', 8192, 1.0, 5)]):
+        reads = []
+        for i in range(n):
+            kind = rng.randint(4)
+            length = int(rng.choice([0, 1, 2, 511, 512, 513, 1023, 1024, 1025, rng.randint(0, 3 * scan + 1)]))
+            if kind == 0:
+                reads.append(synthetic_signals(1, seed=trial * 1000 + i, length=length)[0])
+            else:
+                src = pool[rng.randint(len(pool))]
+                a = rng.randint(0, max(len(src) - length, 0) + 1)
+                reads.append(src[a:a + length].copy())
+        model = models[name]
+        ocalls, oprobs = orc.call_batch(oracle_weights[name], reads, side, scan, thr)
+        for eng in engines(model):
+            model.set_engine(eng)
+            calls, probs = model.call_batch(reads, side, scan, thr)
+            got = ['none' if c == 0 else str(int(c)) for c in calls]
+            err = np.abs(probs - np.array(oprobs, dtype=float)).max()
+            assert got == ocalls, (name, side, scan, eng)
+            assert err <= TOL, (name, side, scan, eng, err)
