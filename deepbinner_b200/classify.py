@@ -11,6 +11,7 @@ normalisation, CNN, step merge, renormalisation and call (reference classify.py:
 `.predict` (seam b1) still works through the generic host loop.
 """
 
+import concurrent.futures
 import os
 import pathlib
 import sys
@@ -109,11 +110,17 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
     input_size = start_input_size if use_start else end_input_size
     keep = int(args.scan_size) + input_size // 2
     classifications, read_id_to_fast5_file = {}, {}
-    for batch in chunker(fast5_files, args.batch_size):
+    # Each batch is parsed on native host threads (only the samples call_batch can look at - the
+    # first / last scan_size + input_size/2 - are kept, which gives identical calls); the parse of
+    # batch i+1 runs in the background (the C call releases the GIL) while batch i is on the GPU.
+    batches = list(chunker(fast5_files, args.batch_size))
+    prefetcher = concurrent.futures.ThreadPoolExecutor(max_workers=1)
+    pending = prefetcher.submit(load_batch, batches[0], keep)
+    for index, batch in enumerate(batches):
         read_ids, signals = [], []
-        # the whole batch is parsed on native host threads; only the samples call_batch can look at
-        # (first / last scan_size + input_size/2) are kept, which gives identical calls
-        loaded = load_batch(batch, keep)
+        loaded = pending.result()
+        if index + 1 < len(batches):
+            pending = prefetcher.submit(load_batch, batches[index + 1], keep)
         for fast5_file, (read_id, signal) in zip(batch, loaded):
             if signal is None:       # unreadable file: skipped, as in the reference (:135-136)
                 continue
@@ -152,6 +159,7 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
         print_classification_progress(len(classifications), len(fast5_files), 'fast5s',
                                       out_dest=out_dest)
 
+    prefetcher.shutdown()
     if full_output:
         print('', file=sys.stderr)
         if summary_table:
