@@ -2,23 +2,30 @@
 // network_architecture.py:18-95; executed by model.predict at classify.py:361).
 //
 // One CTA processes TWO windows.  All activations stay in shared memory as split-bf16 pairs
-// (hi = bf16(x), lo = bf16(x - hi)); every Conv1D from conv1d_2 to conv1d_20 is a sequence of
-// tcgen05.mma (kind::f16, M=128 positions x N=Cout x K=16) instructions that accumulate in fp32 in
-// tensor memory, issued by one thread.  A k=3 'same' convolution is three accumulating MMAs per
+// (hi = bf16_rn(x), lo = upper half of the exact remainder x - hi); every Conv1D from conv1d_2 to
+// conv1d_20 is a sequence of tcgen05.mma (kind::f16, M=128 positions x N=Cout x K=16) instructions
+// accumulating in fp32 in tensor memory.  A k=3 'same' convolution is three accumulating MMAs per
 // 16-channel block over the SAME shared-memory tile: activations are stored [C/8][L+2][8] (one
 // 16-byte row per position and channel-group, zero halo rows), which is the canonical K-major
 // no-swizzle UMMA layout, so a tap shift is a +16 B start-address offset in the descriptor - no
-// im2col is ever materialised.  Precision: three MMA terms per block (A_hi*W_hi + A_lo*W_hi +
-// A_hi*W_lo) give ~16 mantissa bits on both operands, which SURVEY Appendix C shows is needed for
-// the 1e-3 probability bar (single bf16 fails, fp16 overflows).
+// im2col is ever materialised.  Precision: three MMA terms per K block (A_hi*W_hi, A_hi*W_lo with
+// A_hi reused from the tensor core's collector buffer, A_lo*W_hi) give ~16 mantissa bits on both
+// operands, which SURVEY Appendix C shows is needed for the 1e-3 probability bar (single bf16
+// fails, fp16 overflows).
 //
 // A whole layer's output for one window (up to 4 tiles x 48 fp32 columns) lives in TMEM, so the
 // epilogue (bias, ReLU, [MaxPool2], [BatchNorm affine], hi/lo split) can overwrite the layer's
 // input in place once its MMAs have completed; the two windows of a CTA alternate so that the
-// tensor pipe works on one while the 4 epilogue warps drain the other.
+// tensor pipe works on one while the epilogue warps drain the other.  The network is a table of 21
+// MMA jobs in constant memory (conv1d_12 + conv1d_14 share one job; conv1d_17 is four K-slices);
+// from conv1d_17 on both windows are stacked in ONE M=128 tile (row = 18 w + position).
 //
-// Warp roles: warps 0-3 = epilogue / CUDA-core stages (conv1d_1, average pool, softmax head),
-// warp 4 = TMEM allocator, weight loader (cp.async.bulk + mbarrier) and MMA issuer.
+// Warp roles (448 threads): warp 0 = TMEM allocator + MMA issuer (one elected lane, operands on
+// the uniform datapath), warp 1 = weight loader (cp.async.bulk + mbarrier; each job's weights come
+// in two K-block parts so the next job's first part streams in while the second is still in use),
+// warps 2-13 = epilogue (TMEM lane quadrant = warp % 4, 16 accumulator columns per warp) and the
+// CUDA-core stages (z-score + conv1d_1, average pool, softmax head).  The control warps have the
+// lowest warp ids because the scheduler favours higher ones.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
