@@ -335,3 +335,110 @@ def test_randomised_ragged_reads_against_oracle(models, oracle_weights, fixture_
             err = np.abs(probs - np.array(oprobs, dtype=float)).max()
             assert got == ocalls, (name, side, scan, eng)
             assert err <= TOL, (name, side, scan, eng, err)
+
+
+def random_model_blob(n_classes, seed):
+    """A DBNW blob of the Deepbinner topology with random (He-style) weights and `n_classes` outputs
+    (reference tests/test_network_architecture.py builds 13- and 25-class networks)."""
+    from deepbinner_b200 import weights
+    rng = np.random.RandomState(seed)
+    tensors = {}
+    for name, k, s, cin, cout in weights.CONV_SPECS:
+        cout = n_classes if cout is None else cout
+        tensors[name + '/kernel'] = (rng.randn(k, cin, cout) * np.sqrt(2.0 / (k * cin))).astype(np.float32)
+        tensors[name + '/bias'] = (rng.randn(cout) * 0.1).astype(np.float32)
+    for i, ch in enumerate(weights.BN_CHANNELS, start=1):
+        n = 'batch_normalization_{}'.format(i)
+        tensors[n + '/gamma'] = rng.uniform(0.5, 2.0, ch).astype(np.float32)
+        tensors[n + '/beta'] = (rng.randn(ch) * 0.2).astype(np.float32)
+        tensors[n + '/moving_mean'] = (rng.randn(ch) * 0.5).astype(np.float32)
+        tensors[n + '/moving_variance'] = rng.uniform(0.2, 3.0, ch).astype(np.float32)
+    return weights.pack_blob(1024, n_classes, tensors)
+
+
+@pytest.mark.parametrize('n_classes', [5, 13, 25])
+def test_other_class_counts_with_random_weights(n_classes, tmp_path, fixture_reads):
+    from deepbinner_b200 import _native, weights
+    from deepbinner_b200.model import B200Model
+    blob = random_model_blob(n_classes, seed=n_classes)
+    assert weights.parameter_count(blob) == {5: 106805, 13: 107197, 25: 107785}[n_classes]   # test_network_architecture.py:37,47
+    path = tmp_path / 'm.dbnw'
+    path.write_bytes(blob)
+    model = B200Model(str(path))
+    assert int(model.outputs[0].shape[1]) == n_classes
+    w = orc.load_weights(str(path))
+    _, sigs, _ = fixture_reads
+    x = np.concatenate([orc.make_windows(sigs, 1024, s, 'start') for s in (0, 3)]
+                       + [sliding_windows(sigs, 50, seed=n_classes)])
+    ref = orc.forward(w, x.astype(np.float32))
+    names = engines(model)
+    if n_classes > 16:     # the tensor-core head handles at most 16 classes; the fp32 engine any
+        assert names == ['fp32'] and model.engine == 'fp32'
+        with pytest.raises(_native.NativeError):
+            model.set_engine('tcgen05')
+    else:
+        assert 'tcgen05' in names
+    for eng in names:
+        model.set_engine(eng)
+        got = model.predict(x)
+        assert got.shape == ref.shape and np.abs(got - ref).max() <= TOL
+        ocalls, oprobs = orc.call_batch(w, sigs, 'start', 2048, 0.3)
+        calls, probs = model.call_batch(sigs, 'start', 2048, 0.3)
+        assert ['none' if c == 0 else str(int(c)) for c in calls] == ocalls
+        assert np.abs(probs - np.array(oprobs, dtype=float)).max() <= TOL
+
+
+def _oracle_call_batch_torch(path, reads, side, scan, thr):
+    """call_batch with the torch-CPU fp32 oracle as the network (fast enough for full-size configs)."""
+    from oracle.torch_cpu import TorchCpuModel
+    net = TorchCpuModel(path)
+    steps = [net.predict(orc.make_windows(reads, 1024, s, side)) for s in range(scan // 512)]
+    merged = orc.merge_steps(steps)
+    calls, probs = [], []
+    for row in merged:
+        p = orc.make_sum_to_one(list(row))
+        probs.append(p)
+        calls.append(orc.get_barcode_call_from_probabilities(p, thr))
+    return calls, np.array(probs, dtype=float)
+
+
+def test_baseline_config2_native_preset_batch256(models, fixture_reads, multi_reads):
+    """BASELINE.json configs[1]: EXP-NBD103 start+end models, combined calls, batch 256 (6 144
+    windows per batch) - full size, against the CPU oracle; reads are a mix of real fixture reads
+    (barcoded) and synthetic no-barcode signals."""
+    from deepbinner_b200 import classify as cls
+    _, sigs, _ = fixture_reads
+    _, msigs = multi_reads
+    reads = (sigs + msigs) * 4 + synthetic_signals(256 - 4 * 37, seed=9, length=list(
+        np.random.RandomState(9).randint(2000, 30000, 256 - 4 * 37)))
+    assert len(reads) == 256
+    ids = ['r%d' % i for i in range(256)]
+    args = make_args(batch_size=256, require_either=True)
+    start, end = models['EXP-NBD103_read_starts'], models['EXP-NBD103_read_ends']
+    oc_s, op_s = _oracle_call_batch_torch(model_path('EXP-NBD103_read_starts'), reads, 'start', 6144, 0.5)
+    oc_e, op_e = _oracle_call_batch_torch(model_path('EXP-NBD103_read_ends'), reads, 'end', 6144, 0.5)
+    expected = [orc.combine_calls(a, b, require_either=True) for a, b in zip(oc_s, oc_e)]
+    for eng in engines(start):
+        start.set_engine(eng)
+        end.set_engine(eng)
+        cs, ps = cls.call_batch(1024, 13, ids, reads, start, args, 'start')
+        ce, pe = cls.call_batch(1024, 13, ids, reads, end, args, 'end')
+        assert cs == oc_s and ce == oc_e
+        assert [cls.combine_calls(a, b, args) for a, b in zip(cs, ce)] == expected
+        assert np.abs(np.array(ps) - op_s).max() <= TOL and np.abs(np.array(pe) - op_e).max() <= TOL
+    assert len(set(expected)) >= 4     # several barcodes and 'none' are present in the batch
+
+
+def test_baseline_config3_rapid_model_batch512(models, fixture_reads, multi_reads):
+    """BASELINE.json configs[2]: SQK-RBK004_read_starts, batch 512 (6 144 windows) - full size."""
+    _, sigs, _ = fixture_reads
+    _, msigs = multi_reads
+    reads = (sigs + msigs) * 8 + synthetic_signals(512 - 8 * 37, seed=10, length=4000)
+    assert len(reads) == 512
+    model = models['SQK-RBK004_read_starts']
+    ocalls, oprobs = _oracle_call_batch_torch(model_path('SQK-RBK004_read_starts'), reads, 'start', 6144, 0.5)
+    for eng in engines(model):
+        model.set_engine(eng)
+        calls, probs = model.call_batch(reads, 'start', 6144, 0.5)
+        assert ['none' if c == 0 else str(int(c)) for c in calls] == ocalls
+        assert np.abs(probs - oprobs).max() <= TOL
