@@ -168,13 +168,9 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
 
 
 def load_batch(fast5_batch, keep):
-    """[(read_id, signal)] for a batch of files.  Indirection point: tests substitute the loader."""
-    if get_read_id_and_signal is not _DEFAULT_SINGLE_LOADER:    # a test / caller patched the loader
-        return [get_read_id_and_signal(f) for f in fast5_batch]
+    """[(read_id, signal) or (None, None)] for a batch of fast5 files, parsed on native host threads
+    (reference classify.py:133-139 calls get_read_id_and_signal per file)."""
     return read_fast5_batch(fast5_batch, keep=keep)
-
-
-_DEFAULT_SINGLE_LOADER = get_read_id_and_signal
 
 
 def classify_training_data(input_file, start_model, start_input_size, end_model, end_input_size,

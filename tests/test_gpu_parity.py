@@ -175,8 +175,8 @@ def test_classify_fast5_files_end_to_end(models, fixture_reads, reference_golden
     from deepbinner_b200 import classify as cls
     ids, sigs, names = fixture_reads
     table = {n: (i, s) for n, i, s in zip(names, ids, sigs)}
-    monkeypatch.setattr(cls, 'get_read_id_and_signal',
-                        lambda f: table.get(str(f).split('/')[-1], (None, None)))
+    monkeypatch.setattr(cls, 'load_batch',
+                        lambda batch, keep: [table.get(str(f).split('/')[-1], (None, None)) for f in batch])
     monkeypatch.setattr(cls, 'determine_single_or_multi_fast5s', lambda files: 'single')
     start, end = models['EXP-NBD103_read_starts'], models['EXP-NBD103_read_ends']
     files = ['/x/' + n for n in names] + ['/x/unreadable.fast5']
