@@ -14,7 +14,8 @@ import pathlib
 import numpy as np
 
 _PKG = pathlib.Path(__file__).resolve().parent
-LIB_PATH = _PKG / 'libdeepbinner_b200.so'
+# DEEPBINNER_B200_LIB: load a differently built copy of the same library (kernel A/B experiments)
+LIB_PATH = pathlib.Path(os.environ.get('DEEPBINNER_B200_LIB') or _PKG / 'libdeepbinner_b200.so')
 
 DBN_OK = 0
 SIDE_START, SIDE_END = 0, 1

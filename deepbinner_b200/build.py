@@ -31,20 +31,26 @@ def needs_build():
     return any(d.stat().st_mtime > t for d in deps)
 
 
-def build_library(force=False, verbose=False):
-    if not force and not needs_build():
+def build_library(force=False, verbose=False, defines=(), out=None):
+    """`defines` / `out`: build an experimental variant (-D macros) next to the default library."""
+    out = pathlib.Path(out) if out else LIB
+    if not force and out == LIB and not needs_build():
         return str(LIB)
     cmd = [_nvcc()] + [f for f in NVCC_FLAGS if f != '--use_fast_math=false']
+    cmd += ['-D' + d for d in defines]
     if verbose:
         cmd += ['-Xptxas', '-v']
-    cmd += [str(CSRC / s) for s in SOURCES] + ['-lz', '-o', str(LIB)]
+    cmd += [str(CSRC / s) for s in SOURCES] + ['-lz', '-o', str(out)]
     proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
     if proc.returncode != 0:
         raise RuntimeError('nvcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout)
     if verbose:
         print(proc.stdout)
-    return str(LIB)
+    return str(out)
 
 
 if __name__ == '__main__':
-    print(build_library(force='--force' in sys.argv, verbose='-v' in sys.argv))
+    defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
+    outs = [a[6:] for a in sys.argv[1:] if a.startswith('--out=')]
+    print(build_library(force='--force' in sys.argv or bool(defs), verbose='-v' in sys.argv, defines=defs,
+                        out=outs[0] if outs else None))

@@ -1,0 +1,312 @@
+// tcgen05 micro-benchmarks used to size the engine's schedule (not part of the product path):
+//   1. burst latency: n K-blocks x 3 MMAs (the engine's hi/lo pattern) + commit + mbarrier wait,
+//      for M in {128, 64} and several N - gives the fixed start-up/commit cost and the marginal
+//      cost per MMA of a shape;
+//   2. hand-off latency MMA -> commit -> epilogue warp (tcgen05.ld) -> mbarrier arrive -> issuer;
+//   3. TMEM lane layout of an M=64 accumulator (which lanes hold which rows).
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -o tools/tc_microbench tools/tc_microbench.cu
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstdlib>
+#include <vector>
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+    return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 24)) __trap();
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_commit(uint32_t bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+template <int COLL>
+__device__ __forceinline__ void tc_mma(uint32_t d, uint64_t ad, uint64_t bd, uint32_t idesc, uint32_t acc) {
+    if (COLL == 1)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                     "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+    else if (COLL == 2)
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}" ::"r"(d),
+                     "l"(ad), "l"(bd), "r"(idesc), "r"(acc) : "memory");
+    else
+        asm volatile("{\n\t.reg .pred p;\n\tsetp.ne.b32 p, %4, 0;\n\t"
+                     "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}" ::"r"(d), "l"(ad), "l"(bd),
+                     "r"(idesc), "r"(acc) : "memory");
+}
+__device__ __forceinline__ void tmem_ld8(uint32_t taddr, uint32_t* r) {
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+                 : "r"(taddr) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+__device__ __forceinline__ uint64_t make_desc16(uint32_t addr16, uint32_t lbo16) {
+    return (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(lbo16 & 0x3FFF) << 16) |
+           static_cast<uint64_t>(addr16 & 0x3FFF);
+}
+__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
+           (static_cast<uint32_t>(m >> 4) << 24);
+}
+
+constexpr int kRows = 514;                 // activation rows per channel group (as conv1d_2..4)
+constexpr int kActArr = 6 * kRows * 16;    // one array (hi or lo), 6 channel groups
+constexpr int kSmemA = 0;                  // hi at 0, lo at kActArr
+constexpr int kSmemB = 2 * kActArr;        // weights: up to 9 K blocks x (hi, lo) x 2 x 128 rows x 16 B
+constexpr int kSmemBBytes = 9 * 2 * 2 * 128 * 16;
+constexpr int kSmemBar = kSmemB + kSmemBBytes;
+constexpr int kSmemBytes = kSmemBar + 64;
+
+struct Result {
+    long long t_issue, t_done, t_roundtrip;
+};
+
+
+__device__ __forceinline__ uint32_t elect_one() {
+    uint32_t pred = 0;
+    asm volatile("{\n\t.reg .b32 rx;\n\t.reg .pred px;\n\telect.sync rx|px, 0xffffffff;\n\t@px mov.s32 %0, 1;\n\t}" : "+r"(pred));
+    return pred;
+}
+
+// Fully unrolled issue of TILES x NKB K blocks x 3 MMAs (the engine's pattern), warp-uniform operands.
+template <int M, int N, int NKB, int TILES, int COLL>
+__device__ __forceinline__ void issue_burst(uint32_t sbase) {
+    const uint32_t idesc = make_idesc(M, N);
+    const uint64_t a_word = (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(kRows) << 16);
+    const uint64_t b_word = (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(N) << 16);
+    const uint32_t a0 = (sbase + kSmemA) >> 4, b0 = (sbase + kSmemB) >> 4;
+    constexpr int kTileStride = N > 64 ? 128 : 64;
+#pragma unroll
+    for (int tile = 0; tile < TILES; ++tile) {
+#pragma unroll
+        for (int kb = 0; kb < NKB; ++kb) {
+            const int t = kb / 3, cb = kb % 3;
+            const uint32_t a16 = a0 + tile * 128 + t + 2 * cb * kRows;
+            const uint64_t ad = a_word | (a16 & 0x3FFF), al = a_word | ((a16 + (kActArr >> 4)) & 0x3FFF);
+            const uint32_t b16 = b0 + (kb % 2) * 2 * N;   // two alternating weight blocks (keeps N = 256 inside the buffer)
+            const uint64_t bh = b_word | (b16 & 0x3FFF), bl = b_word | ((b16 + 2 * 2 * N) & 0x3FFF);
+            if (COLL) {
+                tc_mma<1>(tile * kTileStride, ad, bh, idesc, kb ? 1u : 0u);
+                tc_mma<2>(tile * kTileStride, ad, bl, idesc, 1u);
+            } else {
+                tc_mma<0>(tile * kTileStride, ad, bh, idesc, kb ? 1u : 0u);
+                tc_mma<0>(tile * kTileStride, ad, bl, idesc, 1u);
+            }
+            tc_mma<0>(tile * kTileStride, al, bh, idesc, 1u);
+        }
+    }
+}
+
+// MODE 0: burst (issue, commit, wait).  MODE 1: burst + epilogue-warp round trip.
+// MODE 2: two-term variant (A_hi x W and A_lo x W only) for reference.
+template <int M, int N, int NKB, int TILES, int COLL, int MODE>
+__global__ void __launch_bounds__(160, 1) k_burst(int reps, Result* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_mma = sbase + kSmemBar, bar_epi = sbase + kSmemBar + 8;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 32);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    for (int i = threadIdx.x; i < kSmemBar / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_epi, 32);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemBar + 32), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    if (warp == 0) {
+        if (tmem != 0) __trap();
+        if (elect_one()) {
+            long long best_issue = 1ll << 60, best_done = 1ll << 60, best_rt = 1ll << 60;
+            uint32_t ph = 0;
+            for (int rep = 0; rep < reps; ++rep) {
+                const long long t0 = clock64();
+                issue_burst<M, N, NKB, TILES, COLL>(sbase);
+                const long long t1 = clock64();
+                tc_commit(bar_mma);
+                if (MODE == 0) {
+                    mbar_wait(bar_mma, ph);
+                    const long long t2 = clock64();
+                    if (t1 - t0 < best_issue) best_issue = t1 - t0;
+                    if (t2 - t0 < best_done) best_done = t2 - t0;
+                } else {
+                    mbar_wait(bar_epi, ph);
+                    const long long t2 = clock64();
+                    if (t2 - t0 < best_rt) best_rt = t2 - t0;
+                }
+                ph ^= 1;
+                tc_fence_after();
+            }
+            out->t_issue = best_issue;
+            out->t_done = best_done;
+            out->t_roundtrip = best_rt;
+        }
+    } else if (warp == 1 && MODE == 1) {
+        uint32_t ph = 0;
+        for (int rep = 0; rep < reps; ++rep) {
+            mbar_wait(bar_mma, ph);
+            ph ^= 1;
+            tc_fence_after();
+            uint32_t r[8];
+            tmem_ld8(tmem + (32u << 16), r);   // warp 1 -> lane quadrant 1
+            tmem_wait_ld();
+            if (r[0] == 0x12345678u) out->t_issue = 0;
+            tc_fence_before();
+            mbar_arrive(bar_epi);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+// layout probe: A row r = (r + 1) in k = 0 (other k zero), B col c = 1 in k = 0 -> D[r][c] = r + 1
+__global__ void __launch_bounds__(128, 1) k_layout(int M, int N, int dlane, float* out /*[128 lanes][8]*/) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_mma = sbase + kSmemBar;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 32);
+    const int warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < kSmemBar / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0;
+    __syncthreads();
+    __nv_bfloat16* A = reinterpret_cast<__nv_bfloat16*>(smem + kSmemA);
+    __nv_bfloat16* B = reinterpret_cast<__nv_bfloat16*>(smem + kSmemB);
+    for (int r = threadIdx.x; r < 128; r += blockDim.x) {
+        A[r * 8] = __float2bfloat16(static_cast<float>(r + 1));   // channel group 0, row r, element 0
+        B[r * 8] = __float2bfloat16(1.0f);
+    }
+    if (threadIdx.x == 0) {
+        mbar_init(bar_mma, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemBar + 32), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    // clear the accumulator lanes first with an M=128 product of zeros so stale TMEM cannot confuse us
+    if (threadIdx.x == 0) {
+        const uint64_t zd = make_desc16((sbase + kSmemA + 64 * 1024) >> 4, kRows);   // zero area
+        tc_mma<0>(tmem, zd, zd, make_idesc(128, N), 0u);
+        const uint64_t ad = make_desc16((sbase + kSmemA) >> 4, kRows);
+        const uint64_t bd = make_desc16((sbase + kSmemB) >> 4, N);
+        tc_mma<0>(tmem + (static_cast<uint32_t>(dlane) << 16), ad, bd, make_idesc(M, N), 0u);
+        tc_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    uint32_t r[8];
+    tmem_ld8(tmem + (static_cast<uint32_t>(warp * 32) << 16), r);
+    tmem_wait_ld();
+    for (int c = 0; c < 8; ++c) out[threadIdx.x * 8 + c] = __uint_as_float(r[c]);
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+#define CK(x)                                                                              \
+    do {                                                                                   \
+        cudaError_t e_ = (x);                                                              \
+        if (e_ != cudaSuccess) {                                                           \
+            std::printf("CUDA error %s at %s:%d\n", cudaGetErrorString(e_), __FILE__, __LINE__); \
+            std::exit(1);                                                                  \
+        }                                                                                  \
+    } while (0)
+
+
+static Result* d_res;
+template <int M, int N, int NKB, int TILES, int COLL, int MODE>
+static void run_burst() {
+    CK(cudaFuncSetAttribute(k_burst<M, N, NKB, TILES, COLL, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    k_burst<M, N, NKB, TILES, COLL, MODE><<<1, 160, kSmemBytes>>>(20, d_res);
+    CK(cudaDeviceSynchronize());
+    Result r;
+    CK(cudaMemcpy(&r, d_res, sizeof(r), cudaMemcpyDeviceToHost));
+    const int mmas = 3 * NKB * TILES;
+    if (MODE == 0)
+        std::printf("burst M %3d N %3d nkb %d tiles %d coll %d | %3d MMAs | issue %6lld done %6lld | %.1f cyc/MMA\n", M, N, NKB,
+                    TILES, COLL, mmas, r.t_issue, r.t_done, mmas ? static_cast<double>(r.t_done) / mmas : 0.0);
+    else
+        std::printf("roundtrip M %3d N %3d nkb %d tiles %d | %lld cycles\n", M, N, NKB, TILES, r.t_roundtrip);
+}
+template <int M, int N>
+static void run_shape() {
+    run_burst<M, N, 0, 1, 0, 0>();
+    run_burst<M, N, 1, 1, 1, 0>();
+    run_burst<M, N, 3, 1, 1, 0>();
+    run_burst<M, N, 9, 1, 1, 0>();
+    run_burst<M, N, 9, 1, 0, 0>();
+    if (M == 128 && N <= 128) run_burst<M, N, 9, 4, 1, 0>();
+    if (M == 128 && N <= 128) run_burst<M, N, 9, 4, 0, 0>();
+}
+
+int main() {
+    CK(cudaFuncSetAttribute(k_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
+    CK(cudaMalloc(&d_res, sizeof(Result)));
+    run_shape<128, 48>();
+    run_shape<64, 48>();
+    run_shape<128, 16>();
+    run_shape<64, 16>();
+    run_shape<128, 32>();
+    run_shape<128, 96>();
+    run_shape<64, 96>();
+    run_shape<128, 128>();
+    run_shape<128, 192>();
+    run_shape<128, 256>();
+    run_burst<128, 48, 0, 1, 1, 1>();
+    run_burst<128, 48, 1, 1, 1, 1>();
+    run_burst<128, 48, 3, 1, 1, 1>();
+    run_burst<128, 48, 9, 1, 1, 1>();
+    float* d_out;
+    CK(cudaMalloc(&d_out, 128 * 8 * 4));
+    for (int cfg = 0; cfg < 4; ++cfg) {
+        const int M = cfg == 0 ? 128 : 64, dlane = cfg == 2 ? 16 : (cfg == 3 ? 64 : 0);
+        CK(cudaMemset(d_out, 0, 128 * 8 * 4));
+        k_layout<<<1, 128, kSmemBytes>>>(M, 16, dlane, d_out);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) {
+            std::printf("# layout M=%d dlane=%d: CUDA error %s\n", M, dlane, cudaGetErrorString(e));
+            return 0;
+        }
+        std::vector<float> h(128 * 8);
+        CK(cudaMemcpy(h.data(), d_out, h.size() * 4, cudaMemcpyDeviceToHost));
+        std::printf("# layout M=%d D lane offset %d: lane -> row+1 (column 0)\n", M, dlane);
+        for (int l = 0; l < 128; ++l) std::printf("%g%s", h[l * 8], (l % 32 == 31) ? "\n" : " ");
+    }
+    return 0;
+}

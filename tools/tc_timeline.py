@@ -32,14 +32,14 @@ def main():
     misc = trace[31].reshape(-1)
     t0 = misc[0] if misc[0] > 0 else trace[:nj][trace[:nj] > 0].min()
     print('kernel start 0 | conv1 w0 done {} | conv1 w1 done {}'.format(int(misc[1] - t0), int(misc[2] - t0)))
-    print('job      win | mma_issue_start issue_end | epi_start epi_end | issue_dur epi_dur | epi: params tmem compute fence')
+    print('job      win | mma_issue_start issue_end | epi_start epi_end | issue_dur epi_dur | epi: params tmem compute fence | mma: wfull0 part0 wfull1 part1')
     for j in range(nj):
         for w in range(2):
             a, b, c, d, e4, e5, e6, e7 = [int(v - t0) if v > 0 else -1 for v in trace[j, w][:8]]
             x8, x9, x10 = [int(v - t0) if v > 0 else -1 for v in trace[j, w][8:11]]
-            print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d} | {:5d} {:5d} {:5d} {:5d} {:5d}'.format(
+            print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d} | {:5d} {:5d} {:5d} {:5d} {:5d} | {:5d} {:5d} {:5d} {:5d}'.format(
                 NAMES[j], w, a, b, c, d, b - a, (d - c) if c >= 0 else -1,
-                e4 - c, e5 - e4, e6 - e5, e7 - e6, d - e7))
+                e4 - c, e5 - e4, e6 - e5, e7 - e6, d - e7, x8 - a, x9 - x8, x10 - x9, b - x10))
     print('total', int(trace[:nj].max() - t0))
 
 
