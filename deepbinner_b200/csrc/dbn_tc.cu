@@ -46,7 +46,7 @@ namespace dbn {
 // The warp scheduler favours higher warp ids, so the two single-lane control warps get the LOWEST
 // ids: their issue / spin loops then only take slots the epilogue warps leave idle.
 #ifndef DBN_TC_CONTROL_HIGH
-#define DBN_TC_CONTROL_HIGH 0
+#define DBN_TC_CONTROL_HIGH 1
 #endif
 constexpr int kEpiWarps = 12;
 #if DBN_TC_CONTROL_HIGH
@@ -70,7 +70,7 @@ constexpr int kSmemAct1 = kActBytes;
 constexpr int kSmemWbuf = 2 * kActBytes;
 constexpr int kSmemPrm = kSmemWbuf + kWbufBytes;
 constexpr int kSmemBar = kSmemPrm + kPrmFloats * 4;   // mbarriers, tmem pointer, reduction scratch
-constexpr int kTcSmemBytes = kSmemBar + 384;
+constexpr int kTcSmemBytes = kSmemBar + 384;   // [0,72) mbarriers, 96 TMEM pointer, [128,320) reduction scratch, [320,384) joint rings
 static_assert(kTcSmemBytes <= 232448, "shared memory budget");
 constexpr int kTmemCols = 512;
 constexpr int kTmemWindowCols = 256;
@@ -96,26 +96,42 @@ enum EpiKind {
     EPI_HEAD = 5          // bias + ReLU + global average pool + softmax
 };
 
+// Joint jobs (conv1d_10 onwards) serve BOTH windows of the CTA in one MMA burst and one epilogue pass:
+//   JOINT_PAIR  (inception block, L = 64): one M=64 MMA set per window into the SAME accumulator
+//               columns, window 0 in TMEM lanes 0-15 and window 1 in lanes 16-31 of every lane
+//               quadrant (a D lane offset of 16 is honoured for M=64; measured with
+//               tools/tc_microbench.cu), so each epilogue warp drains 16 rows of either window;
+//   JOINT_STACK (conv1d_17 onwards): both windows stacked in one tensor (row = 18 w + position) in
+//               window 0's region, one M=64 MMA set (conv1d_20: M=128, head epilogue).
+// Joint jobs rotate over three accumulator slots and carry `need` = number of joint epilogues that
+// must have completed before their MMAs may be issued (input produced / slot drained), so the
+// tensor pipe runs up to two jobs ahead of the epilogue warps where the graph allows it.
+enum JointKind { JOINT_NONE = 0, JOINT_PAIR = 1, JOINT_STACK = 2 };
+
 struct alignas(128) TcJob {
     int n;            // MMA N (Cout padded to a multiple of 16)
-    int cout;         // real Cout
+    int idesc;        // tcgen05 instruction descriptor (the host builder keeps M here until finalize_jobs())
     int ntiles;       // M tiles of 128 positions
     int L;            // valid positions
     int lp;           // rows per channel-group of the input tensor
     int ntaps;
-    int tap_off[3];   // byte offset (from the window's ACT base) of row 0 of each tap, hi array
-    int lo_delta;     // bytes from hi array to lo array of the input
+    int tap16[3];     // offset (from the window's ACT base) of row 0 of each tap, hi array, in 16-byte units
+    int lo16;         // distance from the hi array to the lo array of the input, in 16-byte units
+                      // (the host builder keeps byte offsets in tap16 / lo16 until finalize_jobs())
     int ncb;          // 16-channel K blocks per tap handled by this job
     int cb0;          // first K block (conv1d_17 is split in 4 jobs)
     int w_goff;       // byte offset of this job's packed weights in global memory ([part 0 | part 1])
-    int kb_split;     // K blocks [0, kb_split) are weight part 0, [kb_split, ntaps*ncb) part 1
+    int tcol;         // joint jobs: first accumulator column (slot * 64)
     int w_part[2];    // bytes of each part; a part is [hi blocks | lo blocks] of its K-block range
     int first, last;  // first: zero the accumulators; last: run the epilogue
     // epilogue
     int kind, bias_off, bn_off;  // float offsets into the smem parameter block
     int out_off, out_lp, out_lo_delta, out_cg_base, out_ncg, out_L;
-    int avgpool_after, zero_y;
-    int stack;        // 1: both windows stacked in one tile (single pass); 2: first such job (joins windows)
+    int edge15;       // scale the accumulators of the first / last position by 1.5 (folded average pool)
+    int zero_y;
+    int joint;        // JointKind
+    int need;         // joint jobs: joint epilogues that must be complete before the MMAs are issued
+    int eseq;         // joint jobs with an epilogue: index of that epilogue in the joint sequence (else -1)
 };
 
 __constant__ TcJob c_jobs[kMaxJobs];
@@ -123,8 +139,11 @@ static_assert(sizeof(TcJob) == 128, "one job descriptor = two 64-byte constant-c
 
 // Touch both constant-cache lines of a job descriptor so that the accesses made one job later hit
 // (the volatile asm consumes the values, which pins the two LDCs at this point of the program).
+#ifndef DBN_TC_PREFETCH_JOB
+#define DBN_TC_PREFETCH_JOB 1
+#endif
 __device__ __forceinline__ void prefetch_job(int j) {
-    if (j < kMaxJobs) asm volatile("" ::"r"(c_jobs[j].n), "r"(c_jobs[j].zero_y));
+    if (DBN_TC_PREFETCH_JOB && j < kMaxJobs) asm volatile("" ::"r"(c_jobs[j].n), "r"(c_jobs[j].eseq));
 }
 
 struct TcParams {
@@ -155,8 +174,22 @@ __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
 }
+#ifndef DBN_TC_WAIT_HINT_NS
+#define DBN_TC_WAIT_HINT_NS 2000
+#endif
 __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
     uint32_t ok;
+#if DBN_TC_WAIT_HINT_NS > 0
+    // suspend-time hint: a waiting warp sleeps in hardware until the phase completes (or the hint
+    // expires) instead of re-issuing the poll, leaving issue slots to the warps that have work
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity), "r"(DBN_TC_WAIT_HINT_NS)
+        : "memory");
+#else
     asm volatile(
         "{\n\t.reg .pred p;\n\t"
         "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
@@ -164,6 +197,7 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
         : "=r"(ok)
         : "r"(bar), "r"(parity)
         : "memory");
+#endif
     return ok != 0;
 }
 // Bounded wait: a protocol bug must become a trap (reported as a CUDA error), never a hang.
@@ -199,9 +233,16 @@ __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols)
                  : "memory");
 }
-__device__ __forceinline__ void tc_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar)
-                 : "memory");
+// `leader`: the MMA warp runs its control flow converged on all 32 lanes (so that ptxas keeps the
+// descriptor arithmetic on the uniform datapath) and only the tcgen05 instructions themselves are
+// predicated on the one elected lane.
+__device__ __forceinline__ void tc_commit(uint32_t bar, uint32_t leader = 1) {
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "setp.ne.b32 q, %1, 0;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}" ::"r"(bar),
+        "r"(leader)
+        : "memory");
 }
 // D[tmem] (+)= A[smem] * B[smem], bf16 inputs, fp32 accumulate.  Issued by the one elected lane of
 // the MMA warp from a warp-uniform region, so ptxas keeps the descriptor arithmetic on the uniform
@@ -210,27 +251,30 @@ __device__ __forceinline__ void tc_commit(uint32_t bar) {
 // (take A from the collector buffer instead of re-reading shared memory).
 template <int COLL>
 __device__ __forceinline__ void tc_mma(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
-                                       uint32_t accumulate) {
+                                       uint32_t accumulate, uint32_t leader) {
     if (COLL == 1)
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
+            "{\n\t.reg .pred p, q;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            "setp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::fill [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
             : "memory");
     else if (COLL == 2)
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
+            "{\n\t.reg .pred p, q;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            "setp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16.collector::a::lastuse [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
             : "memory");
     else
         asm volatile(
-            "{\n\t.reg .pred p;\n\t"
+            "{\n\t.reg .pred p, q;\n\t"
             "setp.ne.b32 p, %4, 0;\n\t"
-            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
-            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            "setp.ne.b32 q, %5, 0;\n\t"
+            "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+            ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(leader)
             : "memory");
 }
 __device__ __forceinline__ uint32_t elect_one() {
@@ -282,7 +326,7 @@ __device__ __forceinline__ uint64_t make_desc16(uint32_t addr16, uint32_t lbo16)
            static_cast<uint64_t>(addr16 & 0x3FFF);
 }
 // Instruction descriptor (cute::UMMA::InstrDescriptor): fp32 accumulate, bf16 A/B, both K-major.
-__device__ __forceinline__ uint32_t make_idesc(int m, int n) {
+__host__ __device__ __forceinline__ uint32_t make_idesc(int m, int n) {
     return (1u << 4) | (1u << 7) | (1u << 10) | (static_cast<uint32_t>(n >> 3) << 17) |
            (static_cast<uint32_t>(m >> 4) << 24);
 }
@@ -404,36 +448,6 @@ __device__ void conv1_stage(const TcParams& P, const WindowInput& in, uint32_t a
     }
 }
 
-// AveragePooling1D(3, stride 1, 'same') with TF's in-range divisor (Appendix B.3): X -> P, both
-// [6][66][8] hi/lo (X at ACT+0, P at ACT+12672).
-__device__ void avgpool_stage(uint32_t act, int tid) {
-    for (int item = tid; item < 6 * 64; item += kEpiThreads) {
-        const int cg = item >> 6, p = item & 63;
-        float s[8] = {0, 0, 0, 0, 0, 0, 0, 0};
-#pragma unroll
-        for (int t = 0; t < 3; ++t) {
-            const uint32_t a0 = act + (cg * 66 + p + t) * 16;
-            float v[8];
-            unpack8(ld_shared_v4(a0), ld_shared_v4(a0 + 6336), v);
-#pragma unroll
-            for (int e = 0; e < 8; ++e) s[e] += v[e];
-        }
-        const float div = (p == 0 || p == 63) ? 2.0f : 3.0f;
-#pragma unroll
-        for (int e = 0; e < 8; ++e) s[e] = s[e] / div;
-        uint4 hi, lo;
-        split8(s, &hi, &lo);
-        const uint32_t o = act + 12672 + (cg * 66 + p + 1) * 16;
-        st_shared_v4(o, hi);
-        st_shared_v4(o + 6336, lo);
-    }
-    if (tid < 24) {
-        const int cg = tid % 6, which = tid / 6;
-        const uint32_t a0 = act + 12672 + (which & 1 ? 6336 : 0) + (cg * 66 + (which & 2 ? 65 : 0)) * 16;
-        st_shared_v4(a0, make_uint4(0, 0, 0, 0));
-    }
-}
-
 // Epilogue of one job for one window: TMEM accumulators -> bias, ReLU, [pool], [BN], split -> smem.
 // Warp w handles TMEM lane quadrant (w & 3) and column group (w >> 2): NC = 16 columns per warp
 // (three groups for N = 48; for N = 16 only group 0 has work).  The
@@ -448,13 +462,14 @@ __device__ __forceinline__ void tmem_load_cols(uint32_t taddr, uint32_t (&r)[NC]
 // Everything a pass needs from the job descriptor, fetched into registers BEFORE waiting for the
 // accumulators (the wait has slack; the constant/shared loads would otherwise sit on the critical path).
 struct EpiArgs {
-    int kind, n, ntiles, L, stack, zero_y;
+    int kind, n, ntiles, L, joint, zero_y, edge15;
     int bias_off, bn_off;
     int out_off, out_lp, out_lo_delta, out_cg_base, out_ncg, out_L;
 };
 __device__ __forceinline__ EpiArgs load_epi_args(const TcJob& J) {
     EpiArgs a;
-    a.kind = J.kind; a.n = J.n; a.ntiles = J.ntiles; a.L = J.L; a.stack = J.stack; a.zero_y = J.zero_y;
+    a.kind = J.kind; a.n = J.n; a.ntiles = J.ntiles; a.L = J.L; a.joint = J.joint; a.zero_y = J.zero_y;
+    a.edge15 = J.edge15;
     a.bias_off = J.bias_off; a.bn_off = J.bn_off;
     a.out_off = J.out_off; a.out_lp = J.out_lp; a.out_lo_delta = J.out_lo_delta;
     a.out_cg_base = J.out_cg_base; a.out_ncg = J.out_ncg; a.out_L = J.out_L;
@@ -470,6 +485,7 @@ __device__ __forceinline__ void wait_accumulators(uint32_t bar, uint32_t parity,
 }
 
 // Zero padding rows written by each pass (after the wait: the output may alias the layer's input).
+// `act` = ACT region the output tensor lives in, `w` = window (selects the window's rows of Y).
 __device__ __forceinline__ void zero_padding_rows(const EpiArgs& A, uint32_t act, uint32_t act0, int w, int tid) {
     if (A.kind == EPI_PARITY) {
         if (A.zero_y && tid < 192) {   // rows 16, 17 of this window in every array / channel-group
@@ -485,7 +501,11 @@ __device__ __forceinline__ void zero_padding_rows(const EpiArgs& A, uint32_t act
     }
 }
 
-template <int NC, bool POOL, bool BN, bool PARITY>
+// JOINT: 0 = one window per pass (M=128 tiles: TMEM lane = position within the tile),
+//        1 = JOINT_PAIR  (M=64 per window: lanes 0-15 of a quadrant = 16 rows of window 0, lanes 16-31 =
+//            the same rows of window 1),
+//        2 = JOINT_STACK (M=64, stacked tensor in window 0's region: lanes 0-15 = rows, 16-31 idle).
+template <int NC, bool POOL, bool BN, bool PARITY, int JOINT>
 __device__ __forceinline__ void epilogue_tiles(const EpiArgs& A, uint32_t act, uint32_t act0, int w, uint32_t prm,
                                                uint32_t tmem_win, int tid, uint32_t bar, uint32_t parity,
                                                long long* tr) {
@@ -494,9 +514,14 @@ __device__ __forceinline__ void epilogue_tiles(const EpiArgs& A, uint32_t act, u
     const int lane = tid & 31;
     const int q = ((tid >> 5) + kEpiWarp0) & 3, h = tid >> 7;
     const bool active = h * NC < A.n;
-    const int row = q * 32 + lane;
-    const int ntiles = A.ntiles, L = A.L;
-    const bool stack = A.stack != 0;
+    constexpr bool stack = JOINT == JOINT_STACK;
+    const int row = JOINT ? q * 16 + (lane & 15) : q * 32 + lane;
+    const bool lane_ok = JOINT != JOINT_STACK || lane < 16;
+    if (JOINT == JOINT_PAIR) {   // this lane's window
+        w = lane >> 4;
+        act = act0 + w * kActBytes;
+    }
+    const int ntiles = JOINT ? 1 : A.ntiles, L = A.L;
     const int cg0 = A.out_cg_base + (h * NC) / 8;
     const uint32_t out_base = act + A.out_off;
     const int out_lp = A.out_lp, out_lo = A.out_lo_delta;
@@ -522,12 +547,22 @@ __device__ __forceinline__ void epilogue_tiles(const EpiArgs& A, uint32_t act, u
     }
     wait_accumulators(bar, parity, tr);
     if (!active) {
-        zero_padding_rows(A, act, act0, w, tid);
+        if (JOINT == JOINT_PAIR) {
+            zero_padding_rows(A, act0, act0, 0, tid);
+            zero_padding_rows(A, act0 + kActBytes, act0, 1, tid);
+        } else {
+            zero_padding_rows(A, act, act0, w, tid);
+        }
         return;
     }
     uint32_t r[NC];
     tmem_load_cols<NC>(taddr0, r);
-    zero_padding_rows(A, act, act0, w, tid);
+    if (JOINT == JOINT_PAIR) {
+        zero_padding_rows(A, act0, act0, 0, tid);
+        zero_padding_rows(A, act0 + kActBytes, act0, 1, tid);
+    } else {
+        zero_padding_rows(A, act, act0, w, tid);
+    }
     if (tr) tr[4] = clock64();
     for (int tile = 0; tile < ntiles; ++tile) {
         const int p = tile * 128 + row;
@@ -539,13 +574,15 @@ __device__ __forceinline__ void epilogue_tiles(const EpiArgs& A, uint32_t act, u
         if (tile + 1 < ntiles) tmem_load_cols<NC>(taddr0 + (tile + 1) * kTmemTileCols, r);
         const int qpos = POOL ? p >> 1 : p;
         // stacked tail: rows 18 w + i, i < 16 are positions; the other rows below L are separators
-        const bool valid = stack ? (p < L && (p % kStackPitch) < 16) : (p < L);
-        const bool writer = (stack && !POOL) ? (p < L) : (valid && (!POOL || (p & 1) == 0));
+        const bool valid = lane_ok && (stack ? (p < L && (p % kStackPitch) < 16) : (p < L));
+        const bool writer = (stack && !POOL) ? (lane_ok && p < L) : (valid && (!POOL || (p & 1) == 0));
+        // folded average pool (conv1d_10): TF divides the two in-range taps of the end positions by 2
+        const float es = (A.edge15 && (p == 0 || p == L - 1)) ? 1.5f : 1.0f;
 #pragma unroll
         for (int g = 0; g < NC / 8; ++g) {
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(acc[g * 8 + e] + bias[g * 8 + e], 0.f);
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(acc[g * 8 + e], es, bias[g * 8 + e]), 0.f);
             if (POOL) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
@@ -625,17 +662,25 @@ __device__ void run_epilogue(const TcParams& P, const TcJob& J, uint32_t act, ui
                              uint32_t tmem_win, int tid, uint32_t bar, uint32_t parity, float* probs0,
                              float* probs1, long long* tr) {
     const EpiArgs A = load_epi_args(J);
-    if (A.kind == EPI_N48 || A.kind == EPI_N16) {
-        epilogue_tiles<16, false, false, false>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+    if (A.joint == JOINT_PAIR) {
+        if (A.kind == EPI_PARITY)
+            epilogue_tiles<16, true, true, true, JOINT_PAIR>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+        else   // EPI_N48 / EPI_N16
+            epilogue_tiles<16, false, false, false, JOINT_PAIR>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+    } else if (A.joint == JOINT_STACK && A.kind != EPI_HEAD) {
+        if (A.kind == EPI_N48_BN)
+            epilogue_tiles<16, false, true, false, JOINT_STACK>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+        else if (A.kind == EPI_N48_POOL_BN)
+            epilogue_tiles<16, true, true, false, JOINT_STACK>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+        else   // EPI_N48
+            epilogue_tiles<16, false, false, false, JOINT_STACK>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+    } else if (A.kind == EPI_N48 || A.kind == EPI_N16) {
+        epilogue_tiles<16, false, false, false, JOINT_NONE>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
     } else if (A.kind == EPI_N48_POOL_BN) {
-        epilogue_tiles<16, true, true, false>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
-    } else if (A.kind == EPI_PARITY) {
-        epilogue_tiles<16, true, true, true>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
-    } else if (A.kind == EPI_N48_BN) {
-        epilogue_tiles<16, false, true, false>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
-    } else {   // EPI_HEAD
+        epilogue_tiles<16, true, true, false, JOINT_NONE>(A, act, act0, w, prm, tmem_win, tid, bar, parity, tr);
+    } else {   // EPI_HEAD (conv1d_20: M=128 stacked tile)
         wait_accumulators(bar, parity, tr);
-        // rows 0..16 live in TMEM lane quadrant 0: hardware warp 4 = epilogue-relative warp 2;
+        // rows 0..16 live in TMEM lane quadrant 0: one of the first four epilogue warps owns it;
         // scratch: 2 KB of window 0's ACT region behind the (tiny) conv1d_19 output
         if ((tid >> 5) < 4 && (((tid >> 5) + kEpiWarp0) & 3) == 0)
             epilogue_head(A.bias_off, prm, tmem_win, act0 + 8192, tid & 31, P.n_classes, probs0, probs1);
@@ -649,7 +694,7 @@ __device__ void run_epilogue(const TcParams& P, const TcJob& J, uint32_t act, ui
 template <int NCB, int KB0, int KB1>
 __device__ __forceinline__ void issue_part(uint32_t dwin, uint32_t ntiles, uint32_t a16, const uint32_t (&tap16)[3],
                                            uint32_t cb_first, uint32_t lp, uint32_t lo16, uint32_t b16,
-                                           uint32_t blk16, uint32_t n, uint32_t idesc, bool zero_first) {
+                                           uint32_t blk16, uint32_t n, uint32_t idesc, bool zero_first, uint32_t leader) {
     const uint64_t a_hi_word = (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(lp & 0x3FFF) << 16);
     const uint64_t b_hi_word = (static_cast<uint64_t>(0x4008u) << 32) | (static_cast<uint64_t>(n & 0x3FFF) << 16);
     constexpr int NKB = KB1 - KB0;
@@ -664,9 +709,9 @@ __device__ __forceinline__ void issue_part(uint32_t dwin, uint32_t ntiles, uint3
             const uint64_t ad = a_hi_word | (a & 0x3FFF);
             const uint64_t bd_hi = b_hi_word | ((b16 + (kb - KB0) * blk16) & 0x3FFF);
             const uint64_t bd_lo = b_hi_word | ((b16 + (NKB + kb - KB0) * blk16) & 0x3FFF);
-            tc_mma<1>(d, ad, bd_hi, idesc, acc);
-            tc_mma<2>(d, ad, bd_lo, idesc, 1u);
-            tc_mma<0>(d, a_hi_word | ((a + lo16) & 0x3FFF), bd_hi, idesc, 1u);
+            tc_mma<1>(d, ad, bd_hi, idesc, acc, leader);
+            tc_mma<2>(d, ad, bd_lo, idesc, 1u, leader);
+            tc_mma<0>(d, a_hi_word | ((a + lo16) & 0x3FFF), bd_hi, idesc, 1u, leader);
             acc = 1u;
         }
     }
@@ -676,17 +721,38 @@ template <int PART>
 __device__ __forceinline__ void issue_job_part(int ntaps, int ncb, uint32_t dwin, uint32_t ntiles, uint32_t a16,
                                                const uint32_t (&tap16)[3], uint32_t cb_first, uint32_t lp,
                                                uint32_t lo16, uint32_t b16, uint32_t blk16, uint32_t n,
-                                               uint32_t idesc, bool zero_first) {
+                                               uint32_t idesc, bool zero_first, uint32_t leader) {
     if (ntaps == 3 && ncb == 3) {          // 9 K blocks: 5 + 4
-        if (PART == 0) issue_part<3, 0, 5>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
-        else issue_part<3, 5, 9>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+        if (PART == 0) issue_part<3, 0, 5>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first, leader);
+        else issue_part<3, 5, 9>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first, leader);
     } else if (ntaps == 1) {               // 1x1 conv over 48 channels: 3 K blocks: 2 + 1
-        if (PART == 0) issue_part<3, 0, 2>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
-        else issue_part<3, 2, 3>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+        if (PART == 0) issue_part<3, 0, 2>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first, leader);
+        else issue_part<3, 2, 3>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first, leader);
     } else {                               // k=3 conv over 16 channels: 3 K blocks (one per tap): 2 + 1
-        if (PART == 0) issue_part<1, 0, 2>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
-        else issue_part<1, 2, 3>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first);
+        if (PART == 0) issue_part<1, 0, 2>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first, leader);
+        else issue_part<1, 2, 3>(dwin, ntiles, a16, tap16, cb_first, lp, lo16, b16, blk16, n, idesc, zero_first, leader);
     }
+}
+
+// What the MMA issuer needs from a job descriptor, held in registers one job ahead.
+struct IssueArgs {
+    uint32_t n, idesc, ntiles, lp, lo16, cb0, tcol, tap16[3];
+    int ntaps, ncb, first, last, joint, need, eseq;
+};
+__device__ __forceinline__ IssueArgs load_issue_args(const TcJob& J) {
+    IssueArgs a;
+    a.n = J.n; a.idesc = J.idesc; a.ntiles = J.ntiles; a.lp = J.lp; a.lo16 = J.lo16; a.cb0 = J.cb0; a.tcol = J.tcol;
+    a.tap16[0] = J.tap16[0]; a.tap16[1] = J.tap16[1]; a.tap16[2] = J.tap16[2];
+    a.ntaps = J.ntaps; a.ncb = J.ncb; a.first = J.first; a.last = J.last; a.joint = J.joint; a.need = J.need;
+    a.eseq = J.eseq;
+    return a;
+}
+// Consume the values so that the constant loads above are scheduled before this point (i.e. behind
+// the MMA burst of the current job) instead of being sunk to their first use in the next iteration.
+__device__ __forceinline__ void pin_issue_args(const IssueArgs& a) {
+    asm volatile("" ::"r"(a.n), "r"(a.idesc), "r"(a.ntiles), "r"(a.lp), "r"(a.lo16), "r"(a.cb0), "r"(a.tcol),
+                 "r"(a.tap16[0]), "r"(a.tap16[1]), "r"(a.tap16[2]), "r"(a.ntaps), "r"(a.ncb), "r"(a.first),
+                 "r"(a.last), "r"(a.joint), "r"(a.need), "r"(a.eseq));
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -707,6 +773,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t bar_mma[2] = {bar0 + 32, bar0 + 40};
     const uint32_t bar_epi[2] = {bar0 + 48, bar0 + 56};
     const uint32_t bar_final = bar0 + 64;
+    // joint phase: rings of 4 (the MMA issuer runs at most 3 epilogues ahead, see TcJob::need)
+    const uint32_t bar_jmma = bar0 + 320, bar_jepi = bar0 + 352;   // + 8 * (eseq & 3)
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 96);
     const int tid = threadIdx.x;
     // warp index via shfl: tells the compiler it is warp-uniform, so the role branches below are
@@ -723,6 +791,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         mbar_init(bar_epi[0], kEpiThreads);
         mbar_init(bar_epi[1], kEpiThreads);
         mbar_init(bar_final, 1);
+        for (int i = 0; i < 4; ++i) {
+            mbar_init(bar_jmma + 8 * i, 1);
+            mbar_init(bar_jepi + 8 * i, kEpiThreads);
+        }
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(sbase + kSmemBar + 96, kTmemCols);
@@ -785,29 +857,37 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         epi_bar_sync();   // parameter block staged by all epilogue threads is now visible
         uint32_t mma_phase[2] = {0, 0};
+        float* p0 = valid[0] ? probs + static_cast<size_t>(win[0]) * P.n_classes : nullptr;
+        float* p1 = valid[1] ? probs + static_cast<size_t>(win[1]) * P.n_classes : nullptr;
         for (int j = 0; j < njobs; ++j) {
             const TcJob& J = c_jobs[j];
             if ((tid & 31) == 0) prefetch_job(j + 1);
             if (!J.last) continue;
-            const int nw = J.stack ? 1 : 2;   // stacked tail jobs: one pass serves both windows
-            for (int w = 0; w < nw; ++w) {
+            if (J.joint) {   // one pass serves both windows
+                const int e = J.eseq;
+                long long* tr = (P.trace && blockIdx.x == 0 && tid == 0) ? P.trace + (j * 2) * 16 : nullptr;
+                run_epilogue(P, J, sbase + kSmemAct0, sbase + kSmemAct0, 0, prm, tmem_base + J.tcol, tid,
+                             bar_jmma + 8 * (e & 3), (e >> 2) & 1, p0, p1, tr);
+                if (tr) tr[6] = clock64();
+                fence_proxy_async();
+                if (tr) tr[7] = clock64();
+                tc_fence_before();
+                mbar_arrive(bar_jepi + 8 * (e & 3));
+                if (tr) tr[3] = clock64();
+                continue;
+            }
+            for (int w = 0; w < 2; ++w) {
                 const uint32_t act = sbase + (w ? kSmemAct1 : kSmemAct0);
-                float* p0 = valid[0] ? probs + static_cast<size_t>(win[0]) * P.n_classes : nullptr;
-                float* p1 = valid[1] ? probs + static_cast<size_t>(win[1]) * P.n_classes : nullptr;
                 long long* tr = (P.trace && blockIdx.x == 0 && tid == 0) ? P.trace + (j * 2 + w) * 16 : nullptr;
                 run_epilogue(P, J, act, sbase + kSmemAct0, w, prm, tmem_base + w * kTmemWindowCols, tid,
                              bar_mma[w], mma_phase[w], p0, p1, tr);
                 mma_phase[w] ^= 1;
                 if (tr) tr[6] = clock64();
-                if (J.avgpool_after) {
-                    epi_bar_sync();
-                    avgpool_stage(act, tid);
-                }
                 fence_proxy_async();
                 if (tr) tr[7] = clock64();
                 tc_fence_before();
                 mbar_arrive(bar_epi[w]);
-                if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[(j * 2 + w) * 16 + 3] = clock64();
+                if (tr) tr[3] = clock64();
             }
         }
         if (P.dbg_job >= 0) {   // debug: dump both ACT regions after the last processed job
@@ -823,53 +903,84 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // the literal keeps every MMA operand derived from uniform sources.
         if (tmem_base != 0) __trap();
         if (elect_one()) {
+            constexpr uint32_t leader = 1;   // (a converged-warp variant with predicated tcgen05 ops was slower: R2UR.BROADCAST per operand)
+            const bool tracing = P.trace && blockIdx.x == 0;
             uint32_t wfull_phase = 0, epi_phase[2] = {0, 0};
+            int jepi_seen = 0;   // joint epilogues known to be complete
+            const uint32_t wp16[2] = {wbuf >> 4, (wbuf + kWPart0) >> 4};
+            const uint32_t act16_0 = (sbase + kSmemAct0) >> 4, act16_1 = (sbase + kSmemAct1) >> 4;
+            // The issuer is ONE thread: a chain of dependent constant loads costs it ~40 cycles per
+            // link, so the next job's descriptor is fetched while this job's MMAs are issued.
+            IssueArgs nxt = load_issue_args(c_jobs[0]);
             for (int j = 0; j < njobs; ++j) {
-                const TcJob& J = c_jobs[j];
-                prefetch_job(j + 1);
-                const int ntaps = J.ntaps, ncb = J.ncb;
-                const uint32_t n = J.n, lp = J.lp, ntiles = J.ntiles, cb0 = J.cb0;
-                const uint32_t idesc = make_idesc(128, n);
-                const uint32_t blk16 = 2u * n;                   // one K=16 block of B, in 16-byte units
-                const uint32_t lo16 = J.lo_delta >> 4;
-                const uint32_t tap16[3] = {static_cast<uint32_t>(J.tap_off[0]) >> 4,
-                                           static_cast<uint32_t>(J.tap_off[1]) >> 4,
-                                           static_cast<uint32_t>(J.tap_off[2]) >> 4};
+                const IssueArgs J = nxt;
+                if (j + 1 < njobs) nxt = load_issue_args(c_jobs[j + 1]);
+                const uint32_t blk16 = 2u * J.n;                 // one K=16 block of B, in 16-byte units
+                const uint32_t tap16[3] = {J.tap16[0], J.tap16[1], J.tap16[2]};
                 const bool first = J.first != 0, last = J.last != 0;
-                const uint32_t wp16[2] = {wbuf >> 4, (wbuf + kWPart0) >> 4};
-                const int nw = J.stack ? 1 : 2;
-                for (int w = 0; w < nw; ++w) {
+                if (J.joint) {
+                    // ---- both windows in one burst: [part 0: w0, w1] [part 1: w0, w1], one commit ----
+                    if (first && J.eseq == 0) {   // first joint job: the per-window epilogues of the last
+                        for (int w = 0; w < 2; ++w) {   // single-window job must be done
+                            mbar_wait(bar_epi[w], epi_phase[w]);
+                            epi_phase[w] ^= 1;
+                        }
+                    }
+                    for (const int need = J.need; jepi_seen < need; ++jepi_seen)
+                        mbar_wait(bar_jepi + 8 * (jepi_seen & 3), (jepi_seen >> 2) & 1);
+                    tc_fence_after();
+                    if (tracing) P.trace[(j * 2) * 16 + 0] = clock64();
+                    const int nw = J.joint == JOINT_PAIR ? 2 : 1;
+                    const uint32_t dcol = J.tcol;
+                    mbar_wait(bar_wfull[0], wfull_phase);
+                    if (tracing) P.trace[(j * 2) * 16 + 8] = clock64();
+                    for (int w = 0; w < nw; ++w)
+                        issue_job_part<0>(J.ntaps, J.ncb, dcol + (static_cast<uint32_t>(16 * w) << 16), 1,
+                                          (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[0], blk16, J.n,
+                                          J.idesc, first, leader);
+                    tc_commit(bar_wfree[0], leader);
+                    if (tracing) P.trace[(j * 2) * 16 + 9] = clock64();
+                    mbar_wait(bar_wfull[1], wfull_phase);
+                    if (tracing) P.trace[(j * 2) * 16 + 10] = clock64();
+                    for (int w = 0; w < nw; ++w)
+                        issue_job_part<1>(J.ntaps, J.ncb, dcol + (static_cast<uint32_t>(16 * w) << 16), 1,
+                                          (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[1], blk16, J.n,
+                                          J.idesc, false, leader);
+                    if (last) tc_commit(bar_jmma + 8 * (J.eseq & 3), leader);
+                    tc_commit(bar_wfree[1], leader);
+                    if (tracing) P.trace[(j * 2) * 16 + 1] = clock64();
+                    wfull_phase ^= 1;
+                    pin_issue_args(nxt);
+                    continue;
+                }
+                for (int w = 0; w < 2; ++w) {
                     if (first) {   // input written and previous accumulators drained
                         mbar_wait(bar_epi[w], epi_phase[w]);
                         epi_phase[w] ^= 1;
-                        if (J.stack == 2) {   // first stacked job: window 1's last epilogue must be done too
-                            mbar_wait(bar_epi[1], epi_phase[1]);
-                            epi_phase[1] ^= 1;
-                        }
                     }
                     tc_fence_after();
-                    if (P.trace && blockIdx.x == 0) P.trace[(j * 2 + w) * 16 + 0] = clock64();
-                    const uint32_t act16 = (sbase + (w ? kSmemAct1 : kSmemAct0)) >> 4;
+                    if (tracing) P.trace[(j * 2 + w) * 16 + 0] = clock64();
                     const uint32_t dwin = w * kTmemWindowCols;
                     // ---- weight part 0 (first K blocks); freed early so the loader can refill it ----
                     if (w == 0) mbar_wait(bar_wfull[0], wfull_phase);
-                    if (P.trace && blockIdx.x == 0) P.trace[(j * 2 + w) * 16 + 8] = clock64();
-                    issue_job_part<0>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, wp16[0], blk16, n,
-                                      idesc, first);
-                    if (w == nw - 1) tc_commit(bar_wfree[0]);
-                    if (P.trace && blockIdx.x == 0) P.trace[(j * 2 + w) * 16 + 9] = clock64();
+                    if (tracing) P.trace[(j * 2 + w) * 16 + 8] = clock64();
+                    issue_job_part<0>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[0],
+                                      blk16, J.n, J.idesc, first, leader);
+                    if (w == 1) tc_commit(bar_wfree[0], leader);
+                    if (tracing) P.trace[(j * 2 + w) * 16 + 9] = clock64();
                     // ---- weight part 1 (remaining K blocks) ----
                     if (w == 0) mbar_wait(bar_wfull[1], wfull_phase);
-                    if (P.trace && blockIdx.x == 0) P.trace[(j * 2 + w) * 16 + 10] = clock64();
-                    issue_job_part<1>(ntaps, ncb, dwin, ntiles, act16, tap16, cb0, lp, lo16, wp16[1], blk16, n,
-                                      idesc, false);
-                    if (last) tc_commit(bar_mma[w]);
-                    if (w == nw - 1) tc_commit(bar_wfree[1]);
-                    if (P.trace && blockIdx.x == 0) P.trace[(j * 2 + w) * 16 + 1] = clock64();
+                    if (tracing) P.trace[(j * 2 + w) * 16 + 10] = clock64();
+                    issue_job_part<1>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[1],
+                                      blk16, J.n, J.idesc, false, leader);
+                    if (last) tc_commit(bar_mma[w], leader);
+                    if (w == 1) tc_commit(bar_wfree[1], leader);
+                    if (tracing) P.trace[(j * 2 + w) * 16 + 1] = clock64();
                 }
                 wfull_phase ^= 1;
+                pin_issue_args(nxt);
             }
-            tc_commit(bar_final);
+            tc_commit(bar_final, leader);
             mbar_wait(bar_final, 0);
         }
     } else if (warp == kLoadWarp && elect_one()) {
@@ -934,18 +1045,20 @@ struct JobBuilder {
     // channel block kb % ncb), each part [hi blocks | lo blocks], block = [2 chunks][n rows][8] bf16
     // `layer2` (optional): a second conv with the same input and kernel size whose output channels
     // are appended along N (rows cout .. cout + cout2 - 1): one MMA job computes both.
-    void pack_weights(int layer, int n, int cb0, int ncb, TcJob* J, int layer2 = 0) {
+    // `fold_avg3`: a 1x1 conv that follows AveragePooling1D(3, 1, 'same') becomes a k=3 conv with every
+    // tap = W / 3 (the epilogue rescales the two end positions, where TF divides by 2).
+    void pack_weights(int layer, int n, int cb0, int ncb, TcJob* J, int layer2 = 0, bool fold_avg3 = false) {
         const ConvSpec& s = kConvSpecs[layer];
+        const int ktaps = fold_avg3 ? 3 : s.k;
         const int cout = s.cout ? s.cout : blob.n_classes;
         const float* k = blob.find("conv1d_" + std::to_string(layer) + "/kernel")->data;
         const int cout2 = layer2 ? kConvSpecs[layer2].cout : 0;
         const float* k2 = layer2 ? blob.find("conv1d_" + std::to_string(layer2) + "/kernel")->data : nullptr;
-        const int nkb = s.k * ncb;
+        const int nkb = ktaps * ncb;
         const int split = nkb == 9 ? 5 : 2;
         const size_t blk = static_cast<size_t>(2) * n * 8;   // bf16 elements per K block
         while (w.size() % 128) w.push_back(0);
         J->w_goff = static_cast<int>(w.size());
-        J->kb_split = split;
         const int range[3] = {0, split, nkb};
         for (int part = 0; part < 2; ++part) {
             const int kb0 = range[part], kb1 = range[part + 1], cnt = kb1 - kb0;
@@ -957,7 +1070,8 @@ struct JobBuilder {
                         for (int e = 0; e < 8; ++e) {
                             const int cin = (cb0 + cb) * 16 + j * 8 + e;
                             float v = 0.f;
-                            if (row < cout && cin < s.cin) v = k[(t * s.cin + cin) * cout + row];
+                            if (fold_avg3) v = row < cout && cin < s.cin ? k[cin * cout + row] / 3.0f : 0.f;
+                            else if (row < cout && cin < s.cin) v = k[(t * s.cin + cin) * cout + row];
                             else if (row < cout + cout2 && cin < s.cin) v = k2[(t * s.cin + cin) * cout2 + row - cout];
                             const uint16_t hi = bf16_rn(v);
                             const uint16_t lo = bf16_rn(v - bf16_to_float(hi));
@@ -990,33 +1104,71 @@ struct JobBuilder {
 
     // generic conv job; in_* describe the input tensor, out_* the output tensor
     TcJob& add(int layer, int L, int in_off, int in_lp, int in_lo_delta, int kind, int bn, int out_off,
-               int out_cg_base, int layer2 = 0) {
+               int out_cg_base, int layer2 = 0, bool fold_avg3 = false) {
         const ConvSpec& s = kConvSpecs[layer];
         const int cout = (s.cout ? s.cout : blob.n_classes) + (layer2 ? kConvSpecs[layer2].cout : 0);
+        const int ktaps = fold_avg3 ? 3 : s.k;
         const bool pool = kind == EPI_N48_POOL_BN || kind == EPI_PARITY;
         TcJob J{};
         J.n = (cout + 15) / 16 * 16;
-        J.cout = cout;
+        J.idesc = 128;
         J.ntiles = (L + 127) / 128;
         J.L = L;
         J.lp = in_lp;
-        J.ntaps = s.k;
-        for (int t = 0; t < 3; ++t) J.tap_off[t] = in_off + (s.k == 3 ? t : 1) * 16;
-        J.lo_delta = in_lo_delta;
+        J.ntaps = ktaps;
+        for (int t = 0; t < 3; ++t) J.tap16[t] = in_off + (ktaps == 3 ? t : 1) * 16;
+        J.lo16 = in_lo_delta;
         J.ncb = s.cin / 16;
         J.cb0 = 0;
         J.first = J.last = 1;
         J.kind = kind;
+        J.edge15 = fold_avg3 ? 1 : 0;
         J.out_L = pool ? L / 2 : L;
         J.out_off = out_off;
         J.out_lp = J.out_L + 2;
         J.out_ncg = cout / 8;
         J.out_lo_delta = J.out_ncg * J.out_lp * 16;
         J.out_cg_base = out_cg_base;
-        pack_weights(layer, J.n, 0, J.ncb, &J, layer2);
+        pack_weights(layer, J.n, 0, J.ncb, &J, layer2, fold_avg3);
         pack_params(layer, J.n, bn, kind == EPI_PARITY ? out_cg_base * 8 : 0, &J, layer2);
         jobs.push_back(J);
         return jobs.back();
+    }
+
+    // Convert the builder's M / byte offsets into what the MMA issuer consumes directly.
+    void finalize_jobs() {
+        for (TcJob& J : jobs) {
+            J.idesc = static_cast<int>(make_idesc(J.idesc, J.n));
+            for (int t = 0; t < 3; ++t) J.tap16[t] >>= 4;
+            J.lo16 >>= 4;
+        }
+    }
+
+    // Mark the jobs from index `j0` on as the joint phase: accumulator slots rotate over three 64-column
+    // slots (K-slices of one conv share a slot) and `need` is derived from the data flow: `producer[j]`
+    // = job whose epilogue writes this job's input (-1: available before the joint phase).
+    void finish_joint(int j0, const std::vector<int>& producer) {
+        std::vector<int> eseq_of(jobs.size(), -1), slot_of(jobs.size(), 0);
+        int e = 0, slot = -1;
+        std::vector<int> last_user(3, -1);   // job with the epilogue that last drained the slot
+        for (size_t j = j0; j < jobs.size(); ++j) {
+            TcJob& J = jobs[j];
+            if (J.first) slot = (slot + 1) % 3;
+            slot_of[j] = slot;
+            J.tcol = slot * kTmemTileCols;
+            int need = 0;
+            const int prod = producer[j - j0];
+            if (prod >= 0) need = std::max(need, eseq_of[prod] + 1);
+            if (J.first && last_user[slot] >= 0) need = std::max(need, eseq_of[last_user[slot]] + 1);
+            if (j > static_cast<size_t>(j0)) need = std::max(need, jobs[j - 1].need);   // waits are cumulative
+            J.need = need;
+            J.eseq = -1;
+            if (J.last) {
+                J.eseq = e;
+                eseq_of[j] = e++;
+                last_user[slot] = static_cast<int>(j);
+            }
+        }
     }
 };
 
@@ -1030,37 +1182,54 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     B->add(6, 256, 0, 258, 8256, EPI_N48, 0, 0, 0);               // -> [6][258][8]
     B->add(7, 256, 0, 258, 24768, EPI_N48_POOL_BN, 3, 0, 0);      // -> [6][130][8], lo +12480
     B->add(8, 128, 0, 130, 12480, EPI_N48, 0, 0, 0);
-    B->add(9, 128, 0, 130, 12480, EPI_N48_POOL_BN, 4, 0, 0).avgpool_after = 1;   // X [6][66][8], lo +6336
-    // inception block: X @0, P @12672 (later T15), T1214 @25344 (conv1d_12 | conv1d_14 outputs as
-    // one 32-channel tensor: both are 1x1 convs of X, so ONE MMA job with N = 32 computes them); Y
-    // (parity split, both windows) in window 0's region @43392;
-    // concat order [conv10, conv11, conv13, conv16] (network_architecture.py:68), BN5 per channel
-    B->add(10, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 0).zero_y = 1;
-    B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6);
-    B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 25344, 0, 14);      // -> [4][66][8], lo +4224
-    B->add(13, 64, 25344, 66, 4224, EPI_PARITY, 5, 0, 12);       // reads channel-groups 0-1 (conv1d_12)
-    B->add(15, 64, 25344 + 2 * 66 * 16, 66, 4224, EPI_N48, 0, 12672, 0);   // groups 2-3 (conv1d_14); T15 in P's slot
-    B->add(16, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 18);
-    // conv1d_17 .. conv1d_20 run on BOTH windows stacked in one tile (row = 18 w + position).
+    B->add(9, 128, 0, 130, 12480, EPI_N48_POOL_BN, 4, 0, 0);      // X [6][66][8], lo +6336
+    // ---- joint phase (both windows per job) ----
+    // Inception block, JOINT_PAIR: X @0, T15 @12672, T1214 @25344 (conv1d_12 | conv1d_14 outputs as one
+    // 32-channel tensor: both are 1x1 convs of X, so ONE job with N = 32 computes them); Y (parity
+    // split, both windows) in window 0's region @43392.  The average pool in front of conv1d_10 is
+    // folded into its weights (k=3, W/3).  Concat order [conv10, conv11, conv13, conv16]
+    // (network_architecture.py:68), BN5 per channel.  Job order: the long dependency chain
+    // conv1d_14 -> 15 -> 16 first, independent branches in between, so that the MMAs of one job run
+    // while the epilogue warps drain another.
+    const int j0 = static_cast<int>(B->jobs.size());
+    std::vector<int> producer;
+    auto joint = [&](TcJob& J, int kind, int prod) {
+        J.joint = kind;
+        J.idesc = 64;
+        J.ntiles = 1;
+        producer.push_back(prod);
+    };
+    joint(B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 25344, 0, 14), JOINT_PAIR, -1);              // j0: -> [4][66][8], lo +4224
+    joint(B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6), JOINT_PAIR, -1);                   // j0+1
+    B->jobs.back().zero_y = 1;
+    joint(B->add(15, 64, 25344 + 2 * 66 * 16, 66, 4224, EPI_N48, 0, 12672, 0), JOINT_PAIR, j0);   // j0+2: groups 2-3 (conv1d_14)
+    joint(B->add(13, 64, 25344, 66, 4224, EPI_PARITY, 5, 0, 12), JOINT_PAIR, j0);              // j0+3: groups 0-1 (conv1d_12)
+    joint(B->add(10, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 0, 0, true), JOINT_PAIR, -1);          // j0+4: avg pool folded
+    joint(B->add(16, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 18), JOINT_PAIR, j0 + 2);          // j0+5
+    // conv1d_17 .. conv1d_20, JOINT_STACK: both windows stacked in one tile (row = 18 w + position).
     // conv1d_17: stride 2 on the parity-split Y (tap0 = Ye[i], tap1 = Yo[i], tap2 = Ye[i+1]),
     // K = 3 x 192 split in 4 jobs of 3 channel blocks so each weight chunk fits the buffer
     for (int s = 0; s < 4; ++s) {
         TcJob J{};
-        J.n = 48; J.cout = 48; J.ntiles = 1; J.L = 34; J.lp = kYRows; J.ntaps = 3;
-        J.tap_off[0] = kYOff; J.tap_off[1] = kYOff + 2 * kYArray; J.tap_off[2] = kYOff + 16;
-        J.lo_delta = kYArray; J.ncb = 3; J.cb0 = 3 * s;
+        J.n = 48; J.idesc = 64; J.ntiles = 1; J.L = 34; J.lp = kYRows; J.ntaps = 3;
+        J.tap16[0] = kYOff; J.tap16[1] = kYOff + 2 * kYArray; J.tap16[2] = kYOff + 16;
+        J.lo16 = kYArray; J.ncb = 3; J.cb0 = 3 * s;
         J.first = (s == 0); J.last = (s == 3);
-        J.stack = s == 0 ? 2 : 1;
+        J.joint = JOINT_STACK;
         J.kind = EPI_N48_BN;
         J.out_L = 34; J.out_off = 0; J.out_lp = 36; J.out_ncg = 6; J.out_lo_delta = 6 * 36 * 16;
         J.out_cg_base = 0;
         B->pack_weights(17, 48, 3 * s, 3, &J);
         if (J.last) B->pack_params(17, 48, 6, 0, &J);
         B->jobs.push_back(J);
+        producer.push_back(s == 0 ? j0 + 5 : -1);   // every Y writer precedes conv1d_16's epilogue
     }
-    B->add(18, 34, 0, 36, 3456, EPI_N48, 0, 0, 0).stack = 1;
-    B->add(19, 34, 0, 36, 3456, EPI_N48_POOL_BN, 7, 0, 0).stack = 1;   // -> [6][19][8], lo +1824
-    B->add(20, 17, 0, 19, 1824, EPI_HEAD, 0, 0, 0).stack = 1;
+    joint(B->add(18, 34, 0, 36, 3456, EPI_N48, 0, 0, 0), JOINT_STACK, j0 + 9);
+    joint(B->add(19, 34, 0, 36, 3456, EPI_N48_POOL_BN, 7, 0, 0), JOINT_STACK, j0 + 10);   // -> [6][19][8], lo +1824
+    joint(B->add(20, 17, 0, 19, 1824, EPI_HEAD, 0, 0, 0), JOINT_STACK, j0 + 11);
+    B->jobs.back().idesc = 128;   // the head epilogue reads all 17 rows from TMEM lane quadrant 0
+    B->finish_joint(j0, producer);
+    B->finalize_jobs();
     if (B->prm.size() > static_cast<size_t>(kPrmFloats) || B->jobs.size() > static_cast<size_t>(kMaxJobs))
         return false;
     for (const TcJob& J : B->jobs)

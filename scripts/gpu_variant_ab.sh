@@ -7,7 +7,7 @@ for lib in $libs; do
   name=$(basename $lib .so)
   export DEEPBINNER_B200_LIB=$PWD/$lib
   echo "=== $name"
-  timeout 600 python -m pytest tests/test_gpu_parity.py tests/test_gpu_tc_layers.py -m gpu -x -q 2>&1 | tail -3
+  timeout 600 python -m pytest tests/test_gpu_tc_layers.py "tests/test_gpu_parity.py::test_predict_parity_on_real_windows" -m gpu -x -q 2>&1 | tail -1
   timeout 300 python tools/tc_timeline.py 296 > gpurun_out/timeline_$name.txt 2>&1; tail -1 gpurun_out/timeline_$name.txt
   timeout 600 python bench.py --steps 10 --warmup 3 --cpu-seconds 2 2>gpurun_out/bench_$name.err | tail -1 > gpurun_out/bench_$name.json
   python - <<PY

@@ -12,8 +12,8 @@ sys.path.insert(0, str(ROOT))
 from deepbinner_b200.model import B200Model, tc_num_jobs  # noqa: E402
 from deepbinner_b200 import _native  # noqa: E402
 
-NAMES = ['conv2', 'conv3', 'conv4', 'conv5', 'conv6', 'conv7', 'conv8', 'conv9', 'conv10', 'conv11',
-         'c12+14', 'conv13', 'conv15', 'conv16', 'c17a', 'c17b', 'c17c', 'c17d', 'conv18',
+NAMES = ['conv2', 'conv3', 'conv4', 'conv5', 'conv6', 'conv7', 'conv8', 'conv9', 'c12+14', 'conv11',
+         'conv15', 'conv13', 'conv10f', 'conv16', 'c17a', 'c17b', 'c17c', 'c17d', 'conv18',
          'conv19', 'conv20']
 
 
