@@ -526,19 +526,25 @@ __device__ __forceinline__ void epilogue_tiles(const EpiArgs& A, uint32_t act, u
     const uint32_t out_base = act + A.out_off;
     const int out_lp = A.out_lp, out_lo = A.out_lo_delta;
     const uint32_t taddr0 = tmem_win + h * NC + (static_cast<uint32_t>(q * 32) << 16);
-    float bias[NC], sc[BN ? NC : 1], sh[BN ? NC : 1];
+    // Pooling passes: the two lanes of a max-pool pair share the work after the maximum - the even lane
+    // finishes columns 0-7 of the warp's 16, the odd lane columns 8-15 - so each lane needs only its
+    // half of the per-channel parameters (PN of them, starting at column `pc0`).
+    constexpr int PN = POOL ? NC / 2 : NC;
+    const int odd = lane & 1;
+    const int pc0 = POOL ? odd * (NC / 2) : 0;
+    float bias[PN], sc[BN ? PN : 1], sh[BN ? PN : 1];
     {   // unconditional (inactive warps read neighbouring parameters they never use) so that the
         // arrays stay in registers
-        const uint32_t bias_a = prm + (A.bias_off + h * NC) * 4;
+        const uint32_t bias_a = prm + (A.bias_off + h * NC + pc0) * 4;
 #pragma unroll
-        for (int g = 0; g < NC / 4; ++g) {
+        for (int g = 0; g < PN / 4; ++g) {
             const float4 b = ld_shared_f4(bias_a + g * 16);
             bias[4 * g] = b.x; bias[4 * g + 1] = b.y; bias[4 * g + 2] = b.z; bias[4 * g + 3] = b.w;
         }
         if (BN) {
-            const uint32_t bn_a = prm + (A.bn_off + h * NC) * 4;
+            const uint32_t bn_a = prm + (A.bn_off + h * NC + pc0) * 4;
 #pragma unroll
-            for (int g = 0; g < NC / 4; ++g) {
+            for (int g = 0; g < PN / 4; ++g) {
                 const float4 a = ld_shared_f4(bn_a + g * 16), b = ld_shared_f4(bn_a + 192 + g * 16);
                 sc[4 * g] = a.x; sc[4 * g + 1] = a.y; sc[4 * g + 2] = a.z; sc[4 * g + 3] = a.w;
                 sh[4 * g] = b.x; sh[4 * g + 1] = b.y; sh[4 * g + 2] = b.z; sh[4 * g + 3] = b.w;
@@ -575,35 +581,62 @@ __device__ __forceinline__ void epilogue_tiles(const EpiArgs& A, uint32_t act, u
         const int qpos = POOL ? p >> 1 : p;
         // stacked tail: rows 18 w + i, i < 16 are positions; the other rows below L are separators
         const bool valid = lane_ok && (stack ? (p < L && (p % kStackPitch) < 16) : (p < L));
-        const bool writer = (stack && !POOL) ? (lane_ok && p < L) : (valid && (!POOL || (p & 1) == 0));
         // folded average pool (conv1d_10): TF divides the two in-range taps of the end positions by 2
         const float es = (A.edge15 && (p == 0 || p == L - 1)) ? 1.5f : 1.0f;
+        if (POOL) {
+            static_assert(!POOL || NC == 16, "pooling epilogue is written for 16 columns per warp");
+            // relu(max(a, b) + bias) == max(relu(a + bias), relu(b + bias)): take the maximum of the raw
+            // accumulators of positions 2i and 2i+1 first.  Each lane keeps the 8 columns it will
+            // finish and sends the other 8 to its partner (8 shuffles instead of 16).
+            if (A.edge15) {
 #pragma unroll
-        for (int g = 0; g < NC / 8; ++g) {
+                for (int c = 0; c < NC; ++c) acc[c] *= es;
+            }
             float v[8];
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(acc[g * 8 + e], es, bias[g * 8 + e]), 0.f);
-            if (POOL) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], __shfl_xor_sync(0xffffffffu, v[e], 1));
+            for (int e = 0; e < 8; ++e) {
+                const float keep = odd ? acc[8 + e] : acc[e];
+                const float send = odd ? acc[e] : acc[8 + e];
+                v[e] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
             }
+#pragma unroll
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e] + bias[e], 0.f);
             if (BN) {
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[g * 8 + e], v[e], sh[g * 8 + e]);
+                for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
             }
             uint4 hi, lo;
             split8(v, &hi, &lo);
-            if (stack && !POOL && !valid) {   // separator rows of a stacked tensor are zero padding
-                hi = make_uint4(0, 0, 0, 0);
-                lo = make_uint4(0, 0, 0, 0);
-            }
-            if (writer) {
+            if (valid) {   // both lanes of a pair write: channel group cg0 (even lane) / cg0 + 1 (odd lane)
                 if (PARITY) {   // even/odd pooled positions in separate arrays (input of conv1d_17)
                     const uint32_t o = act0 + kYOff + (qpos & 1) * (2 * kYArray) +
-                                       ((cg0 + g) * kYRows + w * kStackPitch + (qpos >> 1)) * 16;
+                                       ((cg0 + odd) * kYRows + w * kStackPitch + (qpos >> 1)) * 16;
                     st_shared_v4(o, hi);
                     st_shared_v4(o + kYArray, lo);
                 } else {
+                    const uint32_t o = out_base + ((cg0 + odd) * out_lp + qpos + 1) * 16;
+                    st_shared_v4(o, hi);
+                    st_shared_v4(o + out_lo, lo);
+                }
+            }
+        } else {
+            const bool writer = stack ? (lane_ok && p < L) : valid;
+#pragma unroll
+            for (int g = 0; g < NC / 8; ++g) {
+                float v[8];
+#pragma unroll
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(acc[g * 8 + e], es, bias[g * 8 + e]), 0.f);
+                if (BN) {
+#pragma unroll
+                    for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[g * 8 + e], v[e], sh[g * 8 + e]);
+                }
+                uint4 hi, lo;
+                split8(v, &hi, &lo);
+                if (stack && !valid) {   // separator rows of a stacked tensor are zero padding
+                    hi = make_uint4(0, 0, 0, 0);
+                    lo = make_uint4(0, 0, 0, 0);
+                }
+                if (writer) {
                     const uint32_t o = out_base + ((cg0 + g) * out_lp + qpos + 1) * 16;
                     st_shared_v4(o, hi);
                     st_shared_v4(o + out_lo, lo);
@@ -918,6 +951,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t blk16 = 2u * J.n;                 // one K=16 block of B, in 16-byte units
                 const uint32_t tap16[3] = {J.tap16[0], J.tap16[1], J.tap16[2]};
                 const bool first = J.first != 0, last = J.last != 0;
+                if (tracing) P.trace[(j * 2) * 16 + 11] = clock64();
                 if (J.joint) {
                     // ---- both windows in one burst: [part 0: w0, w1] [part 1: w0, w1], one commit ----
                     if (first && J.eseq == 0) {   // first joint job: the per-window epilogues of the last
@@ -958,6 +992,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         mbar_wait(bar_epi[w], epi_phase[w]);
                         epi_phase[w] ^= 1;
                     }
+                    if (tracing) P.trace[(j * 2 + w) * 16 + 12] = clock64();
                     tc_fence_after();
                     if (tracing) P.trace[(j * 2 + w) * 16 + 0] = clock64();
                     const uint32_t dwin = w * kTmemWindowCols;

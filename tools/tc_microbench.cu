@@ -127,14 +127,16 @@ template <int M, int N, int NKB, int TILES, int COLL, int MODE>
 __global__ void __launch_bounds__(160, 1) k_burst(int reps, Result* out) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
-    const uint32_t bar_mma = sbase + kSmemBar, bar_epi = sbase + kSmemBar + 8;
+    const uint32_t bar_mma = sbase + kSmemBar, bar_epi = sbase + kSmemBar + 8, bar_done = sbase + kSmemBar + 16;
     volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 32);
     const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
     for (int i = threadIdx.x; i < kSmemBar / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
     if (threadIdx.x == 0) {
         mbar_init(bar_mma, 1);
         mbar_init(bar_epi, 32);
+        mbar_init(bar_done, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive(bar_done);   // phase 0 of bar_done is complete from here on
     }
     if (warp == 0) {
         asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemBar + 32), "r"(512) : "memory");
@@ -155,7 +157,16 @@ __global__ void __launch_bounds__(160, 1) k_burst(int reps, Result* out) {
                 issue_burst<M, N, NKB, TILES, COLL>(sbase);
                 const long long t1 = clock64();
                 tc_commit(bar_mma);
-                if (MODE == 0) {
+                if (MODE == 2) {
+                    const long long ta = clock64();
+                    mbar_wait(bar_done, 0);          // completed long ago: how long does the poll take behind a commit?
+                    const long long tb = clock64();
+                    mbar_wait(bar_mma, ph);
+                    const long long t2 = clock64();
+                    if (t1 - t0 < best_issue) best_issue = t1 - t0;
+                    if (t2 - t0 < best_done) best_done = t2 - t0;
+                    if (tb - ta < best_rt) best_rt = tb - ta;
+                } else if (MODE == 0) {
                     mbar_wait(bar_mma, ph);
                     const long long t2 = clock64();
                     if (t1 - t0 < best_issue) best_issue = t1 - t0;
@@ -258,7 +269,10 @@ static void run_burst() {
     Result r;
     CK(cudaMemcpy(&r, d_res, sizeof(r), cudaMemcpyDeviceToHost));
     const int mmas = 3 * NKB * TILES;
-    if (MODE == 0)
+    if (MODE == 2)
+        std::printf("poll-after-commit M %3d N %3d nkb %d tiles %d | %3d MMAs | issue %6lld done %6lld | try_wait on a completed barrier right after the commit: %lld cycles\n",
+                    M, N, NKB, TILES, mmas, r.t_issue, r.t_done, r.t_roundtrip);
+    else if (MODE == 0)
         std::printf("burst M %3d N %3d nkb %d tiles %d coll %d | %3d MMAs | issue %6lld done %6lld | %.1f cyc/MMA\n", M, N, NKB,
                     TILES, COLL, mmas, r.t_issue, r.t_done, mmas ? static_cast<double>(r.t_done) / mmas : 0.0);
     else
@@ -288,6 +302,11 @@ int main() {
     run_shape<128, 128>();
     run_shape<128, 192>();
     run_shape<128, 256>();
+    run_burst<128, 48, 0, 1, 1, 2>();
+    run_burst<128, 48, 3, 1, 1, 2>();
+    run_burst<128, 48, 9, 1, 1, 2>();
+    run_burst<128, 48, 9, 4, 1, 2>();
+    run_burst<64, 48, 9, 1, 1, 2>();
     run_burst<128, 48, 0, 1, 1, 1>();
     run_burst<128, 48, 1, 1, 1, 1>();
     run_burst<128, 48, 3, 1, 1, 1>();
