@@ -3,7 +3,8 @@ Command line of the B200 classifier: the `classify` and `realtime` commands of r
 `deepbinner/deepbinner.py` with the same options, presets, defaults and validation messages
 (`classify_subparser` :90-106, `classify_and_realtime_options` :109-156, `realtime_subparser`
 :177-196, `check_classify_and_realtime_arguments` :283-317, `find_model` :320-345).  The reference's
-other sub-commands (bin, prep, balance, train, refine) are outside the accelerated hot path.
+`bin` (host-side text streaming, bin.py) completes the classify -> bin workflow; the other
+sub-commands (prep, balance, train, refine) are outside the accelerated hot path.
 The four TensorFlow thread knobs are accepted and ignored; `--device` selects the GPU.
 """
 
@@ -25,6 +26,7 @@ def main(argv=None):
     subparsers = parser.add_subparsers(title='Commands', dest='subparser_name')
     classify_subparser(subparsers)
     realtime_subparser(subparsers)
+    bin_subparser(subparsers)
 
     argv = sys.argv[1:] if argv is None else argv
     if not argv:
@@ -40,6 +42,9 @@ def main(argv=None):
         check_classify_and_realtime_arguments(args)
         from .realtime import realtime
         realtime(args)
+    elif args.subparser_name == 'bin':
+        from .bin import bin_reads
+        bin_reads(args)
     else:
         parser.print_help(file=sys.stderr)
         sys.exit(1)
@@ -67,6 +72,18 @@ def realtime_subparser(subparsers):
     group.add_argument('--stop', action='store_true',
                        help='Automatically stop when there are no more input reads (default: '
                             'continue to run and wait for more reads)')
+
+
+def bin_subparser(subparsers):
+    """`deepbinner bin` (reference deepbinner.py:159-174)."""
+    group = subparsers.add_parser('bin', description='Bin fasta/q reads')
+    required = group.add_argument_group('Required')
+    required.add_argument('--classes', type=str, required=True,
+                          help='Deepbinner classification file (made with the deepbinner classify '
+                               'command)')
+    required.add_argument('--reads', type=str, required=True, help='FASTA or FASTQ reads')
+    required.add_argument('--out_dir', type=str, required=True,
+                          help='Directory to output binned read files')
 
 
 def classify_and_realtime_options(group):
