@@ -390,10 +390,41 @@ struct WindowInput {
 // before anyone writes).  Thread t: channel-group t / 64, positions (t % 64) + 64 k, k = 0..7, so
 // the 48 per-channel parameters of its group are loaded once.
 constexpr int kStageOff = kActBytes - 4096;
-__device__ void conv1_stage(const TcParams& P, const WindowInput& in, uint32_t act, unsigned char* act_ptr,
-                            int tid) {
+// Per-thread conv1d_1 / BatchNorm_1 parameters of the thread's channel group (the same for both
+// windows of the CTA: fetched once, early, so the global-memory latency overlaps the kernel set-up).
+struct Conv1Params {
+    float w0[8], w1[8], w2[8], b[8], sc[8], sh[8];
+};
+__device__ __forceinline__ void load_conv1_params(const TcParams& P, int tid, Conv1Params& c) {
+    const int cg = tid >> 6;
+    const float4* w4 = reinterpret_cast<const float4*>(P.prm + P.conv1_w);   // [3][48]
+    const float4* b4 = reinterpret_cast<const float4*>(P.prm + P.conv1_b);
+    const float4* s4 = reinterpret_cast<const float4*>(P.prm + P.bn1_s);
+    const float4* h4 = reinterpret_cast<const float4*>(P.prm + P.bn1_h);
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {
+        const float4 a0 = __ldg(w4 + cg * 2 + q), a1 = __ldg(w4 + 12 + cg * 2 + q);
+        const float4 a2 = __ldg(w4 + 24 + cg * 2 + q), bb = __ldg(b4 + cg * 2 + q);
+        const float4 ss = __ldg(s4 + cg * 2 + q), hh = __ldg(h4 + cg * 2 + q);
+        c.w0[4 * q] = a0.x; c.w0[4 * q + 1] = a0.y; c.w0[4 * q + 2] = a0.z; c.w0[4 * q + 3] = a0.w;
+        c.w1[4 * q] = a1.x; c.w1[4 * q + 1] = a1.y; c.w1[4 * q + 2] = a1.z; c.w1[4 * q + 3] = a1.w;
+        c.w2[4 * q] = a2.x; c.w2[4 * q + 1] = a2.y; c.w2[4 * q + 2] = a2.z; c.w2[4 * q + 3] = a2.w;
+        c.b[4 * q] = bb.x; c.b[4 * q + 1] = bb.y; c.b[4 * q + 2] = bb.z; c.b[4 * q + 3] = bb.w;
+        c.sc[4 * q] = ss.x; c.sc[4 * q + 1] = ss.y; c.sc[4 * q + 2] = ss.z; c.sc[4 * q + 3] = ss.w;
+        c.sh[4 * q] = hh.x; c.sh[4 * q + 1] = hh.y; c.sh[4 * q + 2] = hh.z; c.sh[4 * q + 3] = hh.w;
+    }
+}
+// The thread's three input samples of a window (i = tid + 384 k), fetched ahead of use.
+__device__ __forceinline__ void fetch_window_inputs(const WindowInput& in, int tid, float (&xv)[3]) {
+#pragma unroll
+    for (int k = 0; k < 3; ++k) xv[k] = in.at(tid + k * kEpiThreads);
+}
+__device__ __forceinline__ void conv1_stage(const Conv1Params& c, float x0, float x1, float x2, uint32_t act,
+                                            unsigned char* act_ptr, int tid) {
     float* stage = reinterpret_cast<float*>(act_ptr + kStageOff);
-    for (int i = tid; i < kInputSize; i += kEpiThreads) stage[i] = in.at(i);
+    stage[tid] = x0;
+    stage[tid + kEpiThreads] = x1;
+    if (tid + 2 * kEpiThreads < kInputSize) stage[tid + 2 * kEpiThreads] = x2;
     epi_bar_sync();
     const int cg = tid >> 6, p0 = tid & 63;
     float xs[8][3];
@@ -406,34 +437,17 @@ __device__ void conv1_stage(const TcParams& P, const WindowInput& in, uint32_t a
         xs[k][2] = p < 511 ? stage[2 * p + 2] : 0.f;   // x[1024] = 0: TF SAME pads on the right
     }
     epi_bar_sync();   // all inputs are in registers; the staging area may now be overwritten
-    const float4* w4 = reinterpret_cast<const float4*>(P.prm + P.conv1_w);   // [3][48]
-    const float4* b4 = reinterpret_cast<const float4*>(P.prm + P.conv1_b);
-    const float4* s4 = reinterpret_cast<const float4*>(P.prm + P.bn1_s);
-    const float4* h4 = reinterpret_cast<const float4*>(P.prm + P.bn1_h);
-    float w0[8], w1[8], w2[8], b[8], sc[8], sh[8];
-#pragma unroll
-    for (int q = 0; q < 2; ++q) {
-        const float4 a0 = __ldg(w4 + cg * 2 + q), a1 = __ldg(w4 + 12 + cg * 2 + q);
-        const float4 a2 = __ldg(w4 + 24 + cg * 2 + q), bb = __ldg(b4 + cg * 2 + q);
-        const float4 ss = __ldg(s4 + cg * 2 + q), hh = __ldg(h4 + cg * 2 + q);
-        w0[4 * q] = a0.x; w0[4 * q + 1] = a0.y; w0[4 * q + 2] = a0.z; w0[4 * q + 3] = a0.w;
-        w1[4 * q] = a1.x; w1[4 * q + 1] = a1.y; w1[4 * q + 2] = a1.z; w1[4 * q + 3] = a1.w;
-        w2[4 * q] = a2.x; w2[4 * q + 1] = a2.y; w2[4 * q + 2] = a2.z; w2[4 * q + 3] = a2.w;
-        b[4 * q] = bb.x; b[4 * q + 1] = bb.y; b[4 * q + 2] = bb.z; b[4 * q + 3] = bb.w;
-        sc[4 * q] = ss.x; sc[4 * q + 1] = ss.y; sc[4 * q + 2] = ss.z; sc[4 * q + 3] = ss.w;
-        sh[4 * q] = hh.x; sh[4 * q + 1] = hh.y; sh[4 * q + 2] = hh.z; sh[4 * q + 3] = hh.w;
-    }
 #pragma unroll
     for (int k = 0; k < 8; ++k) {
         const int p = p0 + 64 * k;
         float v[8];
 #pragma unroll
         for (int e = 0; e < 8; ++e) {
-            float a = b[e];
-            a = fmaf(w0[e], xs[k][0], a);
-            a = fmaf(w1[e], xs[k][1], a);
-            a = fmaf(w2[e], xs[k][2], a);
-            v[e] = fmaf(sc[e], fmaxf(a, 0.f), sh[e]);
+            float a = c.b[e];
+            a = fmaf(c.w0[e], xs[k][0], a);
+            a = fmaf(c.w1[e], xs[k][1], a);
+            a = fmaf(c.w2[e], xs[k][2], a);
+            v[e] = fmaf(c.sc[e], fmaxf(a, 0.f), c.sh[e]);
         }
         uint4 hi, lo;
         split8(v, &hi, &lo);
@@ -791,13 +805,17 @@ __device__ __forceinline__ void pin_issue_args(const IssueArgs& a) {
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
-template <bool kCallMode>
+// kDiag: diagnostics build of the kernel (timeline stamps, early stop + ACT dump); the production
+// instantiations carry none of that code.
+template <bool kCallMode, bool kDiag>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_tc_forward(TcParams P, const float* __restrict__ x, const double* __restrict__ xd,
                  const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets, int n_reads,
                  int side, int n_windows, float* __restrict__ probs) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
+    long long* const trace = kDiag ? P.trace : nullptr;
+    const int dbg_job = kDiag ? P.dbg_job : -1;
     const uint32_t wbuf = sbase + kSmemWbuf;
     const uint32_t prm = sbase + kSmemPrm;
     const uint32_t bar0 = sbase + kSmemBar;
@@ -836,15 +854,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int njobs = (P.dbg_job >= 0 && P.dbg_job < P.njobs) ? P.dbg_job + 1 : P.njobs;
+    const int njobs = (dbg_job >= 0 && dbg_job < P.njobs) ? dbg_job + 1 : P.njobs;
 
     if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
         // ================= epilogue / CUDA-core warps =================
         const int tid = static_cast<int>(threadIdx.x) - kEpiWarp0 * 32;   // epilogue-relative thread id
         const int ewarp = tid >> 5;
-        if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[31 * 32 + 0] = clock64();
-        for (int i = tid; i < P.prm_floats / 4; i += kEpiThreads)
-            reinterpret_cast<float4*>(smem + kSmemPrm)[i] = __ldg(reinterpret_cast<const float4*>(P.prm) + i);
+        if (trace && blockIdx.x == 0 && tid == 0) trace[31 * 32 + 0] = clock64();
         int win[2];
         bool valid[2];
         for (int w = 0; w < 2; ++w) {
@@ -852,17 +868,33 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             valid[w] = idx < n_windows;
             win[w] = valid[w] ? idx : n_windows - 1;
         }
+        // Issue every global load of the prologue up front (conv1 parameters, in predict mode the
+        // samples of BOTH windows, the per-job parameter block) so that their latencies overlap.
+        Conv1Params c1;
+        load_conv1_params(P, tid, c1);
+        WindowInput in[2] = {};
+        float xv[2][3];
+        if (!kCallMode) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                if (x) in[w].x = x + static_cast<size_t>(win[w]) * kInputSize;
+                else in[w].xd = xd + static_cast<size_t>(win[w]) * kInputSize;
+                fetch_window_inputs(in[w], tid, xv[w]);
+            }
+        }
+        for (int i = tid; i < P.prm_floats / 4; i += kEpiThreads)
+            reinterpret_cast<float4*>(smem + kSmemPrm)[i] = __ldg(reinterpret_cast<const float4*>(P.prm) + i);
+#pragma unroll
         for (int w = 0; w < 2; ++w) {
-            WindowInput in{};
             if (kCallMode) {
                 const int step = win[w] / n_reads, read = win[w] % n_reads;
                 const int64_t off = offsets[read];
-                in.region = samples + off;
-                in.g = window_geometry(static_cast<int>(offsets[read + 1] - off), step, side);
+                in[w].region = samples + off;
+                in[w].g = window_geometry(static_cast<int>(offsets[read + 1] - off), step, side);
                 // exact integer sums over the slice, reduced over the 384 threads
                 long long s1 = 0, s2 = 0;
-                for (int i = tid; i < in.g.n; i += kEpiThreads) {
-                    const long long v = in.region[in.g.a + i];
+                for (int i = tid; i < in[w].g.n; i += kEpiThreads) {
+                    const long long v = in[w].region[in[w].g.a + i];
                     s1 += v;
                     s2 += v * v;
                 }
@@ -876,17 +908,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 epi_bar_sync();
                 s1 = 0; s2 = 0;
                 for (int i = 0; i < kEpiWarps; ++i) { s1 += red[i]; s2 += red[12 + i]; }
-                in.mean = 0.0; in.stdev = 0.0;
-                if (in.g.n > 0) zscore_params(s1, s2, in.g.n, &in.mean, &in.stdev);
-            } else if (x) {
-                in.x = x + static_cast<size_t>(win[w]) * kInputSize;
-            } else {
-                in.xd = xd + static_cast<size_t>(win[w]) * kInputSize;
+                in[w].mean = 0.0; in[w].stdev = 0.0;
+                if (in[w].g.n > 0) zscore_params(s1, s2, in[w].g.n, &in[w].mean, &in[w].stdev);
+                fetch_window_inputs(in[w], tid, xv[w]);
             }
-            conv1_stage(P, in, sbase + (w ? kSmemAct1 : kSmemAct0), smem + (w ? kSmemAct1 : kSmemAct0), tid);
+            conv1_stage(c1, xv[w][0], xv[w][1], xv[w][2], sbase + (w ? kSmemAct1 : kSmemAct0),
+                        smem + (w ? kSmemAct1 : kSmemAct0), tid);
             fence_proxy_async();
             mbar_arrive(bar_epi[w]);
-            if (P.trace && blockIdx.x == 0 && tid == 0) P.trace[31 * 32 + 1 + w] = clock64();
+            if (trace && blockIdx.x == 0 && tid == 0) trace[31 * 32 + 1 + w] = clock64();
         }
         epi_bar_sync();   // parameter block staged by all epilogue threads is now visible
         uint32_t mma_phase[2] = {0, 0};
@@ -898,7 +928,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             if (!J.last) continue;
             if (J.joint) {   // one pass serves both windows
                 const int e = J.eseq;
-                long long* tr = (P.trace && blockIdx.x == 0 && tid == 0) ? P.trace + (j * 2) * 16 : nullptr;
+                long long* tr = (trace && blockIdx.x == 0 && tid == 0) ? trace + (j * 2) * 16 : nullptr;
                 run_epilogue(P, J, sbase + kSmemAct0, sbase + kSmemAct0, 0, prm, tmem_base + J.tcol, tid,
                              bar_jmma + 8 * (e & 3), (e >> 2) & 1, p0, p1, tr);
                 if (tr) tr[6] = clock64();
@@ -911,7 +941,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             }
             for (int w = 0; w < 2; ++w) {
                 const uint32_t act = sbase + (w ? kSmemAct1 : kSmemAct0);
-                long long* tr = (P.trace && blockIdx.x == 0 && tid == 0) ? P.trace + (j * 2 + w) * 16 : nullptr;
+                long long* tr = (trace && blockIdx.x == 0 && tid == 0) ? trace + (j * 2 + w) * 16 : nullptr;
                 run_epilogue(P, J, act, sbase + kSmemAct0, w, prm, tmem_base + w * kTmemWindowCols, tid,
                              bar_mma[w], mma_phase[w], p0, p1, tr);
                 mma_phase[w] ^= 1;
@@ -923,7 +953,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (tr) tr[3] = clock64();
             }
         }
-        if (P.dbg_job >= 0) {   // debug: dump both ACT regions after the last processed job
+        if (dbg_job >= 0) {   // debug: dump both ACT regions after the last processed job
             mbar_wait(bar_final, 0);
             epi_bar_sync();
             if (blockIdx.x == 0)
@@ -937,7 +967,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (tmem_base != 0) __trap();
         if (elect_one()) {
             constexpr uint32_t leader = 1;   // (a converged-warp variant with predicated tcgen05 ops was slower: R2UR.BROADCAST per operand)
-            const bool tracing = P.trace && blockIdx.x == 0;
+            const bool tracing = trace && blockIdx.x == 0;
             uint32_t wfull_phase = 0, epi_phase[2] = {0, 0};
             int jepi_seen = 0;   // joint epilogues known to be complete
             const uint32_t wp16[2] = {wbuf >> 4, (wbuf + kWPart0) >> 4};
@@ -951,7 +981,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t blk16 = 2u * J.n;                 // one K=16 block of B, in 16-byte units
                 const uint32_t tap16[3] = {J.tap16[0], J.tap16[1], J.tap16[2]};
                 const bool first = J.first != 0, last = J.last != 0;
-                if (tracing) P.trace[(j * 2) * 16 + 11] = clock64();
+                if (tracing) trace[(j * 2) * 16 + 11] = clock64();
                 if (J.joint) {
                     // ---- both windows in one burst: [part 0: w0, w1] [part 1: w0, w1], one commit ----
                     if (first && J.eseq == 0) {   // first joint job: the per-window epilogues of the last
@@ -963,26 +993,26 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     for (const int need = J.need; jepi_seen < need; ++jepi_seen)
                         mbar_wait(bar_jepi + 8 * (jepi_seen & 3), (jepi_seen >> 2) & 1);
                     tc_fence_after();
-                    if (tracing) P.trace[(j * 2) * 16 + 0] = clock64();
+                    if (tracing) trace[(j * 2) * 16 + 0] = clock64();
                     const int nw = J.joint == JOINT_PAIR ? 2 : 1;
                     const uint32_t dcol = J.tcol;
                     mbar_wait(bar_wfull[0], wfull_phase);
-                    if (tracing) P.trace[(j * 2) * 16 + 8] = clock64();
+                    if (tracing) trace[(j * 2) * 16 + 8] = clock64();
                     for (int w = 0; w < nw; ++w)
                         issue_job_part<0>(J.ntaps, J.ncb, dcol + (static_cast<uint32_t>(16 * w) << 16), 1,
                                           (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[0], blk16, J.n,
                                           J.idesc, first, leader);
                     tc_commit(bar_wfree[0], leader);
-                    if (tracing) P.trace[(j * 2) * 16 + 9] = clock64();
+                    if (tracing) trace[(j * 2) * 16 + 9] = clock64();
                     mbar_wait(bar_wfull[1], wfull_phase);
-                    if (tracing) P.trace[(j * 2) * 16 + 10] = clock64();
+                    if (tracing) trace[(j * 2) * 16 + 10] = clock64();
                     for (int w = 0; w < nw; ++w)
                         issue_job_part<1>(J.ntaps, J.ncb, dcol + (static_cast<uint32_t>(16 * w) << 16), 1,
                                           (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[1], blk16, J.n,
                                           J.idesc, false, leader);
                     if (last) tc_commit(bar_jmma + 8 * (J.eseq & 3), leader);
                     tc_commit(bar_wfree[1], leader);
-                    if (tracing) P.trace[(j * 2) * 16 + 1] = clock64();
+                    if (tracing) trace[(j * 2) * 16 + 1] = clock64();
                     wfull_phase ^= 1;
                     pin_issue_args(nxt);
                     continue;
@@ -992,25 +1022,25 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         mbar_wait(bar_epi[w], epi_phase[w]);
                         epi_phase[w] ^= 1;
                     }
-                    if (tracing) P.trace[(j * 2 + w) * 16 + 12] = clock64();
+                    if (tracing) trace[(j * 2 + w) * 16 + 12] = clock64();
                     tc_fence_after();
-                    if (tracing) P.trace[(j * 2 + w) * 16 + 0] = clock64();
+                    if (tracing) trace[(j * 2 + w) * 16 + 0] = clock64();
                     const uint32_t dwin = w * kTmemWindowCols;
                     // ---- weight part 0 (first K blocks); freed early so the loader can refill it ----
                     if (w == 0) mbar_wait(bar_wfull[0], wfull_phase);
-                    if (tracing) P.trace[(j * 2 + w) * 16 + 8] = clock64();
+                    if (tracing) trace[(j * 2 + w) * 16 + 8] = clock64();
                     issue_job_part<0>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[0],
                                       blk16, J.n, J.idesc, first, leader);
                     if (w == 1) tc_commit(bar_wfree[0], leader);
-                    if (tracing) P.trace[(j * 2 + w) * 16 + 9] = clock64();
+                    if (tracing) trace[(j * 2 + w) * 16 + 9] = clock64();
                     // ---- weight part 1 (remaining K blocks) ----
                     if (w == 0) mbar_wait(bar_wfull[1], wfull_phase);
-                    if (tracing) P.trace[(j * 2 + w) * 16 + 10] = clock64();
+                    if (tracing) trace[(j * 2 + w) * 16 + 10] = clock64();
                     issue_job_part<1>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[1],
                                       blk16, J.n, J.idesc, false, leader);
                     if (last) tc_commit(bar_mma[w], leader);
                     if (w == 1) tc_commit(bar_wfree[1], leader);
-                    if (tracing) P.trace[(j * 2 + w) * 16 + 1] = clock64();
+                    if (tracing) trace[(j * 2 + w) * 16 + 1] = clock64();
                 }
                 wfull_phase ^= 1;
                 pin_issue_args(nxt);
@@ -1298,8 +1328,9 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
               cudaMalloc(&e->d_prm, B.prm.size() * sizeof(float)) == cudaSuccess &&
               cudaMemcpy(e->d_w, B.w.data(), B.w.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(e->d_prm, B.prm.data(), B.prm.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaFuncSetAttribute(k_tc_forward<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
-              cudaFuncSetAttribute(k_tc_forward<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess;
+              cudaFuncSetAttribute(k_tc_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+              cudaFuncSetAttribute(k_tc_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+              cudaFuncSetAttribute(k_tc_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         tc_destroy(e);
@@ -1343,7 +1374,7 @@ int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, flo
                cudaStream_t st) {
     if (int rc = sync_jobs(e)) return rc;
     const int grid = static_cast<int>((n + 1) / 2);
-    k_tc_forward<false><<<grid, kTcThreads, kTcSmemBytes, st>>>(e->params, d_x, d_xd, nullptr, nullptr,
+    k_tc_forward<false, false><<<grid, kTcThreads, kTcSmemBytes, st>>>(e->params, d_x, d_xd, nullptr, nullptr,
                                                                0, 0, static_cast<int>(n), d_probs);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(DBN_ECUDA, "tcgen05 kernel launch failed: %s", cudaGetErrorString(err));
@@ -1354,7 +1385,7 @@ int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offs
                     int side, int steps, float* d_step_probs, cudaStream_t st) {
     if (int rc = sync_jobs(e)) return rc;
     const int n = n_reads * steps;
-    k_tc_forward<true><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(e->params, nullptr, nullptr, d_samples,
+    k_tc_forward<true, false><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(e->params, nullptr, nullptr, d_samples,
                                                                       d_offsets, n_reads, side, n,
                                                                       d_step_probs);
     cudaError_t err = cudaGetLastError();
@@ -1370,7 +1401,7 @@ int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_
     if (int rc = sync_jobs(e)) return rc;
     TcParams P = e->params;
     P.trace = d_trace;
-    k_tc_forward<false><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0,
+    k_tc_forward<false, true><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0,
                                                                       n, d_probs);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(DBN_ECUDA, "tcgen05 trace launch failed: %s", cudaGetErrorString(err));
@@ -1383,7 +1414,7 @@ int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, 
     TcParams P = e->params;
     P.dbg_job = job;
     P.dbg_out = d_out;
-    k_tc_forward<false><<<1, kTcThreads, kTcSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0, 2,
+    k_tc_forward<false, true><<<1, kTcThreads, kTcSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0, 2,
                                                             nullptr);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(DBN_ECUDA, "tcgen05 debug launch failed: %s", cudaGetErrorString(err));
