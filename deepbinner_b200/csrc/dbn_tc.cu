@@ -15,17 +15,29 @@
 //
 // A whole layer's output for one window (up to 4 tiles x 48 fp32 columns) lives in TMEM, so the
 // epilogue (bias, ReLU, [MaxPool2], [BatchNorm affine], hi/lo split) can overwrite the layer's
-// input in place once its MMAs have completed; the two windows of a CTA alternate so that the
-// tensor pipe works on one while the epilogue warps drain the other.  The network is a table of 21
-// MMA jobs in constant memory (conv1d_12 + conv1d_14 share one job; conv1d_17 is four K-slices);
-// from conv1d_17 on both windows are stacked in ONE M=128 tile (row = 18 w + position).
+// input in place once its MMAs have completed.  The network is a table of 21 MMA jobs in constant
+// memory, in two phases:
+//   * conv1d_2 .. conv1d_9 (L = 512 .. 128): one pass per window, M=128 tiles; the two windows of
+//     the CTA alternate so that the tensor pipe works on one while the epilogue warps drain the other;
+//   * "joint" jobs from the inception block on (L <= 64): ONE MMA burst and ONE epilogue pass serve
+//     both windows.  Inception (conv1d_10 .. 16): an M=64 MMA set per window into the same
+//     accumulator columns, window 0 in TMEM lanes 0-15 and window 1 in lanes 16-31 of every lane
+//     quadrant, so all 32 lanes of every epilogue warp carry rows.  conv1d_12 + conv1d_14 share one
+//     job (N = 32); the AveragePooling1D in front of conv1d_10 is folded into its weights (k=3, W/3,
+//     end rows rescaled by 1.5 in the epilogue).  conv1d_17 .. 20: both windows stacked in one tensor
+//     (row = 18 w + position), conv1d_17 as four K-slices.  Joint jobs rotate over three accumulator
+//     slots and are ordered so that independent branches sit between dependent ones; each carries
+//     the number of joint epilogues that must be complete before it may issue (`need`), which lets
+//     the tensor pipe run up to two jobs ahead of the epilogue warps.
 //
-// Warp roles (448 threads): warp 0 = TMEM allocator + MMA issuer (one elected lane, operands on
-// the uniform datapath), warp 1 = weight loader (cp.async.bulk + mbarrier; each job's weights come
-// in two K-block parts so the next job's first part streams in while the second is still in use),
-// warps 2-13 = epilogue (TMEM lane quadrant = warp % 4, 16 accumulator columns per warp) and the
-// CUDA-core stages (z-score + conv1d_1, average pool, softmax head).  The control warps have the
-// lowest warp ids because the scheduler favours higher ones.
+// Warp roles (448 threads): warps 0-11 = epilogue (TMEM lane quadrant = warp % 4, 16 accumulator
+// columns per warp) and the CUDA-core stages (z-score + conv1d_1, softmax head); warp 12 = weight
+// loader (cp.async.bulk + mbarrier; each job's weights come in two K-block parts so the next job's
+// first part streams in while the second is still in use); warp 13 = TMEM allocator + MMA issuer (one
+// elected lane).  The issuer is a single thread (one dependent instruction every ~4 cycles, slower
+// when the epilogue warps of its scheduler are busy), so everything it does between two MMAs
+// matters: job descriptors are fetched one job ahead, tcgen05 descriptors are built from
+// pre-shifted fields, and all diagnostics live in a separate kernel instantiation.
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 

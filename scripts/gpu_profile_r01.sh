@@ -1,16 +1,17 @@
-# Round-1 evidence run: GPU tests, smoke, bench (both engines), ncu launch list + full capture of the
-# top kernel, clocks.  Everything lands in gpurun_out/.
+# Round-1 evidence run: GPU tests, smoke, bench (both engines + reference arm), ncu launch list +
+# full capture of the top kernel, timeline, micro-benchmark, clocks.  Everything lands in gpurun_out/.
 set -x
 mkdir -p gpurun_out
 nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,clocks.mem,power.draw --format=csv > gpurun_out/r01_nvidia_smi.csv
 timeout 900 python -m pytest tests -m gpu -q 2>&1 | tail -5 > gpurun_out/r01_pytest_gpu.txt
 cat gpurun_out/r01_pytest_gpu.txt
 timeout 300 python -c "import __graft_entry__ as g; g.smoke()" > gpurun_out/r01_smoke.txt 2>&1; tail -4 gpurun_out/r01_smoke.txt
+timeout 600 python bench.py --impl reference --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/r01_bench_reference.json
 timeout 900 python bench.py --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/r01_bench_tcgen05.json
 timeout 900 python bench.py --steps 10 --warmup 3 --engine fp32 --no-cpu-baseline 2>&1 | tail -1 > gpurun_out/r01_bench_fp32.json
-timeout 600 python bench.py --impl reference --steps 20 --warmup 3 2>&1 | tail -1 > gpurun_out/r01_bench_reference.json
 cut -c1-300 gpurun_out/r01_bench_tcgen05.json gpurun_out/r01_bench_fp32.json gpurun_out/r01_bench_reference.json
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 200 --csv --log-file gpurun_out/r01_launches_tcgen05.csv python bench.py --steps 2 --warmup 3 --shard 8192 --no-cpu-baseline > gpurun_out/r01_ncu_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tc_forward -s 8 -c 2 -o gpurun_out/r01_prof_tcgen05 python bench.py --steps 1 --warmup 3 --shard 2048 --no-cpu-baseline > gpurun_out/r01_ncu_full.log 2>&1
 timeout 300 python tools/tc_timeline.py 296 > gpurun_out/r01_tc_timeline.txt 2>&1
+timeout 120 ./tools/tc_microbench > gpurun_out/r01_tc_microbench.txt 2>&1
 ls -la gpurun_out
