@@ -844,7 +844,35 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // convergent regions and the MMA issuer's address arithmetic can use the uniform datapath
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-    if (threadIdx.x == 0) {
+    // Epilogue threads issue every global load of the prologue BEFORE the set-up barrier (conv1
+    // parameters, in predict mode the samples of BOTH windows): their latency overlaps the barrier
+    // initialisation and the TMEM allocation, which the otherwise idle loader warp / MMA warp do.
+    const bool is_epi = warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps;
+    int win[2];
+    bool valid[2];
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+        const int idx = 2 * blockIdx.x + w;
+        valid[w] = idx < n_windows;
+        win[w] = valid[w] ? idx : n_windows - 1;
+    }
+    Conv1Params c1;
+    WindowInput in[2] = {};
+    float xv[2][3];
+    if (is_epi) {
+        const int etid = static_cast<int>(threadIdx.x) - kEpiWarp0 * 32;
+        load_conv1_params(P, etid, c1);
+        if (!kCallMode) {
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                if (x) in[w].x = x + static_cast<size_t>(win[w]) * kInputSize;
+                else in[w].xd = xd + static_cast<size_t>(win[w]) * kInputSize;
+                fetch_window_inputs(in[w], etid, xv[w]);
+            }
+        }
+    }
+
+    if (threadIdx.x == kLoadWarp * 32) {
         mbar_init(bar_wfull[0], 1);
         mbar_init(bar_wfull[1], 1);
         mbar_init(bar_wfree[0], 1);
@@ -868,32 +896,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 
     const int njobs = (dbg_job >= 0 && dbg_job < P.njobs) ? dbg_job + 1 : P.njobs;
 
-    if (warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps) {
+    if (is_epi) {
         // ================= epilogue / CUDA-core warps =================
         const int tid = static_cast<int>(threadIdx.x) - kEpiWarp0 * 32;   // epilogue-relative thread id
         const int ewarp = tid >> 5;
         if (trace && blockIdx.x == 0 && tid == 0) trace[31 * 32 + 0] = clock64();
-        int win[2];
-        bool valid[2];
-        for (int w = 0; w < 2; ++w) {
-            const int idx = 2 * blockIdx.x + w;
-            valid[w] = idx < n_windows;
-            win[w] = valid[w] ? idx : n_windows - 1;
-        }
-        // Issue every global load of the prologue up front (conv1 parameters, in predict mode the
-        // samples of BOTH windows, the per-job parameter block) so that their latencies overlap.
-        Conv1Params c1;
-        load_conv1_params(P, tid, c1);
-        WindowInput in[2] = {};
-        float xv[2][3];
-        if (!kCallMode) {
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                if (x) in[w].x = x + static_cast<size_t>(win[w]) * kInputSize;
-                else in[w].xd = xd + static_cast<size_t>(win[w]) * kInputSize;
-                fetch_window_inputs(in[w], tid, xv[w]);
-            }
-        }
         for (int i = tid; i < P.prm_floats / 4; i += kEpiThreads)
             reinterpret_cast<float4*>(smem + kSmemPrm)[i] = __ldg(reinterpret_cast<const float4*>(P.prm) + i);
 #pragma unroll
