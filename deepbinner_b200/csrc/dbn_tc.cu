@@ -41,6 +41,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdio>
 #include <cstring>
 #include <string>
@@ -160,6 +161,7 @@ __device__ __forceinline__ void prefetch_job(int j) {
 
 struct TcParams {
     int njobs;
+    const struct TcJob* jobs;   // global-memory copy of the job table (the MMA issuer prefetches from it)
     const unsigned char* w;   // packed bf16 weights
     const float* prm;         // global copy of the smem parameter block + conv1 parameters
     int prm_floats;
@@ -216,6 +218,21 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
         if (spin > (1u << 26)) __trap();
+}
+// Non-blocking probe of a phase.  The MMA issuer uses it to look at the barrier of its NEXT wait
+// early: a poll queues behind the epilogue warps' shared-memory traffic (hundreds of cycles when
+// they are storing), so the probe is issued before the current MMAs and its result is only read
+// when the wait is due - a phase that had completed by then costs nothing.
+__device__ __forceinline__ bool mbar_test(uint32_t bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(bar), "r"(parity)
+        : "memory");
+    return ok != 0;
 }
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
     asm volatile(
@@ -798,22 +815,32 @@ struct IssueArgs {
     uint32_t n, idesc, ntiles, lp, lo16, cb0, tcol, tap16[3];
     int ntaps, ncb, first, last, joint, need, eseq;
 };
-__device__ __forceinline__ IssueArgs load_issue_args(const TcJob& J) {
+// Issued as volatile loads: the instructions sit exactly where this is called (the top of the
+// previous job's iteration) and their results are first touched one job later, so the whole
+// latency is hidden.  (Plain loads of the __constant__ table were sunk by the compiler to their first
+// use, which put a constant-cache miss of several hundred cycles between every two jobs.)
+__device__ __forceinline__ uint4 ldg_volatile_v4(const void* p) {
+    uint4 v;
+    asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ IssueArgs load_issue_args(const TcJob* J) {
+    const uint4* q = reinterpret_cast<const uint4*>(J);
+    const uint4 a0 = ldg_volatile_v4(q), a1 = ldg_volatile_v4(q + 1), a2 = ldg_volatile_v4(q + 2);
+    const uint4 a3 = ldg_volatile_v4(q + 3), a4 = ldg_volatile_v4(q + 4), a7 = ldg_volatile_v4(q + 7);
     IssueArgs a;
-    a.n = J.n; a.idesc = J.idesc; a.ntiles = J.ntiles; a.lp = J.lp; a.lo16 = J.lo16; a.cb0 = J.cb0; a.tcol = J.tcol;
-    a.tap16[0] = J.tap16[0]; a.tap16[1] = J.tap16[1]; a.tap16[2] = J.tap16[2];
-    a.ntaps = J.ntaps; a.ncb = J.ncb; a.first = J.first; a.last = J.last; a.joint = J.joint; a.need = J.need;
-    a.eseq = J.eseq;
+    a.n = a0.x; a.idesc = a0.y; a.ntiles = a0.z;                       // n, idesc, ntiles, L
+    a.lp = a1.x; a.ntaps = a1.y; a.tap16[0] = a1.z; a.tap16[1] = a1.w;  // lp, ntaps, tap16[0], tap16[1]
+    a.tap16[2] = a2.x; a.lo16 = a2.y; a.ncb = a2.z; a.cb0 = a2.w;       // tap16[2], lo16, ncb, cb0
+    a.tcol = a3.y;                                                     // w_goff, tcol, w_part[2]
+    a.first = a4.x; a.last = a4.y;                                     // first, last, kind, bias_off
+    a.joint = a7.y; a.need = a7.z; a.eseq = a7.w;                      // zero_y, joint, need, eseq
     return a;
 }
-// Consume the values so that the constant loads above are scheduled before this point (i.e. behind
-// the MMA burst of the current job) instead of being sunk to their first use in the next iteration.
-__device__ __forceinline__ void pin_issue_args(const IssueArgs& a) {
-    asm volatile("" ::"r"(a.n), "r"(a.idesc), "r"(a.ntiles), "r"(a.lp), "r"(a.lo16), "r"(a.cb0), "r"(a.tcol),
-                 "r"(a.tap16[0]), "r"(a.tap16[1]), "r"(a.tap16[2]), "r"(a.ntaps), "r"(a.ncb), "r"(a.first),
-                 "r"(a.last), "r"(a.joint), "r"(a.need), "r"(a.eseq));
-}
-
+static_assert(offsetof(TcJob, lp) == 16 && offsetof(TcJob, tap16) == 24 && offsetof(TcJob, lo16) == 36 &&
+                  offsetof(TcJob, cb0) == 44 && offsetof(TcJob, tcol) == 52 && offsetof(TcJob, first) == 64 &&
+                  offsetof(TcJob, joint) == 116 && offsetof(TcJob, eseq) == 124,
+              "load_issue_args reads TcJob by 16-byte words");
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -989,33 +1016,41 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             const bool tracing = trace && blockIdx.x == 0;
             uint32_t wfull_phase = 0, epi_phase[2] = {0, 0};
             int jepi_seen = 0;   // joint epilogues known to be complete
+            bool pre_epi[2] = {false, false}, pre_wfull0 = false;   // early probes that already succeeded
             const uint32_t wp16[2] = {wbuf >> 4, (wbuf + kWPart0) >> 4};
             const uint32_t act16_0 = (sbase + kSmemAct0) >> 4, act16_1 = (sbase + kSmemAct1) >> 4;
             // The issuer is ONE thread: a chain of dependent constant loads costs it ~40 cycles per
-            // link, so the next job's descriptor is fetched while this job's MMAs are issued.
-            IssueArgs nxt = load_issue_args(c_jobs[0]);
+            // link, so the next job's descriptor is fetched (from the global copy of the table) while
+            // this job's MMAs are issued.
+            IssueArgs nxt = load_issue_args(P.jobs);
             for (int j = 0; j < njobs; ++j) {
                 const IssueArgs J = nxt;
-                if (j + 1 < njobs) nxt = load_issue_args(c_jobs[j + 1]);
+                if (j + 1 < njobs) nxt = load_issue_args(P.jobs + j + 1);
                 const uint32_t blk16 = 2u * J.n;                 // one K=16 block of B, in 16-byte units
                 const uint32_t tap16[3] = {J.tap16[0], J.tap16[1], J.tap16[2]};
                 const bool first = J.first != 0, last = J.last != 0;
                 if (tracing) trace[(j * 2) * 16 + 11] = clock64();
                 if (J.joint) {
                     // ---- both windows in one burst: [part 0: w0, w1] [part 1: w0, w1], one commit ----
+                    // weights first (normally landed long ago; the poll then overlaps the wait for the
+                    // job's input instead of following it), part 1 only probed
+                    if (!pre_wfull0) mbar_wait(bar_wfull[0], wfull_phase);
+                    pre_wfull0 = false;
+                    bool pre_wfull1 = mbar_test(bar_wfull[1], wfull_phase);
                     if (first && J.eseq == 0) {   // first joint job: the per-window epilogues of the last
+#pragma unroll
                         for (int w = 0; w < 2; ++w) {   // single-window job must be done
-                            mbar_wait(bar_epi[w], epi_phase[w]);
+                            if (!pre_epi[w]) mbar_wait(bar_epi[w], epi_phase[w]);
                             epi_phase[w] ^= 1;
                         }
                     }
                     for (const int need = J.need; jepi_seen < need; ++jepi_seen)
                         mbar_wait(bar_jepi + 8 * (jepi_seen & 3), (jepi_seen >> 2) & 1);
+                    if (!pre_wfull1) pre_wfull1 = mbar_test(bar_wfull[1], wfull_phase);
                     tc_fence_after();
                     if (tracing) trace[(j * 2) * 16 + 0] = clock64();
                     const int nw = J.joint == JOINT_PAIR ? 2 : 1;
                     const uint32_t dcol = J.tcol;
-                    mbar_wait(bar_wfull[0], wfull_phase);
                     if (tracing) trace[(j * 2) * 16 + 8] = clock64();
                     for (int w = 0; w < nw; ++w)
                         issue_job_part<0>(J.ntaps, J.ncb, dcol + (static_cast<uint32_t>(16 * w) << 16), 1,
@@ -1023,7 +1058,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                                           J.idesc, first, leader);
                     tc_commit(bar_wfree[0], leader);
                     if (tracing) trace[(j * 2) * 16 + 9] = clock64();
-                    mbar_wait(bar_wfull[1], wfull_phase);
+                    if (!pre_wfull1) mbar_wait(bar_wfull[1], wfull_phase);
                     if (tracing) trace[(j * 2) * 16 + 10] = clock64();
                     for (int w = 0; w < nw; ++w)
                         issue_job_part<1>(J.ntaps, J.ncb, dcol + (static_cast<uint32_t>(16 * w) << 16), 1,
@@ -1033,12 +1068,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     tc_commit(bar_wfree[1], leader);
                     if (tracing) trace[(j * 2) * 16 + 1] = clock64();
                     wfull_phase ^= 1;
-                    pin_issue_args(nxt);
+                    if (j + 1 < njobs) pre_wfull0 = mbar_test(bar_wfull[0], wfull_phase);
                     continue;
                 }
+#pragma unroll
                 for (int w = 0; w < 2; ++w) {
                     if (first) {   // input written and previous accumulators drained
-                        mbar_wait(bar_epi[w], epi_phase[w]);
+                        if (!pre_epi[w]) mbar_wait(bar_epi[w], epi_phase[w]);
+                        pre_epi[w] = false;
                         epi_phase[w] ^= 1;
                     }
                     if (tracing) trace[(j * 2 + w) * 16 + 12] = clock64();
@@ -1046,7 +1083,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     if (tracing) trace[(j * 2 + w) * 16 + 0] = clock64();
                     const uint32_t dwin = w * kTmemWindowCols;
                     // ---- weight part 0 (first K blocks); freed early so the loader can refill it ----
-                    if (w == 0) mbar_wait(bar_wfull[0], wfull_phase);
+                    if (w == 0 && !pre_wfull0) mbar_wait(bar_wfull[0], wfull_phase);
+                    if (w == 0) pre_wfull0 = false;
                     if (tracing) trace[(j * 2 + w) * 16 + 8] = clock64();
                     issue_job_part<0>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[0],
                                       blk16, J.n, J.idesc, first, leader);
@@ -1055,6 +1093,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     // ---- weight part 1 (remaining K blocks) ----
                     if (w == 0) mbar_wait(bar_wfull[1], wfull_phase);
                     if (tracing) trace[(j * 2 + w) * 16 + 10] = clock64();
+                    // probe the barrier of the NEXT pass now; the answer arrives while part 1 is issued
+                    if (w == 0) pre_epi[1] = mbar_test(bar_epi[1], epi_phase[1]);
+                    else pre_epi[0] = mbar_test(bar_epi[0], epi_phase[0]);
                     issue_job_part<1>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[1],
                                       blk16, J.n, J.idesc, false, leader);
                     if (last) tc_commit(bar_mma[w], leader);
@@ -1062,7 +1103,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     if (tracing) trace[(j * 2 + w) * 16 + 1] = clock64();
                 }
                 wfull_phase ^= 1;
-                pin_issue_args(nxt);
+                if (j + 1 < njobs) pre_wfull0 = mbar_test(bar_wfull[0], wfull_phase);
             }
             tc_commit(bar_final, leader);
             mbar_wait(bar_final, 0);
@@ -1094,6 +1135,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // ---------------------------------------------------------------------------------------------
 struct TcEngine {
     unsigned char* d_w = nullptr;
+    TcJob* d_jobs = nullptr;
     float* d_prm = nullptr;
     TcParams params{};
     int njobs = 0;
@@ -1347,6 +1389,8 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
               cudaMalloc(&e->d_prm, B.prm.size() * sizeof(float)) == cudaSuccess &&
               cudaMemcpy(e->d_w, B.w.data(), B.w.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(e->d_prm, B.prm.data(), B.prm.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc(&e->d_jobs, B.jobs.size() * sizeof(TcJob)) == cudaSuccess &&
+              cudaMemcpy(e->d_jobs, B.jobs.data(), B.jobs.size() * sizeof(TcJob), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaFuncSetAttribute(k_tc_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
               cudaFuncSetAttribute(k_tc_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
               cudaFuncSetAttribute(k_tc_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess;
@@ -1358,6 +1402,7 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
     e->njobs = static_cast<int>(B.jobs.size());
     P.njobs = e->njobs;
     P.w = e->d_w;
+    P.jobs = e->d_jobs;
     P.prm = e->d_prm;
     P.dbg_job = -1;
     P.dbg_out = nullptr;
@@ -1369,6 +1414,7 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
 void tc_destroy(TcEngine* e) {
     if (!e) return;
     cudaFree(e->d_w);
+    cudaFree(e->d_jobs);
     cudaFree(e->d_prm);
     delete e;
 }
