@@ -20,7 +20,7 @@ import numpy as np
 
 from . import hdf5_lite, weights
 from .load_fast5s import (find_all_fast5s, get_read_id_and_signal, determine_single_or_multi_fast5s,
-                          read_fast5_batch)
+                          read_fast5_batch, read_fast5_batch_packed)
 from .misc import print_summary_table
 from .model import B200Model, signals_fit_int16
 from .trim_signal import normalise
@@ -117,16 +117,11 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
     prefetcher = concurrent.futures.ThreadPoolExecutor(max_workers=1)
     pending = prefetcher.submit(load_batch, batches[0], keep)
     for index, batch in enumerate(batches):
-        read_ids, signals = [], []
-        loaded = pending.result()
+        read_ids, signals, kept = pending.result()   # unreadable files are skipped (reference :135-136)
         if index + 1 < len(batches):
             pending = prefetcher.submit(load_batch, batches[index + 1], keep)
-        for fast5_file, (read_id, signal) in zip(batch, loaded):
-            if signal is None:       # unreadable file: skipped, as in the reference (:135-136)
-                continue
-            read_id_to_fast5_file[read_id] = fast5_file
-            read_ids.append(read_id)
-            signals.append(signal)
+        for read_id, file_index in zip(read_ids, kept):
+            read_id_to_fast5_file[read_id] = batch[file_index]
 
         start_calls = start_probs = end_calls = end_probs = None
         if use_start:
@@ -168,9 +163,10 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
 
 
 def load_batch(fast5_batch, keep):
-    """[(read_id, signal) or (None, None)] for a batch of fast5 files, parsed on native host threads
-    (reference classify.py:133-139 calls get_read_id_and_signal per file)."""
-    return read_fast5_batch(fast5_batch, keep=keep)
+    """(read_ids, signals, kept file indices) of the readable files of a batch, parsed on native host
+    threads (reference classify.py:133-139 calls get_read_id_and_signal per file).  `signals` is a
+    load_fast5s.PackedSignals: a list of int16 views plus the packed buffer behind them."""
+    return read_fast5_batch_packed(fast5_batch, keep=keep)
 
 
 def classify_training_data(input_file, start_model, start_input_size, end_model, end_input_size,

@@ -24,7 +24,31 @@ def _native_lib():
         return None
 
 
-def read_fast5_batch(fast5_files, keep=0, threads=None):
+class PackedSignals(list):
+    """A list of per-read int16 signals (views) that also carries the packed buffer they are views
+    of: `samples` (all reads of the batch concatenated), `offsets` (int64 [n_packed + 1]) and `rows`
+    (for every list entry, its row in the packed arrays - unreadable files are rows without a list
+    entry).  `call_batch` hands the packed arrays straight to the C ABI instead of re-packing."""
+
+    def __init__(self, signals, samples, offsets, rows):
+        super().__init__(signals)
+        self.samples, self.offsets, self.rows = samples, offsets, rows
+
+
+def read_fast5_batch_packed(fast5_files, keep, threads=None):
+    """-> (read_ids, PackedSignals) of the readable files, in input order, plus the list of kept file
+    indices: (read_ids, signals, kept)."""
+    loaded = read_fast5_batch(fast5_files, keep=keep, threads=threads, _packed=True)
+    if not isinstance(loaded, tuple):     # pure-Python reader: plain lists
+        kept = [i for i, (_, sig) in enumerate(loaded) if sig is not None]
+        return [loaded[i][0] for i in kept], [loaded[i][1] for i in kept], kept
+    ids, samples, offsets, status = loaded
+    kept = [i for i in range(len(ids)) if status[i] == 0]
+    views = [samples[offsets[i]:offsets[i + 1]] for i in kept]
+    return [ids[i] for i in kept], PackedSignals(views, samples, offsets, np.asarray(kept, dtype=np.int64)), kept
+
+
+def read_fast5_batch(fast5_files, keep=0, threads=None, _packed=False):
     """Parse many single-read fast5 files on native host threads.
     -> list of (read_id, int16 signal) or (None, None) per file, in input order.  If keep > 0 only the
     first and last `keep` samples of longer signals are returned (concatenated) - everything
@@ -58,16 +82,14 @@ def read_fast5_batch(fast5_files, keep=0, threads=None):
         status = np.ctypeslib.as_array(ctypes.cast(ptrs[4], ctypes.POINTER(ctypes.c_int32)), (max(n, 1),))[:n].copy()
     finally:
         lib.db_fast5_batch_free(handle)
-    out = []
-    for i in range(n):
-        if status[i] == 2:
-            sys.exit('Error: Deepbinner does not (yet) support multi-read fast5 files')
-        if status[i] != 0:
-            out.append((None, None))
-            continue
-        rid = ids[i * 64:(i + 1) * 64].split(b'\x00')[0].decode()
-        out.append((rid, samples[offsets[i]:offsets[i + 1]]))
-    return out
+    if (status == 2).any():
+        sys.exit('Error: Deepbinner does not (yet) support multi-read fast5 files')
+    read_ids = [ids[i * 64:(i + 1) * 64].split(b'\x00')[0].decode() if status[i] == 0 else None
+                for i in range(n)]
+    if _packed:
+        return read_ids, samples, offsets, status
+    return [(read_ids[i], samples[offsets[i]:offsets[i + 1]]) if status[i] == 0 else (None, None)
+            for i in range(n)]
 
 
 def get_read_id_and_signal(fast5_file):

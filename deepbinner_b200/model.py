@@ -100,8 +100,17 @@ class B200Model:
     def call_batch(self, signals, side, scan_size, score_diff):
         """signals: list of 1-D integer arrays.  Returns (calls int8 [n] with 0 = 'none',
         probabilities float32 [n, n_classes] after make_sum_to_one)."""
-        samples, offsets = pack_scan_regions(signals, side, int(scan_size), self.input_size)
-        n = len(signals)
+        rows = None
+        if hasattr(signals, 'samples') and hasattr(signals, 'offsets'):
+            # already packed by the native fast5 reader (load_fast5s.PackedSignals): the C ABI takes
+            # whole reads and cuts the scan regions itself; rows of unreadable files are empty reads
+            samples, offsets, rows = signals.samples, signals.offsets, signals.rows
+            if samples.size == 0:
+                samples = np.zeros(1, dtype=np.int16)
+            n = len(offsets) - 1
+        else:
+            samples, offsets = pack_scan_regions(signals, side, int(scan_size), self.input_size)
+            n = len(signals)
         probs = np.empty((n, self.n_classes), dtype=np.float32)
         calls = np.empty(n, dtype=np.int8)
         rc = self._lib.db_call_batch(self._handle, _native.as_ptr(samples), _native.as_ptr(offsets),
@@ -109,6 +118,8 @@ class B200Model:
                                      int(scan_size), float(score_diff), _native.as_ptr(probs),
                                      _native.as_ptr(calls))
         _native.check(rc, 'db_call_batch')
+        if rows is not None and len(rows) != n:
+            return calls[rows], probs[rows]
         return calls, probs
 
     # -- device-resident entry points (used by bench.py for kernel-only timing) --------------------

@@ -58,3 +58,18 @@ def test_batch_reader_truncation_keeps_the_scan_regions(fast5_dir, fixture_reads
     full = lf.read_fast5_batch(files[:-1], keep=0)
     assert all(np.array_equal(s, ref) for (_, s), ref in zip(full, sigs))
     assert lf.read_fast5_batch([]) == []
+
+
+def test_packed_batch_keeps_the_buffer_behind_the_views(fast5_dir, fixture_reads):
+    """read_fast5_batch_packed: readable files only, views into one packed buffer, `rows` = their
+    positions in the packed arrays (what B200Model.call_batch hands to the C ABI unchanged)."""
+    ids, sigs, names = fixture_reads
+    files = [str(fast5_dir / 'nope.fast5')] + [str(fast5_dir / 'fast5_files' / n) for n in names]
+    keep = 6144 + 512
+    read_ids, signals, kept = lf.read_fast5_batch_packed(files, keep=keep)
+    assert read_ids == list(ids) and kept == list(range(1, 8))
+    assert isinstance(signals, lf.PackedSignals) and signals.rows.tolist() == kept
+    assert len(signals.offsets) == len(files) + 1 and signals.offsets[1] == 0   # unreadable: empty row
+    for s, row, ref in zip(signals, signals.rows, sigs):
+        assert np.array_equal(s, signals.samples[signals.offsets[row]:signals.offsets[row + 1]])
+        assert np.array_equal(s[:keep], ref[:keep]) and np.array_equal(s[-keep:], ref[-keep:])

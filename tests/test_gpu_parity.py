@@ -175,8 +175,11 @@ def test_classify_fast5_files_end_to_end(models, fixture_reads, reference_golden
     from deepbinner_b200 import classify as cls
     ids, sigs, names = fixture_reads
     table = {n: (i, s) for n, i, s in zip(names, ids, sigs)}
-    monkeypatch.setattr(cls, 'load_batch',
-                        lambda batch, keep: [table.get(str(f).split('/')[-1], (None, None)) for f in batch])
+    def load_batch(batch, keep):   # same contract as classify.load_batch: readable files only
+        loaded = [table.get(str(f).split('/')[-1], (None, None)) for f in batch]
+        kept = [i for i, (_, sig) in enumerate(loaded) if sig is not None]
+        return [loaded[i][0] for i in kept], [loaded[i][1] for i in kept], kept
+    monkeypatch.setattr(cls, 'load_batch', load_batch)
     monkeypatch.setattr(cls, 'determine_single_or_multi_fast5s', lambda files: 'single')
     start, end = models['EXP-NBD103_read_starts'], models['EXP-NBD103_read_ends']
     files = ['/x/' + n for n in names] + ['/x/unreadable.fast5']
@@ -277,6 +280,21 @@ def test_cli_classify_on_real_fast5_files(fast5_dir, reference_goldens, capsys):
     with pytest.raises(SystemExit) as e:     # multi-read input is rejected like the reference does
         cli.main(['classify', '--native', str(fast5_dir / 'multi_read_fast5_files')])
     assert 'one-read-per-file' in str(e.value)
+
+
+def test_packed_signals_take_the_same_fused_path(models, fast5_dir, fixture_reads):
+    """call_batch on the packed output of the native fast5 reader (no Python re-packing, unreadable
+    files as empty rows) == call_batch on the plain list of signals."""
+    from deepbinner_b200 import classify as cls, load_fast5s as lf
+    ids, sigs, names = fixture_reads
+    files = [str(fast5_dir / 'nope.fast5')] + [str(fast5_dir / 'fast5_files' / n) for n in names]
+    read_ids, packed, kept = lf.read_fast5_batch_packed(files, keep=6144 + 512)
+    assert read_ids == list(ids)
+    for side, name in (('start', 'EXP-NBD103_read_starts'), ('end', 'EXP-NBD103_read_ends')):
+        a = cls.call_batch(1024, 13, read_ids, packed, models[name], make_args(), side)
+        b = cls.call_batch(1024, 13, read_ids, list(sigs), models[name], make_args(), side)
+        assert a[0] == b[0] and len(a[0]) == 7
+        assert np.array_equal(np.array(a[1]), np.array(b[1]))
 
 
 def test_realtime_on_real_fast5_files(fast5_dir, tmp_path, capsys):
