@@ -36,10 +36,10 @@ def main():
     for j in range(nj):
         for w in range(2):
             a, b, c, d, e4, e5, e6, e7 = [int(v - t0) if v > 0 else -1 for v in trace[j, w][:8]]
-            x8, x9, x10, x11, x12 = [int(v - t0) if v > 0 else -1 for v in trace[j, w][8:13]]
-            print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d} | {:5d} {:5d} {:5d} {:5d} {:5d} | {:5d} {:5d} {:5d} {:5d} | top {:6d} waited {:6d}'.format(
+            x8, x9, x10, x11, x12, x13 = [int(v - t0) if v > 0 else -1 for v in trace[j, w][8:14]]
+            print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d} | {:5d} {:5d} {:5d} {:5d} {:5d} | {:5d} {:5d} {:5d} {:5d} | top {:6d} waited {:6d} need {:6d}'.format(
                 NAMES[j], w, a, b, c, d, b - a, (d - c) if c >= 0 else -1,
-                e4 - c, e5 - e4, e6 - e5, e7 - e6, d - e7, x8 - a, x9 - x8, x10 - x9, b - x10, x11, x12))
+                e4 - c, e5 - e4, e6 - e5, e7 - e6, d - e7, x8 - a, x9 - x8, x10 - x9, b - x10, x11, x12, x13))
     print('total', int(trace[:nj].max() - t0))
 
 
