@@ -185,6 +185,20 @@ __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+#ifndef DBN_TC_WARP_ARRIVE
+#define DBN_TC_WARP_ARRIVE 1
+#endif
+// Epilogue -> issuer hand-off: every thread has fenced its shared-memory writes towards the async
+// proxy; one lane per warp then arrives for the warp (12 arrivals per phase instead of 384).
+constexpr uint32_t kEpiArrivals = DBN_TC_WARP_ARRIVE ? 12 : 384;
+__device__ __forceinline__ void epi_arrive(uint32_t bar) {
+#if DBN_TC_WARP_ARRIVE
+    __syncwarp();
+    if ((threadIdx.x & 31) == 0) mbar_arrive(bar);
+#else
+    mbar_arrive(bar);
+#endif
+}
 __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes)
                  : "memory");
@@ -913,8 +927,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         mbar_init(bar_wfree[1], 1);
         mbar_init(bar_mma[0], 1);
         mbar_init(bar_mma[1], 1);
-        mbar_init(bar_epi[0], kEpiThreads);
-        mbar_init(bar_epi[1], kEpiThreads);
+        mbar_init(bar_epi[0], kEpiArrivals);
+        mbar_init(bar_epi[1], kEpiArrivals);
         mbar_init(bar_final, 1);
         for (int i = 0; i < 3; ++i) {
             mbar_init(bar_jwfull0 + 8 * i, 1);
@@ -922,7 +936,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
         for (int i = 0; i < 4; ++i) {
             mbar_init(bar_jmma + 8 * i, 1);
-            mbar_init(bar_jepi + 8 * i, kEpiThreads);
+            mbar_init(bar_jepi + 8 * i, kEpiArrivals);
         }
         fence_barrier_init();
     }
@@ -972,7 +986,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             conv1_stage(c1, xv[w][0], xv[w][1], xv[w][2], sbase + (w ? kSmemAct1 : kSmemAct0),
                         smem + (w ? kSmemAct1 : kSmemAct0), tid);
             fence_proxy_async();
-            mbar_arrive(bar_epi[w]);
+            epi_arrive(bar_epi[w]);
             if (trace && blockIdx.x == 0 && tid == 0) trace[31 * 32 + 1 + w] = clock64();
         }
         epi_bar_sync();   // parameter block staged by all epilogue threads is now visible
@@ -992,7 +1006,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 fence_proxy_async();
                 if (tr) tr[7] = clock64();
                 tc_fence_before();
-                mbar_arrive(bar_jepi + 8 * (e & 3));
+                epi_arrive(bar_jepi + 8 * (e & 3));
                 if (tr) tr[3] = clock64();
                 continue;
             }
@@ -1006,7 +1020,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 fence_proxy_async();
                 if (tr) tr[7] = clock64();
                 tc_fence_before();
-                mbar_arrive(bar_epi[w]);
+                epi_arrive(bar_epi[w]);
                 if (tr) tr[3] = clock64();
             }
         }

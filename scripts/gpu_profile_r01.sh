@@ -13,5 +13,6 @@ cut -c1-300 gpurun_out/r01_bench_tcgen05.json gpurun_out/r01_bench_fp32.json gpu
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -s 20 -c 200 --csv --log-file gpurun_out/r01_launches_tcgen05.csv python bench.py --steps 2 --warmup 3 --shard 8192 --no-cpu-baseline > gpurun_out/r01_ncu_launches.log 2>&1
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_tc_forward -s 8 -c 2 -o gpurun_out/r01_prof_tcgen05 python bench.py --steps 1 --warmup 3 --shard 2048 --no-cpu-baseline > gpurun_out/r01_ncu_full.log 2>&1
 timeout 300 python tools/tc_timeline.py 296 > gpurun_out/r01_tc_timeline.txt 2>&1
+timeout 300 python tools/bench_classify_dir.py 3000 2>&1 | tail -3 > gpurun_out/r01_classify_dir.txt
 timeout 120 ./tools/tc_microbench > gpurun_out/r01_tc_microbench.txt 2>&1
 ls -la gpurun_out
