@@ -381,6 +381,9 @@ def main():
             'gpu_launches': int(launches),
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': achieved / peak, 'traffic': traffic,
+                         # split-bf16: three tensor-core MMAs per algorithmic one
+                         'issued': achieved * (3 if model.engine == 'tcgen05' else 1),
+                         'issued_frac': achieved * (3 if model.engine == 'tcgen05' else 1) / peak,
                          'note': 'algorithmic 33,629,952 FLOP/window x {} windows per launch / '
                                  'average launch duration (timed region / launches; launches on {} '
                                  'streams overlap); peak = {}'.format(BATCH, N_STREAMS, peak_src)},
