@@ -200,7 +200,7 @@ def main():
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--engine', default=None, choices=[None, 'fp32', 'tcgen05'])
+    ap.add_argument('--engine', default=None, choices=[None, 'fp32', 'tcgen05', 'tcgen05-split'])
     ap.add_argument('--shard', type=int, default=SHARD)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -352,7 +352,9 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        avg_launch_ms = ms / max(launches, 1)
+        # one network pass over a batch = one kernel (two for the split engine: front + tail)
+        kernels_per_batch = 2 if model.engine == 'tcgen05-split' else 1
+        avg_launch_ms = ms / max(launches // kernels_per_batch, 1)
         achieved = FLOP_PER_WINDOW * BATCH / (avg_launch_ms * 1e-3) / 1e12
         traffic = None
         tfile = ROOT / 'profiles' / 'traffic_r01.json'
@@ -382,8 +384,8 @@ def main():
             'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
                          'frac': achieved / peak, 'traffic': traffic,
                          # split-bf16: three tensor-core MMAs per algorithmic one
-                         'issued': achieved * (3 if model.engine == 'tcgen05' else 1),
-                         'issued_frac': achieved * (3 if model.engine == 'tcgen05' else 1) / peak,
+                         'issued': achieved * (1 if model.engine == 'fp32' else 3),
+                         'issued_frac': achieved * (1 if model.engine == 'fp32' else 3) / peak,
                          'note': 'algorithmic 33,629,952 FLOP/window x {} windows per launch / '
                                  'average launch duration (timed region / launches; launches on {} '
                                  'streams overlap); peak = {}'.format(BATCH, N_STREAMS, peak_src)},

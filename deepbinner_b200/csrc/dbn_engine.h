@@ -15,11 +15,13 @@ int fail(int code, const char* fmt, ...);
 TcEngine* tc_create(const Blob& blob, int sm_count);
 void tc_destroy(TcEngine* e);
 // d_x (float32) or d_xd (float64): [n][1024] normalised windows -> d_probs [n][n_classes]
+// split = true: front kernel + four-window tail kernel (experimental DBN_ENGINE_TCGEN05_SPLIT)
 int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, float* d_probs,
-               cudaStream_t st);
+               cudaStream_t st, bool split = false);
+bool tc_split_available(const TcEngine* e);
 // fused call_batch front end: window w = step*n_reads + read -> d_step_probs [steps][n_reads][nc]
 int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offsets, int n_reads,
-                    int side, int steps, float* d_step_probs, cudaStream_t st);
+                    int side, int steps, float* d_step_probs, cudaStream_t st, bool split = false);
 
 int tc_num_jobs(const TcEngine* e);
 int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st);

@@ -190,11 +190,12 @@ static int launch_predict(db_model* m, const void* d_x, bool is_f64, int64_t n, 
                           cudaStream_t st) {
     if (n <= 0) return 0;
     if (n > 0x7fffffff) return fail(DBN_EINVAL, "too many windows in one launch");
-    if (m->engine == DBN_ENGINE_TCGEN05) {
+    if (m->engine == DBN_ENGINE_TCGEN05 || m->engine == DBN_ENGINE_TCGEN05_SPLIT) {
         int rc = tc_predict(m->tc, is_f64 ? nullptr : static_cast<const float*>(d_x),
-                            is_f64 ? static_cast<const double*>(d_x) : nullptr, n, d_probs, st);
+                            is_f64 ? static_cast<const double*>(d_x) : nullptr, n, d_probs, st,
+                            m->engine == DBN_ENGINE_TCGEN05_SPLIT);
         if (rc) return rc;
-        m->launches += 1;
+        m->launches += m->engine == DBN_ENGINE_TCGEN05_SPLIT ? 2 : 1;
         return 0;
     }
     const dim3 grid(static_cast<unsigned>(n));
@@ -215,8 +216,9 @@ static int launch_call_batch(db_model* m, const int16_t* d_samples, const int64_
     if (n_reads <= 0) return 0;
     const int64_t windows = static_cast<int64_t>(n_reads) * steps;
     if (windows > 0x7fffffff) return fail(DBN_EINVAL, "too many windows in one launch");
-    if (m->engine == DBN_ENGINE_TCGEN05) {
-        int rc = tc_call_windows(m->tc, d_samples, d_offsets, n_reads, side, steps, d_step, st);
+    if (m->engine == DBN_ENGINE_TCGEN05 || m->engine == DBN_ENGINE_TCGEN05_SPLIT) {
+        int rc = tc_call_windows(m->tc, d_samples, d_offsets, n_reads, side, steps, d_step, st,
+                                 m->engine == DBN_ENGINE_TCGEN05_SPLIT);
         if (rc) return rc;
     } else {
         k_fp32_call_windows<<<static_cast<unsigned>(windows), kThreads, kFp32SmemBytes, st>>>(
@@ -352,6 +354,11 @@ int db_set_engine(db_model* m, int engine) {
     }
     if (engine == DBN_ENGINE_TCGEN05) {
         if (!m->tc_available) return fail(DBN_EINVAL, "tcgen05 engine is not available in this build");
+        m->engine = engine;
+        return DBN_OK;
+    }
+    if (engine == DBN_ENGINE_TCGEN05_SPLIT) {
+        if (!tc_split_available(m->tc)) return fail(DBN_EINVAL, "split tcgen05 engine is not available");
         m->engine = engine;
         return DBN_OK;
     }

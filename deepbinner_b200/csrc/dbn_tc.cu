@@ -171,6 +171,7 @@ struct TcParams {
     int dbg_job;              // >= 0: stop after this job's epilogue and dump ACT of both windows
     unsigned char* dbg_out;
     long long* trace;         // optional timeline of CTA 0: [job][window][4] clock64 stamps
+    unsigned char* mid;       // front kernel of the split engine: [n_windows][49536] BatchNorm_2 outputs
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -854,7 +855,9 @@ static_assert(offsetof(TcJob, lp) == 16 && offsetof(TcJob, tap16) == 24 && offse
 // ---------------------------------------------------------------------------------------------
 // kDiag: diagnostics build of the kernel (timeline stamps, early stop + ACT dump); the production
 // instantiations carry none of that code.
-template <bool kCallMode, bool kDiag>
+// kFront: front kernel of the split engine - stops after conv1d_4 and copies each window's pooled
+// BatchNorm_2 tensor (the first 49 536 B of its region) to P.mid for the tail kernel (dbn_tc_tail.cuh).
+template <bool kCallMode, bool kDiag, bool kFront = false>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_tc_forward(TcParams P, const float* __restrict__ x, const double* __restrict__ xd,
                  const int16_t* __restrict__ samples, const int64_t* __restrict__ offsets, int n_reads,
@@ -938,7 +941,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    const int njobs = (dbg_job >= 0 && dbg_job < P.njobs) ? dbg_job + 1 : P.njobs;
+    const int njobs = kFront ? 3 : ((dbg_job >= 0 && dbg_job < P.njobs) ? dbg_job + 1 : P.njobs);
 
     if (is_epi) {
         // ================= epilogue / CUDA-core warps =================
@@ -1008,6 +1011,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 run_epilogue(P, J, act, sbase + kSmemAct0, w, prm, tmem_base + w * kTmemWindowCols, tid,
                              bar_mma[w], mma_phase[w], p0, p1, tr);
                 mma_phase[w] ^= 1;
+                if (kFront && j == 2) {   // hand the window over to the tail kernel
+                    epi_bar_sync();       // every epilogue thread has written its part of the tensor
+                    if (valid[w]) {
+                        const uint4* src = reinterpret_cast<const uint4*>(smem + (w ? kSmemAct1 : kSmemAct0));
+                        uint4* dst = reinterpret_cast<uint4*>(P.mid + static_cast<size_t>(win[w]) * 49536);
+                        for (int i = tid; i < 49536 / 16; i += kEpiThreads) dst[i] = src[i];
+                    }
+                }
                 if (tr) tr[6] = clock64();
                 fence_proxy_async();
                 if (tr) tr[7] = clock64();
@@ -1167,6 +1178,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
+}  // namespace dbn
+
+#include "dbn_tc_tail.cuh"
+
+namespace dbn {
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1177,6 +1194,19 @@ struct TcEngine {
     TcParams params{};
     int njobs = 0;
     std::vector<TcJob> jobs;   // uploaded to constant memory (identical for every model of this topology)
+    // split engine (front kernel + four-window tail kernel, dbn_tc_tail.cuh)
+    bool tail_ok = false;
+    unsigned char* d_tw = nullptr;
+    TcJob* d_tjobs = nullptr;
+    float* d_tprm = nullptr;
+    TailParams tparams{};
+    std::vector<TcJob> tjobs;
+    struct MidBuffer {          // staging of the BatchNorm_2 tensors, one per stream in use
+        cudaStream_t stream;
+        unsigned char* ptr;
+        size_t bytes;
+    };
+    std::vector<MidBuffer> mids;
 };
 
 static uint16_t bf16_rn(float f) {
@@ -1310,7 +1340,7 @@ struct JobBuilder {
     // Mark the jobs from index `j0` on as the joint phase: accumulator slots rotate over three 64-column
     // slots (K-slices of one conv share a slot) and `need` is derived from the data flow: `producer[j]`
     // = job whose epilogue writes this job's input (-1: available before the joint phase).
-    void finish_joint(int j0, const std::vector<int>& producer) {
+    void finish_joint(int j0, const std::vector<int>& producer, int slot_cols = kTmemTileCols) {
         std::vector<int> eseq_of(jobs.size(), -1), slot_of(jobs.size(), 0);
         int e = 0, slot = -1;
         std::vector<int> last_user(3, -1);   // job with the epilogue that last drained the slot
@@ -1318,7 +1348,7 @@ struct JobBuilder {
             TcJob& J = jobs[j];
             if (J.first) slot = (slot + 1) % 3;
             slot_of[j] = slot;
-            J.tcol = slot * kTmemTileCols;
+            J.tcol = slot * slot_cols;
             int need = 0;
             const int prod = producer[j - j0];
             if (prod >= 0) need = std::max(need, eseq_of[prod] + 1);
@@ -1415,6 +1445,64 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     return true;
 }
 
+// Job table of the tail kernel (conv1d_5 .. conv1d_20, four windows per CTA; layout in dbn_tc_tail.cuh).
+static bool build_tail_jobs(const Blob& blob, JobBuilder* B, TailParams* P) {
+    if (blob.n_classes > 16) return false;
+    B->add(5, 256, 0, 258, 24768, EPI_N16, 0, 0, 0);              // BN2 [6][258][8] -> [2][258][8], lo +8256
+    B->add(6, 256, 0, 258, 8256, EPI_N48, 0, 0, 0);               // -> [6][258][8]
+    B->add(7, 256, 0, 258, 24768, EPI_N48_POOL_BN, 3, 0, 0);      // -> [6][130][8], lo +12480
+    B->add(8, 128, 0, 130, 12480, EPI_N48, 0, 0, 0);
+    B->add(9, 128, 0, 130, 12480, EPI_N48_POOL_BN, 4, 0, 0);      // X [6][66][8] @0, lo +6336
+    const int j0 = static_cast<int>(B->jobs.size());
+    std::vector<int> producer;
+    auto joint = [&](TcJob& J, int kind, int m, int prod) {
+        J.joint = kind;
+        J.idesc = m;
+        J.ntiles = 1;
+        producer.push_back(prod);
+    };
+    // inception block: X / T15 @0, T1214 @12672; conv1d_10 (folded pool) before conv1d_15 so that T15
+    // may overwrite X; parity arrays of the stacked concat tensor @21120 of regions 0..3
+    joint(B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 12672, 0, 14), JOINT_PAIR, 64, -1);             // j0
+    joint(B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6), JOINT_PAIR, 64, -1);                  // j0+1
+    B->jobs.back().zero_y = 1;
+    joint(B->add(10, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 0, 0, true), JOINT_PAIR, 64, -1);         // j0+2
+    joint(B->add(15, 64, 12672 + 2 * 66 * 16, 66, 4224, EPI_N48, 0, 0, 0), JOINT_PAIR, 64, j0);   // j0+3: T15 over X
+    joint(B->add(13, 64, 12672, 66, 4224, EPI_PARITY, 5, 0, 12), JOINT_PAIR, 64, j0);             // j0+4
+    joint(B->add(16, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 18), JOINT_PAIR, 64, j0 + 3);             // j0+5
+    // conv1d_17 on the four stacked windows (72 rows, M=128): taps Ye[i], Yo[i], Ye[i+1]
+    for (int s = 0; s < 4; ++s) {
+        TcJob J{};
+        J.n = 48; J.idesc = 128; J.ntiles = 1; J.L = kTYRows - 2; J.lp = kTYRows; J.ntaps = 3;
+        J.tap16[0] = kTYOff; J.tap16[1] = kTYOff + 2 * kTReg; J.tap16[2] = kTYOff + 16;
+        J.lo16 = kTReg; J.ncb = 3; J.cb0 = 3 * s;
+        J.first = (s == 0); J.last = (s == 3);
+        J.joint = JOINT_STACK;
+        J.kind = EPI_N48_BN;
+        J.out_L = kTYRows - 2; J.out_off = 0; J.out_lp = kTYRows; J.out_ncg = 6; J.out_lo_delta = 6 * kTYRows * 16;
+        J.out_cg_base = 0;
+        B->pack_weights(17, 48, 3 * s, 3, &J);
+        if (J.last) B->pack_params(17, 48, 6, 0, &J);
+        B->jobs.push_back(J);
+        producer.push_back(s == 0 ? j0 + 5 : -1);
+    }
+    const int lo17 = 6 * kTYRows * 16;   // 6912
+    joint(B->add(18, kTYRows - 2, 0, kTYRows, lo17, EPI_N48, 0, 0, 0), JOINT_STACK, 128, j0 + 9);
+    joint(B->add(19, kTYRows - 2, 0, kTYRows, lo17, EPI_N48_POOL_BN, 7, 0, 0), JOINT_STACK, 128, j0 + 10);   // -> [6][37][8]
+    joint(B->add(20, (kTYRows - 2) / 2, 0, (kTYRows - 2) / 2 + 2, 6 * ((kTYRows - 2) / 2 + 2) * 16, EPI_HEAD, 0, 0, 0),
+          JOINT_STACK, 128, j0 + 11);
+    B->finish_joint(j0, producer, 2 * kTmemTileCols);
+    B->finalize_jobs();
+    if (B->prm.size() > static_cast<size_t>(kTPrmFloats) || B->jobs.size() > static_cast<size_t>(kMaxJobs)) return false;
+    for (const TcJob& J : B->jobs)
+        if (J.w_part[0] > kWPart0 || J.w_part[1] > kWPart1) return false;
+    while (B->prm.size() % 4) B->prm.push_back(0.f);
+    P->prm_floats = static_cast<int>(B->prm.size());
+    P->n_classes = blob.n_classes;
+    P->njobs = static_cast<int>(B->jobs.size());
+    return true;
+}
+
 TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
     if (getenv("DBN_DISABLE_TC")) return nullptr;
     JobBuilder B(blob);
@@ -1444,7 +1532,34 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
     P.dbg_job = -1;
     P.dbg_out = nullptr;
     P.trace = nullptr;
+    P.mid = nullptr;
     e->params = P;
+    // split engine (optional): tail job table, weights and parameters
+    JobBuilder T(blob);
+    TailParams TP{};
+    if (build_tail_jobs(blob, &T, &TP)) {
+        e->tjobs = T.jobs;
+        const bool tok =
+            cudaMalloc(&e->d_tw, T.w.size()) == cudaSuccess &&
+            cudaMalloc(&e->d_tprm, T.prm.size() * sizeof(float)) == cudaSuccess &&
+            cudaMalloc(&e->d_tjobs, T.jobs.size() * sizeof(TcJob)) == cudaSuccess &&
+            cudaMemcpy(e->d_tw, T.w.data(), T.w.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(e->d_tprm, T.prm.data(), T.prm.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaMemcpy(e->d_tjobs, T.jobs.data(), T.jobs.size() * sizeof(TcJob), cudaMemcpyHostToDevice) == cudaSuccess &&
+            cudaFuncSetAttribute(k_tc_forward<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+            cudaFuncSetAttribute(k_tc_forward<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+            cudaFuncSetAttribute(k_tc_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes) == cudaSuccess;
+        if (tok) {
+            TP.jobs = e->d_tjobs;
+            TP.w = e->d_tw;
+            TP.prm = e->d_tprm;
+            TP.mid = nullptr;
+            e->tparams = TP;
+            e->tail_ok = true;
+        } else {
+            cudaGetLastError();
+        }
+    }
     return e;
 }
 
@@ -1453,6 +1568,10 @@ void tc_destroy(TcEngine* e) {
     cudaFree(e->d_w);
     cudaFree(e->d_jobs);
     cudaFree(e->d_prm);
+    cudaFree(e->d_tw);
+    cudaFree(e->d_tjobs);
+    cudaFree(e->d_tprm);
+    for (auto& m : e->mids) cudaFree(m.ptr);
     delete e;
 }
 
@@ -1472,8 +1591,71 @@ static int sync_jobs(TcEngine* e) {
     return 0;
 }
 
+static std::vector<TcJob> g_uploaded_tjobs;
+static int sync_tail_jobs(TcEngine* e) {
+    const size_t bytes = e->tjobs.size() * sizeof(TcJob);
+    if (g_uploaded_tjobs.size() == e->tjobs.size() &&
+        std::memcmp(g_uploaded_tjobs.data(), e->tjobs.data(), bytes) == 0)
+        return 0;
+    if (cudaDeviceSynchronize() != cudaSuccess ||
+        cudaMemcpyToSymbol(c_tjobs, e->tjobs.data(), bytes) != cudaSuccess)
+        return fail(DBN_ECUDA, "uploading the tail job table failed");
+    g_uploaded_tjobs = e->tjobs;
+    return 0;
+}
+
+// Staging buffer of the split engine for `n` windows on stream `st` (one buffer per stream in use, so
+// that launches on different streams never share it; grown on demand).
+static unsigned char* mid_buffer(TcEngine* e, int64_t n, cudaStream_t st) {
+    const size_t need = static_cast<size_t>(n) * kTReg;
+    for (auto& m : e->mids) {
+        if (m.stream != st) continue;
+        if (m.bytes < need) {
+            cudaStreamSynchronize(st);
+            cudaFree(m.ptr);
+            m.ptr = nullptr;
+            m.bytes = 0;
+            if (cudaMalloc(&m.ptr, need) != cudaSuccess) return nullptr;
+            m.bytes = need;
+        }
+        return m.ptr;
+    }
+    TcEngine::MidBuffer m{st, nullptr, 0};
+    if (cudaMalloc(&m.ptr, need) != cudaSuccess) return nullptr;
+    m.bytes = need;
+    e->mids.push_back(m);
+    return m.ptr;
+}
+
+bool tc_split_available(const TcEngine* e) { return e && e->tail_ok; }
+
+// front kernel (kFront) + tail kernel on the same stream
+template <bool kCall>
+static int launch_split(TcEngine* e, const float* d_x, const double* d_xd, const int16_t* d_samples,
+                        const int64_t* d_offsets, int n_reads, int side, int n, float* d_probs, cudaStream_t st) {
+    if (!e->tail_ok) return fail(DBN_EINVAL, "split tcgen05 engine is not available");
+    if (int rc = sync_jobs(e)) return rc;
+    if (int rc = sync_tail_jobs(e)) return rc;
+    unsigned char* mid = mid_buffer(e, n, st);
+    if (!mid) {
+        cudaGetLastError();
+        return fail(DBN_ENOMEM, "out of device memory for the split engine's staging buffer");
+    }
+    TcParams P = e->params;
+    P.mid = mid;
+    TailParams T = e->tparams;
+    T.mid = mid;
+    k_tc_forward<kCall, false, true><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(P, d_x, d_xd, d_samples, d_offsets,
+                                                                             n_reads, side, n, d_probs);
+    k_tc_tail<<<(n + kTW - 1) / kTW, kTcThreads, kTSmemBytes, st>>>(T, n, d_probs);
+    cudaError_t err = cudaGetLastError();
+    if (err != cudaSuccess) return fail(DBN_ECUDA, "split tcgen05 launch failed: %s", cudaGetErrorString(err));
+    return 0;
+}
+
 int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, float* d_probs,
-               cudaStream_t st) {
+               cudaStream_t st, bool split) {
+    if (split) return launch_split<false>(e, d_x, d_xd, nullptr, nullptr, 0, 0, static_cast<int>(n), d_probs, st);
     if (int rc = sync_jobs(e)) return rc;
     const int grid = static_cast<int>((n + 1) / 2);
     k_tc_forward<false, false><<<grid, kTcThreads, kTcSmemBytes, st>>>(e->params, d_x, d_xd, nullptr, nullptr,
@@ -1484,9 +1666,10 @@ int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, flo
 }
 
 int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offsets, int n_reads,
-                    int side, int steps, float* d_step_probs, cudaStream_t st) {
-    if (int rc = sync_jobs(e)) return rc;
+                    int side, int steps, float* d_step_probs, cudaStream_t st, bool split) {
     const int n = n_reads * steps;
+    if (split) return launch_split<true>(e, nullptr, nullptr, d_samples, d_offsets, n_reads, side, n, d_step_probs, st);
+    if (int rc = sync_jobs(e)) return rc;
     k_tc_forward<true, false><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(e->params, nullptr, nullptr, d_samples,
                                                                       d_offsets, n_reads, side, n,
                                                                       d_step_probs);

@@ -46,6 +46,8 @@ extern "C" {
 /* Engines (db_set_engine).  Both are hand-written sm_100a CUDA; results agree to ~1e-4. */
 #define DBN_ENGINE_FP32 0    /* CUDA-core fp32 fused per-window kernel (parity anchor) */
 #define DBN_ENGINE_TCGEN05 1 /* tcgen05/TMEM split-bf16 tensor-core kernel */
+#define DBN_ENGINE_TCGEN05_SPLIT 2 /* experimental: same arithmetic as two kernels (conv1d_1-4 with two
+                                    * windows per CTA, conv1d_5-20 with four); not selected by default */
 
 typedef struct db_model db_model;
 

@@ -2,6 +2,7 @@
 and the committed goldens.  Tolerance from BASELINE.json north_star: identical calls, probabilities
 within 1e-3 max-abs.  Run with `pytest -m gpu` on a B200."""
 import io
+import os
 import types
 
 import numpy as np
@@ -71,6 +72,35 @@ def test_predict_parity_on_real_windows(models, oracle_weights, fixture_reads, m
             assert err.max() <= TOL
             assert np.array_equal(got.argmax(axis=1), ref.argmax(axis=1))
             assert np.allclose(got.sum(axis=1), 1.0, atol=1e-5)
+
+
+@pytest.mark.skipif(not os.environ.get('DBN_TEST_SPLIT'), reason='experimental split engine: set DBN_TEST_SPLIT=1')
+def test_split_engine_parity(models, oracle_weights, fixture_reads, multi_reads):
+    """Experimental DBN_ENGINE_TCGEN05_SPLIT (front kernel + four-window tail kernel): same bar as the
+    default engine on the real windows, predict and fused call_batch, odd window counts included."""
+    from deepbinner_b200 import classify as cls
+    ids, sigs, _ = fixture_reads
+    _, msigs = multi_reads
+    x = np.concatenate([orc.make_windows(sigs, 1024, s, side) for side in ('start', 'end')
+                        for s in range(12)] + [sliding_windows(sigs + msigs, 333, seed=5)])
+    for name, model in models.items():
+        try:
+            model.set_engine('tcgen05-split')
+        except Exception as e:  # noqa: BLE001
+            pytest.skip('split engine unavailable: {}'.format(e))
+        ref = orc.forward(oracle_weights[name], x.astype(np.float32))
+        for n in (len(x), 1, 2, 3, 5):
+            got = model.predict(x[:n, :, None], batch_size=256)
+            err = np.abs(got - ref[:n]).max(axis=1)
+            print('{} [split] n={}: max {:.2e}'.format(name, n, err.max()))
+            assert err.max() <= TOL
+            assert np.array_equal(got.argmax(axis=1), ref[:n].argmax(axis=1))
+        side = 'end' if name.endswith('ends') else 'start'
+        calls, probs = cls.call_batch(1024, 13, ids, sigs, model, make_args(), side)
+        ocalls, oprobs = orc.call_batch(oracle_weights[name], sigs, side, 6144, 0.5)
+        assert calls == ocalls
+        assert np.abs(np.array(probs) - np.array(oprobs, dtype=float)).max() <= TOL
+        model.set_engine('tcgen05')
 
 
 def test_predict_accepts_f32_f64_and_returns_fresh_arrays(models, fixture_reads):
