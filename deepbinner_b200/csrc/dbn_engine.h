@@ -24,7 +24,9 @@ int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offs
                     int side, int steps, float* d_step_probs, cudaStream_t st, bool split = false);
 
 int tc_num_jobs(const TcEngine* e);
-int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st);
+// tail = true: timeline of the split engine's tail kernel ([job][4 windows][8] stamps)
+int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st,
+             bool tail = false);
 // Debug: run windows d_x[0..1] through jobs 0..job and dump both activation regions.
 int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, cudaStream_t st);
 

@@ -560,7 +560,8 @@ int db_tc_trace(db_model* m, const float* d_x, int n, float* d_probs, int64_t* t
     if (rc) return rc;
     cudaStream_t st = m->streams[0];
     DBN_CUDA(cudaMemsetAsync(m->d_step, 0, bytes, st));
-    rc = tc_trace(m->tc, d_x, n, d_probs, reinterpret_cast<long long*>(m->d_step), st);
+    rc = tc_trace(m->tc, d_x, n, d_probs, reinterpret_cast<long long*>(m->d_step), st,
+                  m->engine == DBN_ENGINE_TCGEN05_SPLIT);
     if (rc) return rc;
     DBN_CUDA(cudaMemcpyAsync(trace, m->d_step, bytes, cudaMemcpyDeviceToHost, st));
     DBN_CUDA(cudaStreamSynchronize(st));

@@ -1548,12 +1548,14 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
             cudaMemcpy(e->d_tjobs, T.jobs.data(), T.jobs.size() * sizeof(TcJob), cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaFuncSetAttribute(k_tc_forward<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
             cudaFuncSetAttribute(k_tc_forward<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
-            cudaFuncSetAttribute(k_tc_tail, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes) == cudaSuccess;
+            cudaFuncSetAttribute(k_tc_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes) == cudaSuccess &&
+            cudaFuncSetAttribute(k_tc_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes) == cudaSuccess;
         if (tok) {
             TP.jobs = e->d_tjobs;
             TP.w = e->d_tw;
             TP.prm = e->d_tprm;
             TP.mid = nullptr;
+            TP.trace = nullptr;
             e->tparams = TP;
             e->tail_ok = true;
         } else {
@@ -1632,7 +1634,8 @@ bool tc_split_available(const TcEngine* e) { return e && e->tail_ok; }
 // front kernel (kFront) + tail kernel on the same stream
 template <bool kCall>
 static int launch_split(TcEngine* e, const float* d_x, const double* d_xd, const int16_t* d_samples,
-                        const int64_t* d_offsets, int n_reads, int side, int n, float* d_probs, cudaStream_t st) {
+                        const int64_t* d_offsets, int n_reads, int side, int n, float* d_probs, cudaStream_t st,
+                        long long* d_trace = nullptr) {
     if (!e->tail_ok) return fail(DBN_EINVAL, "split tcgen05 engine is not available");
     if (int rc = sync_jobs(e)) return rc;
     if (int rc = sync_tail_jobs(e)) return rc;
@@ -1647,7 +1650,9 @@ static int launch_split(TcEngine* e, const float* d_x, const double* d_xd, const
     T.mid = mid;
     k_tc_forward<kCall, false, true><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(P, d_x, d_xd, d_samples, d_offsets,
                                                                              n_reads, side, n, d_probs);
-    k_tc_tail<<<(n + kTW - 1) / kTW, kTcThreads, kTSmemBytes, st>>>(T, n, d_probs);
+    T.trace = d_trace;
+    if (d_trace) k_tc_tail<true><<<(n + kTW - 1) / kTW, kTcThreads, kTSmemBytes, st>>>(T, n, d_probs);
+    else k_tc_tail<false><<<(n + kTW - 1) / kTW, kTcThreads, kTSmemBytes, st>>>(T, n, d_probs);
     cudaError_t err = cudaGetLastError();
     if (err != cudaSuccess) return fail(DBN_ECUDA, "split tcgen05 launch failed: %s", cudaGetErrorString(err));
     return 0;
@@ -1682,7 +1687,8 @@ int tc_num_jobs(const TcEngine* e) { return e ? e->njobs : 0; }
 
 // Diagnostics: run `n` windows with CTA 0 recording clock64 stamps per (job, window):
 // [0] MMA issue start, [1] MMA issue end, [2] epilogue start (accumulators ready), [3] epilogue end.
-int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st) {
+int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st, bool tail) {
+    if (tail) return launch_split<false>(e, d_x, nullptr, nullptr, nullptr, 0, 0, n, d_probs, st, d_trace);
     if (int rc = sync_jobs(e)) return rc;
     TcParams P = e->params;
     P.trace = d_trace;

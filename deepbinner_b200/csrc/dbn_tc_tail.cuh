@@ -47,6 +47,7 @@ struct TailParams {
     int prm_floats;
     int n_classes;
     const unsigned char* mid;   // [n_windows][kTReg]: BatchNorm_2 output of the front kernel
+    long long* trace;           // diagnostics instantiation: [job][window][8] clock64 stamps of CTA 0
 };
 
 enum TailMode { T_SINGLE = 0, T_PAIR = 1, T_STACK = 2 };
@@ -268,6 +269,9 @@ __device__ __forceinline__ void tail_run_epilogue(const TailParams& P, const TcJ
     }
 }
 
+// kDiag: timeline stamps of CTA 0 ([0] MMA issue start, [1] issue end, [2] epilogue pass start (before the
+// wait for the accumulators), [3] epilogue pass end; slot [31][0][0..1] = kernel start / inputs landed).
+template <bool kDiag>
 __global__ void __launch_bounds__(kTcThreads, 1)
     k_tc_tail(TailParams P, int n_windows, float* __restrict__ probs) {
     extern __shared__ __align__(1024) unsigned char smem[];
@@ -314,13 +318,16 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
     const int njobs = P.njobs;
+    long long* const trace = (kDiag && blockIdx.x == 0) ? P.trace : nullptr;
 
     if (is_epi) {
         // ================= epilogue warps =================
         const int tid = static_cast<int>(threadIdx.x) - kEpiWarp0 * 32;
+        if (trace && tid == 0) trace[(31 * kTW) * 8 + 0] = clock64();
         for (int i = tid; i < P.prm_floats / 4; i += kEpiThreads)
             reinterpret_cast<float4*>(smem + kTSmemPrm)[i] = __ldg(reinterpret_cast<const float4*>(P.prm) + i);
         mbar_wait(bar_in, 0);   // inputs landed (async proxy -> consumed by the async proxy: no fence needed)
+        if (trace && tid == 0) trace[(31 * kTW) * 8 + 1] = clock64();
 #pragma unroll
         for (int w = 0; w < kTW; ++w) epi_arrive(bar_epi + 8 * w);
         epi_bar_sync();         // parameter block visible to all epilogue threads
@@ -336,11 +343,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             for (int w = 0; w < passes; ++w) {
                 const uint32_t bar_in_mma = joint ? bar_jmma + 8 * (e & 3) : bar_mma + 8 * w;
                 const uint32_t bar_out = joint ? bar_jepi + 8 * (e & 3) : bar_epi + 8 * w;
+                if (trace && tid == 0) trace[(j * kTW + w) * 8 + 2] = clock64();
                 tail_run_epilogue(P, J, sbase, w, prm, tmem_base + (joint ? J.tcol : w * kTWinCols), tid, bar_in_mma,
                                   joint ? (e >> 2) & 1 : mma_phase, probs, n_windows);
                 fence_proxy_async();
                 tc_fence_before();
                 epi_arrive(bar_out);
+                if (trace && tid == 0) trace[(j * kTW + w) * 8 + 3] = clock64();
             }
             if (joint) continue;
             mma_phase ^= 1;
@@ -370,6 +379,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     for (const int need = J.need; jepi_seen < need; ++jepi_seen)
                         mbar_wait(bar_jepi + 8 * (jepi_seen & 3), (jepi_seen >> 2) & 1);
                     tc_fence_after();
+                    if (trace) trace[(j * kTW) * 8 + 0] = clock64();
                     const int nw = J.joint == JOINT_PAIR ? kTW : 1;
 #pragma unroll 1
                     for (int w = 0; w < nw; ++w) {   // window w: pair tile w / 2, lane half w % 2
@@ -387,6 +397,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     }
                     if (last) tc_commit(bar_jmma + 8 * (J.eseq & 3), leader);
                     tc_commit(bar_wfree[1], leader);
+                    if (trace) trace[(j * kTW) * 8 + 1] = clock64();
                     wfull_phase ^= 1;
                     continue;
                 }
@@ -394,6 +405,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int w = 0; w < kTW; ++w) {
                     mbar_wait(bar_epi + 8 * w, epi_phase);   // input written and previous accumulators drained
                     tc_fence_after();
+                    if (trace) trace[(j * kTW + w) * 8 + 0] = clock64();
                     const uint32_t dwin = w * kTWinCols;
                     if (w == 0) mbar_wait(bar_wfull[0], wfull_phase);
                     issue_job_part<0>(J.ntaps, J.ncb, dwin, J.ntiles, act16_0 + w * reg16, tap16, J.cb0, J.lp, J.lo16,
@@ -404,6 +416,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                                       wp16[1], blk16, J.n, J.idesc, false, leader);
                     if (last) tc_commit(bar_mma + 8 * w, leader);
                     if (w == kTW - 1) tc_commit(bar_wfree[1], leader);
+                    if (trace) trace[(j * kTW + w) * 8 + 1] = clock64();
                 }
                 epi_phase ^= 1;
                 wfull_phase ^= 1;

@@ -2,7 +2,6 @@
 and the committed goldens.  Tolerance from BASELINE.json north_star: identical calls, probabilities
 within 1e-3 max-abs.  Run with `pytest -m gpu` on a B200."""
 import io
-import os
 import types
 
 import numpy as np
@@ -74,7 +73,6 @@ def test_predict_parity_on_real_windows(models, oracle_weights, fixture_reads, m
             assert np.allclose(got.sum(axis=1), 1.0, atol=1e-5)
 
 
-@pytest.mark.skipif(not os.environ.get('DBN_TEST_SPLIT'), reason='experimental split engine: set DBN_TEST_SPLIT=1')
 def test_split_engine_parity(models, oracle_weights, fixture_reads, multi_reads):
     """Experimental DBN_ENGINE_TCGEN05_SPLIT (front kernel + four-window tail kernel): same bar as the
     default engine on the real windows, predict and fused call_batch, odd window counts included."""
