@@ -533,6 +533,16 @@ int db_call_batch_device(db_model* m, const int16_t* d_samples, const int64_t* d
 
 int db_tc_num_jobs(const db_model* m) { return (m && m->tc) ? tc_num_jobs(m->tc) : 0; }
 
+int db_tc_job_table(const void* weights_blob, size_t blob_bytes, int which, int32_t* out, int max_jobs) {
+    if (!weights_blob || !out) return fail(DBN_EINVAL, "db_tc_job_table: NULL buffer");
+    Blob blob;
+    const std::string err = parse_blob(weights_blob, blob_bytes, &blob);
+    if (!err.empty()) return fail(DBN_EFORMAT, "%s", err.c_str());
+    const int n = tc_job_table(blob, which, out, max_jobs);
+    if (n < 0) return fail(DBN_EFORMAT, "no tcgen05 job table for this model");
+    return n;
+}
+
 int db_tc_debug_dump(db_model* m, const float* x, int job, unsigned char* out) {
     if (!m || !m->tc) return fail(DBN_EINVAL, "tcgen05 engine not available");
     if (!x || !out) return fail(DBN_EINVAL, "NULL buffer");

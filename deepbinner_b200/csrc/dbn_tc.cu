@@ -1685,6 +1685,24 @@ int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offs
 
 int tc_num_jobs(const TcEngine* e) { return e ? e->njobs : 0; }
 
+// Host only (no CUDA call): the MMA job table the engine would use for this model, 32 ints per job in
+// the order of struct TcJob.  which = 0: fused kernel, 1: tail kernel of the split engine.
+int tc_job_table(const Blob& blob, int which, int32_t* out, int max_jobs) {
+    static_assert(sizeof(TcJob) == 32 * sizeof(int32_t), "TcJob is dumped as 32 ints");
+    JobBuilder B(blob);
+    bool ok;
+    if (which == 0) {
+        TcParams P{};
+        ok = build_jobs(blob, &B, &P);
+    } else {
+        TailParams P{};
+        ok = build_tail_jobs(blob, &B, &P);
+    }
+    if (!ok || static_cast<int>(B.jobs.size()) > max_jobs) return -1;
+    std::memcpy(out, B.jobs.data(), B.jobs.size() * sizeof(TcJob));
+    return static_cast<int>(B.jobs.size());
+}
+
 // Diagnostics: run `n` windows with CTA 0 recording clock64 stamps per (job, window):
 // [0] MMA issue start, [1] MMA issue end, [2] epilogue start (accumulators ready), [3] epilogue end.
 int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st, bool tail) {

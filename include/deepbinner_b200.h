@@ -166,6 +166,12 @@ DBN_API void db_fast5_batch_free(db_fast5_batch *batch);
  * csrc/dbn_tc.cu) after running host windows x[0..1] through jobs 0..job.
  */
 DBN_API int db_tc_num_jobs(const db_model *model);
+/* Host only, no GPU needed: the MMA job table built for a weight blob (which = 0: tcgen05 engine,
+ * 1: tail kernel of the split engine), 32 int32 per job in the field order of struct TcJob
+ * (csrc/dbn_tc.cu).  Returns the number of jobs or a negative DBN_E* code.  Used by the CPU tests that
+ * check the schedule (accumulator-slot reuse, hand-off counts, buffer sizes). */
+DBN_API int db_tc_job_table(const void *weights_blob, size_t blob_bytes, int which, int32_t *out,
+                            int max_jobs);
 DBN_API int db_tc_debug_dump(db_model *model, const float *x, int job, unsigned char *out);
 /* Timeline of CTA 0 for n device-resident windows: trace[job][window][8] SM-clock stamps (MMA issue
  * start/end, epilogue start/end, then epilogue internals); host buffer of 32*2*8 int64. */
