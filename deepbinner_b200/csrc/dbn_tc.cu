@@ -41,6 +41,7 @@
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
+#include <algorithm>
 #include <cstddef>
 #include <cstdio>
 #include <cstring>
@@ -1181,6 +1182,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 }  // namespace dbn
 
 #include "dbn_tc_tail.cuh"
+#include "dbn_tc_front.cuh"
 
 namespace dbn {
 
@@ -1194,8 +1196,10 @@ struct TcEngine {
     TcParams params{};
     int njobs = 0;
     std::vector<TcJob> jobs;   // uploaded to constant memory (identical for every model of this topology)
-    // split engine (front kernel + four-window tail kernel, dbn_tc_tail.cuh)
+    // split engine (front kernel + four-window tail kernel, dbn_tc_tail.cuh / dbn_tc_front.cuh)
     bool tail_ok = false;
+    int sm_count = 148;
+    bool persistent_front = true;    // k_tc_front (dbn_tc_front.cuh); DBN_SPLIT_PERSISTENT=0: k_tc_forward<.., kFront>
     unsigned char* d_tw = nullptr;
     TcJob* d_tjobs = nullptr;
     float* d_tprm = nullptr;
@@ -1503,13 +1507,15 @@ static bool build_tail_jobs(const Blob& blob, JobBuilder* B, TailParams* P) {
     return true;
 }
 
-TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
+TcEngine* tc_create(const Blob& blob, int sm_count) {
     if (getenv("DBN_DISABLE_TC")) return nullptr;
     JobBuilder B(blob);
     TcParams P{};
     if (!build_jobs(blob, &B, &P)) return nullptr;
     TcEngine* e = new TcEngine();
     e->jobs = B.jobs;
+    if (sm_count > 0) e->sm_count = sm_count;
+    if (const char* v = getenv("DBN_SPLIT_PERSISTENT")) e->persistent_front = v[0] != '0';
     bool ok = cudaMalloc(&e->d_w, B.w.size()) == cudaSuccess &&
               cudaMalloc(&e->d_prm, B.prm.size() * sizeof(float)) == cudaSuccess &&
               cudaMemcpy(e->d_w, B.w.data(), B.w.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
@@ -1548,6 +1554,8 @@ TcEngine* tc_create(const Blob& blob, int /*sm_count*/) {
             cudaMemcpy(e->d_tjobs, T.jobs.data(), T.jobs.size() * sizeof(TcJob), cudaMemcpyHostToDevice) == cudaSuccess &&
             cudaFuncSetAttribute(k_tc_forward<false, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
             cudaFuncSetAttribute(k_tc_forward<true, false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+            cudaFuncSetAttribute(k_tc_front<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+            cudaFuncSetAttribute(k_tc_front<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
             cudaFuncSetAttribute(k_tc_tail<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes) == cudaSuccess &&
             cudaFuncSetAttribute(k_tc_tail<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTSmemBytes) == cudaSuccess;
         if (tok) {
@@ -1648,8 +1656,13 @@ static int launch_split(TcEngine* e, const float* d_x, const double* d_xd, const
     P.mid = mid;
     TailParams T = e->tparams;
     T.mid = mid;
-    k_tc_forward<kCall, false, true><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(P, d_x, d_xd, d_samples, d_offsets,
-                                                                             n_reads, side, n, d_probs);
+    const int npairs = (n + 1) / 2;
+    if (e->persistent_front)
+        k_tc_front<kCall><<<std::min(npairs, e->sm_count), kTcThreads, kTcSmemBytes, st>>>(P, d_x, d_xd, d_samples,
+                                                                                        d_offsets, n_reads, side, n);
+    else
+        k_tc_forward<kCall, false, true><<<npairs, kTcThreads, kTcSmemBytes, st>>>(P, d_x, d_xd, d_samples, d_offsets,
+                                                                            n_reads, side, n, d_probs);
     T.trace = d_trace;
     if (d_trace) k_tc_tail<true><<<(n + kTW - 1) / kTW, kTcThreads, kTSmemBytes, st>>>(T, n, d_probs);
     else k_tc_tail<false><<<(n + kTW - 1) / kTW, kTcThreads, kTSmemBytes, st>>>(T, n, d_probs);
