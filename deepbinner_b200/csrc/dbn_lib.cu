@@ -6,6 +6,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 #include <string>
@@ -335,6 +336,11 @@ int db_create(const void* weights_blob, size_t blob_bytes, int device, db_model*
     m->tc = tc_create(m->blob, m->sm_count);
     m->tc_available = (m->tc != nullptr);
     m->engine = m->tc_available ? DBN_ENGINE_TCGEN05 : DBN_ENGINE_FP32;
+    // DEEPBINNER_B200_ENGINE = fp32 | tcgen05 | tcgen05-split overrides the default engine of new handles
+    if (const char* want = getenv("DEEPBINNER_B200_ENGINE")) {
+        if (!std::strcmp(want, "fp32")) m->engine = DBN_ENGINE_FP32;
+        else if (!std::strcmp(want, "tcgen05-split") && tc_split_available(m->tc)) m->engine = DBN_ENGINE_TCGEN05_SPLIT;
+    }
     *out = m;
     return DBN_OK;
 }
