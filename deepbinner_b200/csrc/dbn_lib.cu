@@ -385,6 +385,10 @@ static int predict_host(db_model* m, const void* x, bool is_f64, int64_t n, floa
     DBN_CUDA(cudaSetDevice(m->device));
     const size_t esz = is_f64 ? sizeof(double) : sizeof(float);
     const int64_t kChunk = 8192;   // windows per pipelined chunk (32 MiB of fp32 input)
+    // The first chunks are small and double up to kChunk: the pipeline then fills after the 4 MiB copy
+    // of 1024 windows instead of a 32 MiB one (the kernel of chunk i overlaps the copy of chunk i+1).
+    int64_t chunk = 1024;
+    const int64_t cap = std::min(kChunk, n);   // buffers are sized once for the largest chunk
     const size_t row_in = static_cast<size_t>(m->input_size) * esz;
     const size_t row_out = static_cast<size_t>(m->n_classes) * sizeof(float);
     DBN_CUDA(cudaEventRecord(m->ev_start, m->streams[0]));
@@ -401,15 +405,16 @@ static int predict_host(db_model* m, const void* x, bool is_f64, int64_t n, floa
     };
     int slot = 0;
     while (done < n) {
-        const int64_t cnt = std::min(kChunk, n - done);
+        const int64_t cnt = std::min(chunk, n - done);
+        chunk = std::min(chunk * 2, kChunk);
         cudaStream_t st = m->streams[slot];
         int rc = drain(slot);
         if (rc) return rc;
-        rc = grow(&m->d_in[slot], &m->d_in_bytes[slot], cnt * row_in);
+        rc = grow(&m->d_in[slot], &m->d_in_bytes[slot], cap * row_in);
         if (rc) return rc;
-        rc = grow(&m->d_out[slot], &m->d_out_bytes[slot], cnt * row_out);
+        rc = grow(&m->d_out[slot], &m->d_out_bytes[slot], cap * row_out);
         if (rc) return rc;
-        rc = grow_host(&m->h_out[slot], &m->h_out_bytes[slot], cnt * row_out);
+        rc = grow_host(&m->h_out[slot], &m->h_out_bytes[slot], cap * row_out);
         if (rc) return rc;
         DBN_CUDA(cudaMemcpyAsync(m->d_in[slot], static_cast<const char*>(x) + done * row_in,
                                  cnt * row_in, cudaMemcpyHostToDevice, st));
