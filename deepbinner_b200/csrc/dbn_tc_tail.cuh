@@ -22,6 +22,9 @@
 
 namespace dbn {
 
+#ifndef DBN_TAIL_PART_MAJOR
+#define DBN_TAIL_PART_MAJOR 0
+#endif
 constexpr int kTW = 4;                               // windows per CTA
 constexpr int kTReg = 49536;                         // bytes per window region
 constexpr int kTSmemWbuf = kTW * kTReg;              // 198144
@@ -401,6 +404,30 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     wfull_phase ^= 1;
                     continue;
                 }
+#if DBN_TAIL_PART_MAJOR
+                // Variant for A/B runs (not the default): weight part 0 for all four windows, then part 1
+                // for all four - part 0 is released three bursts earlier, so the next job's first part
+                // streams in behind a longer stretch of MMAs; each window's epilogue starts later.
+#pragma unroll 1
+                for (int w = 0; w < kTW; ++w) {
+                    mbar_wait(bar_epi + 8 * w, epi_phase);
+                    tc_fence_after();
+                    if (trace) trace[(j * kTW + w) * 8 + 0] = clock64();
+                    if (w == 0) mbar_wait(bar_wfull[0], wfull_phase);
+                    issue_job_part<0>(J.ntaps, J.ncb, w * kTWinCols, J.ntiles, act16_0 + w * reg16, tap16, J.cb0, J.lp,
+                                      J.lo16, wp16[0], blk16, J.n, J.idesc, first, leader);
+                }
+                tc_commit(bar_wfree[0], leader);
+                mbar_wait(bar_wfull[1], wfull_phase);
+#pragma unroll 1
+                for (int w = 0; w < kTW; ++w) {
+                    issue_job_part<1>(J.ntaps, J.ncb, w * kTWinCols, J.ntiles, act16_0 + w * reg16, tap16, J.cb0, J.lp,
+                                      J.lo16, wp16[1], blk16, J.n, J.idesc, false, leader);
+                    if (last) tc_commit(bar_mma + 8 * w, leader);
+                    if (trace) trace[(j * kTW + w) * 8 + 1] = clock64();
+                }
+                tc_commit(bar_wfree[1], leader);
+#else
 #pragma unroll 1
                 for (int w = 0; w < kTW; ++w) {
                     mbar_wait(bar_epi + 8 * w, epi_phase);   // input written and previous accumulators drained
@@ -418,6 +445,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     if (w == kTW - 1) tc_commit(bar_wfree[1], leader);
                     if (trace) trace[(j * kTW + w) * 8 + 1] = clock64();
                 }
+#endif
                 epi_phase ^= 1;
                 wfull_phase ^= 1;
             }
