@@ -79,6 +79,9 @@ def load_library():
         'db_tc_num_jobs': (ctypes.c_int, [ctypes.c_void_p]),
         'db_tc_job_table': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
                                            ctypes.c_int]),
+        'db_tc_packed': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_size_t, ctypes.c_int, ctypes.c_void_p,
+                                        ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                        ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
         'db_tc_debug_dump': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
                                             ctypes.c_void_p]),
         'db_tc_trace': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
@@ -100,7 +103,7 @@ EXPORTED_SYMBOLS = ['db_abi_version', 'db_last_error', 'db_create', 'db_destroy'
                     'db_set_engine', 'db_get_engine', 'db_predict_windows',
                     'db_predict_windows_f64', 'db_predict_windows_device', 'db_call_batch',
                     'db_call_batch_device', 'db_last_gpu_ms', 'db_kernel_launches',
-                    'db_tc_num_jobs', 'db_tc_job_table', 'db_tc_debug_dump', 'db_tc_trace', 'db_fast5_read',
+                    'db_tc_num_jobs', 'db_tc_job_table', 'db_tc_packed', 'db_tc_debug_dump', 'db_tc_trace', 'db_fast5_read',
                     'db_fast5_list_root', 'db_fast5_batch_read', 'db_fast5_batch_get',
                     'db_fast5_batch_free']
 

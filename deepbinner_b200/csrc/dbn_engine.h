@@ -26,6 +26,8 @@ int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offs
 int tc_num_jobs(const TcEngine* e);
 // Host-only dump of the job table (32 ints per job, struct TcJob order); -1 if the model is unsupported.
 int tc_job_table(const Blob& blob, int which, int32_t* out, int max_jobs);
+int tc_packed(const Blob& blob, int which, unsigned char* w_out, int64_t w_cap, float* prm_out, int64_t prm_cap,
+              int64_t* w_bytes, int64_t* prm_floats);
 // tail = true: timeline of the split engine's tail kernel ([job][4 windows][8] stamps)
 int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st,
              bool tail = false);

@@ -554,6 +554,17 @@ int db_tc_job_table(const void* weights_blob, size_t blob_bytes, int which, int3
     return n;
 }
 
+int db_tc_packed(const void* weights_blob, size_t blob_bytes, int which, unsigned char* w_out, int64_t w_cap,
+                 float* prm_out, int64_t prm_cap, int64_t* w_bytes, int64_t* prm_floats) {
+    if (!weights_blob || !w_bytes || !prm_floats) return fail(DBN_EINVAL, "db_tc_packed: NULL buffer");
+    Blob blob;
+    const std::string err = parse_blob(weights_blob, blob_bytes, &blob);
+    if (!err.empty()) return fail(DBN_EFORMAT, "%s", err.c_str());
+    if (tc_packed(blob, which, w_out, w_cap, prm_out, prm_cap, w_bytes, prm_floats))
+        return fail(DBN_EFORMAT, "no tcgen05 job table for this model");
+    return DBN_OK;
+}
+
 int db_tc_debug_dump(db_model* m, const float* x, int job, unsigned char* out) {
     if (!m || !m->tc) return fail(DBN_EINVAL, "tcgen05 engine not available");
     if (!x || !out) return fail(DBN_EINVAL, "NULL buffer");

@@ -1716,6 +1716,27 @@ int tc_job_table(const Blob& blob, int which, int32_t* out, int max_jobs) {
     return static_cast<int>(B.jobs.size());
 }
 
+// Host only: the packed bf16 weights (what TcJob::w_goff / w_part index) and the parameter block (bias /
+// folded BN, what bias_off / bn_off index) of the same table.  Returns the sizes; copies if they fit.
+int tc_packed(const Blob& blob, int which, unsigned char* w_out, int64_t w_cap, float* prm_out, int64_t prm_cap,
+              int64_t* w_bytes, int64_t* prm_floats) {
+    JobBuilder B(blob);
+    bool ok;
+    if (which == 0) {
+        TcParams P{};
+        ok = build_jobs(blob, &B, &P);
+    } else {
+        TailParams P{};
+        ok = build_tail_jobs(blob, &B, &P);
+    }
+    if (!ok) return -1;
+    *w_bytes = static_cast<int64_t>(B.w.size());
+    *prm_floats = static_cast<int64_t>(B.prm.size());
+    if (w_out && w_cap >= *w_bytes) std::memcpy(w_out, B.w.data(), B.w.size());
+    if (prm_out && prm_cap >= *prm_floats) std::memcpy(prm_out, B.prm.data(), B.prm.size() * sizeof(float));
+    return 0;
+}
+
 // Diagnostics: run `n` windows with CTA 0 recording clock64 stamps per (job, window):
 // [0] MMA issue start, [1] MMA issue end, [2] epilogue start (accumulators ready), [3] epilogue end.
 int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st, bool tail) {

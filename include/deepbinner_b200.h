@@ -172,6 +172,12 @@ DBN_API int db_tc_num_jobs(const db_model *model);
  * check the schedule (accumulator-slot reuse, hand-off counts, buffer sizes). */
 DBN_API int db_tc_job_table(const void *weights_blob, size_t blob_bytes, int which, int32_t *out,
                             int max_jobs);
+/* Host only: the packed split-bf16 weights and the parameter block (bias / folded BatchNorm) that the
+ * job table above indexes (w_goff, w_part / bias_off, bn_off).  *w_bytes and *prm_floats receive the
+ * sizes; the data is copied when the capacities suffice (pass NULL / 0 to query). */
+DBN_API int db_tc_packed(const void *weights_blob, size_t blob_bytes, int which, unsigned char *w_out,
+                         int64_t w_cap, float *prm_out, int64_t prm_cap, int64_t *w_bytes,
+                         int64_t *prm_floats);
 DBN_API int db_tc_debug_dump(db_model *model, const float *x, int job, unsigned char *out);
 /* Timeline of CTA 0 for n device-resident windows: trace[job][window][8] SM-clock stamps (MMA issue
  * start/end, epilogue start/end, then epilogue internals); host buffer of 32*2*8 int64. */

@@ -98,3 +98,97 @@ def test_parameter_blocks_fit(name):
         jobs = job_table(name, which)
         used = max(max(j['bias'] + j['n'], j['bn'] + 96 if j['bn'] else 0) for j in jobs)
         assert used <= cap
+
+
+# ---------------------------------------------------------------------------------------------
+# packed operands: what the jobs feed the tensor cores with, against the model's own tensors
+# ---------------------------------------------------------------------------------------------
+# job -> (conv layers computed by it (second = appended along N), BatchNorm applied in its epilogue)
+FUSED_LAYERS = [((2,), 0), ((3,), 0), ((4,), 2), ((5,), 0), ((6,), 0), ((7,), 3), ((8,), 0), ((9,), 4),
+                ((12, 14), 0), ((11,), 5), ((15,), 0), ((13,), 5), ((10,), 5), ((16,), 5),
+                ((17,), 0), ((17,), 0), ((17,), 0), ((17,), 6), ((18,), 0), ((19,), 7), ((20,), 0)]
+TAIL_LAYERS = [((5,), 0), ((6,), 0), ((7,), 3), ((8,), 0), ((9,), 4),
+               ((12, 14), 0), ((11,), 5), ((10,), 5), ((15,), 0), ((13,), 5), ((16,), 5),
+               ((17,), 0), ((17,), 0), ((17,), 0), ((17,), 6), ((18,), 0), ((19,), 7), ((20,), 0)]
+
+
+def packed(name, which):
+    import ctypes
+    from deepbinner_b200 import _native, weights
+    lib = _native.load_library()
+    blob = weights.load_blob(model_path(name))
+    wb, pf = ctypes.c_int64(), ctypes.c_int64()
+    assert lib.db_tc_packed(blob, len(blob), which, None, 0, None, 0, ctypes.byref(wb), ctypes.byref(pf)) == 0
+    w = np.zeros(wb.value, np.uint8)
+    prm = np.zeros(pf.value, np.float32)
+    assert lib.db_tc_packed(blob, len(blob), which, _native.as_ptr(w), len(w), _native.as_ptr(prm), len(prm),
+                            ctypes.byref(wb), ctypes.byref(pf)) == 0
+    return w, prm
+
+
+def bf16_pairs_to_f32(buf):
+    return (buf.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
+
+
+@pytest.mark.parametrize('which,layers', [(0, FUSED_LAYERS), (1, TAIL_LAYERS)])
+@pytest.mark.parametrize('name', MODELS)
+def test_packed_weights_and_parameters_match_the_model(name, which, layers):
+    from oracle import deepbinner_oracle as orc
+    model = orc.load_weights(model_path(name), dtype=np.float64)
+    jobs = job_table(name, which)
+    w, prm = packed(name, which)
+    assert len(jobs) == len(layers)
+    for j, (convs, bn) in zip(jobs, layers):
+        n, ntaps, ncb, cb0 = j['n'], j['ntaps'], j['ncb'], j['cb0']
+        nkb = ntaps * ncb
+        split = 5 if nkb == 9 else 2
+        # expected kernel [ntaps][cin][n]: layers appended along N, average pool folded (W/3 on three taps)
+        kernels = [model['conv1d_%d/kernel' % c] for c in convs]
+        folded = j['edge15'] == 1
+        assert folded == (convs == (10,))
+        cin_total = kernels[0].shape[1]
+        expect = np.zeros((ntaps, cin_total, n))
+        col = 0
+        for k in kernels:
+            kk = np.repeat(k / 3.0, 3, axis=0) if folded else k
+            assert kk.shape[0] == ntaps and kk.shape[1] == cin_total
+            expect[:, :, col:col + kk.shape[2]] = kk
+            col += kk.shape[2]
+        # unpack [part 0 | part 1], part = [hi blocks | lo blocks], block = [2 chunks][n rows][8]
+        got = np.zeros((ntaps, cin_total, n))
+        seen = np.zeros((ntaps, cin_total), bool)
+        off = j['w_goff']
+        for kb0, kb1 in ((0, split), (split, nkb)):
+            cnt = kb1 - kb0
+            part = bf16_pairs_to_f32(w[off:off + 2 * cnt * 2 * n * 8 * 2]).astype(np.float64)
+            hi, lo = part[:cnt * 2 * n * 8], part[cnt * 2 * n * 8:]
+            both = (hi + lo).reshape(cnt, 2, n, 8)
+            assert np.all(np.abs(lo) <= np.abs(hi) * 2.0 ** -7 + 1e-30)      # lo is the remainder of hi
+            for kb in range(kb0, kb1):
+                t, cb = divmod(kb, ncb)
+                for chunk in range(2):
+                    c0 = (cb0 + cb) * 16 + chunk * 8
+                    got[t, c0:c0 + 8, :] = both[kb - kb0, chunk].T
+                    seen[t, c0:c0 + 8] = True
+            off += 2 * cnt * 2 * n * 8 * 2
+        assert off - j['w_goff'] == j['wp0'] + j['wp1']
+        scale = np.abs(expect).max()
+        assert np.abs(got[seen] - expect[seen]).max() <= scale * 2.0 ** -15, (j, convs)
+        if convs != (17,):
+            assert seen.all()
+        else:
+            assert seen[:, cb0 * 16:(cb0 + 3) * 16].all() and seen.sum() == 3 * 48   # one K-slice of conv1d_17
+        if not j['last']:
+            continue
+        # bias (zero padded to n) and folded BatchNorm of the epilogue
+        bias = np.concatenate([model['conv1d_%d/bias' % c] for c in convs])
+        got_bias = prm[j['bias']:j['bias'] + n]
+        assert np.allclose(got_bias[:len(bias)], bias, rtol=1e-6, atol=0) and not got_bias[len(bias):].any()
+        assert (bn != 0) == (j['bn'] != 0)
+        if bn:
+            p = 'batch_normalization_%d/' % bn
+            s = model[p + 'gamma'] / np.sqrt(model[p + 'moving_variance'] + 1e-3)
+            h = model[p + 'beta'] - model[p + 'moving_mean'] * s
+            ch0 = j['out_cg'] * 8 if j['kind'] == EPI_PARITY else 0
+            assert np.allclose(prm[j['bn']:j['bn'] + 48], s[ch0:ch0 + 48], rtol=1e-6)
+            assert np.allclose(prm[j['bn'] + 48:j['bn'] + 96], h[ch0:ch0 + 48], rtol=1e-5, atol=1e-6)
