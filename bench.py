@@ -200,7 +200,7 @@ def main():
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--engine', default=None, choices=[None, 'fp32', 'tcgen05', 'tcgen05-split'])
+    ap.add_argument('--engine', default=None, choices=[None, 'fp32', 'tcgen05', 'tcgen05-pair'])
     ap.add_argument('--shard', type=int, default=SHARD)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
@@ -352,9 +352,7 @@ def main():
 
     if rank == 0:
         peak, peak_src = measured_peaks()
-        # one network pass over a batch = one kernel (two for the split engine: front + tail)
-        kernels_per_batch = 2 if model.engine == 'tcgen05-split' else 1
-        avg_launch_ms = ms / max(launches // kernels_per_batch, 1)
+        avg_launch_ms = ms / max(launches, 1)      # one network pass over a batch = one kernel
         achieved = FLOP_PER_WINDOW * BATCH / (avg_launch_ms * 1e-3) / 1e12
         traffic = None
         tfile = ROOT / 'profiles' / 'traffic_r01.json'

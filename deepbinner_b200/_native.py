@@ -19,8 +19,8 @@ LIB_PATH = pathlib.Path(os.environ.get('DEEPBINNER_B200_LIB') or _PKG / 'libdeep
 
 DBN_OK = 0
 SIDE_START, SIDE_END = 0, 1
-ENGINE_FP32, ENGINE_TCGEN05, ENGINE_TCGEN05_SPLIT = 0, 1, 2
-ENGINE_NAMES = {ENGINE_FP32: 'fp32', ENGINE_TCGEN05: 'tcgen05', ENGINE_TCGEN05_SPLIT: 'tcgen05-split'}
+ENGINE_FP32, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR = 0, 1, 2
+ENGINE_NAMES = {ENGINE_FP32: 'fp32', ENGINE_TCGEN05: 'tcgen05', ENGINE_TCGEN05_PAIR: 'tcgen05-pair'}
 ABI_VERSION = 1
 
 _lib = None
@@ -35,13 +35,19 @@ def load_library():
     global _lib
     if _lib is not None:
         return _lib
-    if not LIB_PATH.exists() or os.environ.get('DEEPBINNER_B200_REBUILD'):
-        from . import build
+    from . import build
+    default_lib = not os.environ.get('DEEPBINNER_B200_LIB')
+    stale = default_lib and LIB_PATH.exists() and build.needs_build() and build.have_nvcc()
+    if not LIB_PATH.exists() or os.environ.get('DEEPBINNER_B200_REBUILD') or stale:
+        # (a library older than csrc/ is rebuilt when nvcc is here; on a box without nvcc it is used as is)
         try:
             build.build_library(force=True)
         except Exception as e:  # noqa: BLE001
-            raise ImportError('libdeepbinner_b200.so is missing and could not be built: {}\n'
-                              'deepbinner_b200 has no CPU fallback.'.format(e))
+            if not LIB_PATH.exists():
+                raise ImportError('libdeepbinner_b200.so is missing and could not be built: {}\n'
+                                  'deepbinner_b200 has no CPU fallback.'.format(e))
+            import warnings
+            warnings.warn('libdeepbinner_b200.so is older than its sources and could not be rebuilt: {}'.format(e))
     lib = ctypes.CDLL(str(LIB_PATH))
     c_void_pp = ctypes.POINTER(ctypes.c_void_p)
     sigs = {

@@ -23,6 +23,12 @@ def _nvcc():
     return 'nvcc'
 
 
+def have_nvcc():
+    import shutil
+    cand = _nvcc()
+    return bool(os.path.isabs(cand) and os.path.exists(cand) or shutil.which(cand))
+
+
 def needs_build():
     if not LIB.exists():
         return True

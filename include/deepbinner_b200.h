@@ -45,9 +45,10 @@ extern "C" {
 
 /* Engines (db_set_engine).  Both are hand-written sm_100a CUDA; results agree to ~1e-4. */
 #define DBN_ENGINE_FP32 0    /* CUDA-core fp32 fused per-window kernel (parity anchor) */
-#define DBN_ENGINE_TCGEN05 1 /* tcgen05/TMEM split-bf16 tensor-core kernel */
-#define DBN_ENGINE_TCGEN05_SPLIT 2 /* experimental: same arithmetic as two kernels (conv1d_1-4 with two
-                                    * windows per CTA, conv1d_5-20 with four); not selected by default */
+#define DBN_ENGINE_TCGEN05 1 /* tcgen05/TMEM split-bf16 tensor-core kernel, one window per CTA and two CTAs
+                              * per SM (default) */
+#define DBN_ENGINE_TCGEN05_PAIR 2 /* the same arithmetic with two windows per CTA and one CTA per SM
+                                   * (round-1 kernel, kept for A/B measurements) */
 
 typedef struct db_model db_model;
 

@@ -19,6 +19,32 @@ def pytest_configure(config):
     config.addinivalue_line('markers', 'gpu: needs a real B200 (run with -m gpu on the GPU box)')
 
 
+def _gpu_status():
+    """None if a usable B200 is present, else the reason (no library / no device)."""
+    try:
+        from deepbinner_b200.model import B200Model
+        B200Model(str(MODEL_DIR / (MODELS[0] + '.dbnw'))).close()
+        return None
+    except Exception as e:  # noqa: BLE001
+        return str(e)
+
+
+def pytest_collection_modifyitems(config, items):
+    """`gpu`-marked tests are skipped (not errored) on a box without a usable B200 - unless they were
+    asked for explicitly with `-m gpu`, where a missing device must fail loudly."""
+    if not any('gpu' in item.keywords for item in items):
+        return
+    if 'gpu' in (config.getoption('-m') or ''):
+        return
+    why = _gpu_status()
+    if why is None:
+        return
+    skip = pytest.mark.skip(reason='no usable B200: ' + why.splitlines()[0])
+    for item in items:
+        if 'gpu' in item.keywords:
+            item.add_marker(skip)
+
+
 def model_path(name):
     return str(MODEL_DIR / (name + '.dbnw'))
 

@@ -16,12 +16,14 @@ TOL = 1e-3   # north_star: softmax probabilities within 1e-3 max-abs of the CPU 
 
 
 def engines(model):
+    """Engines to test, the default (tcgen05) last.  On an sm_100 device a tensor-core engine that
+    cannot be selected is a FAILURE (the only legitimate exception: more than 16 classes, which the
+    tensor-core head does not handle) - never a silent fp32-only run."""
     names = ['fp32']
-    try:
-        model.set_engine('tcgen05')
-        names.append('tcgen05')
-    except Exception:  # noqa: BLE001
-        pass
+    if model.n_classes <= 16:
+        for name in ('tcgen05-pair', 'tcgen05'):
+            model.set_engine(name)     # raises NativeError if unavailable
+            names.append(name)
     return names
 
 
@@ -61,6 +63,7 @@ def test_predict_parity_on_real_windows(models, oracle_weights, fixture_reads, m
     for name, model in models.items():
         ref = orc.forward(oracle_weights[name], x.astype(np.float32))
         unsat = int((ref.max(axis=1) < 0.99).sum())
+        assert unsat >= 15     # (the dedicated unsaturated population: test_parity_on_unsaturated_windows)
         for eng in engines(model):
             model.set_engine(eng)
             got = model.predict(x[:, :, None], batch_size=256)
@@ -73,32 +76,38 @@ def test_predict_parity_on_real_windows(models, oracle_weights, fixture_reads, m
             assert np.allclose(got.sum(axis=1), 1.0, atol=1e-5)
 
 
-def test_split_engine_parity(models, oracle_weights, fixture_reads, multi_reads):
-    """Experimental DBN_ENGINE_TCGEN05_SPLIT (front kernel + four-window tail kernel): same bar as the
-    default engine on the real windows, predict and fused call_batch, odd window counts included."""
-    from deepbinner_b200 import classify as cls
-    ids, sigs, _ = fixture_reads
-    _, msigs = multi_reads
-    x = np.concatenate([orc.make_windows(sigs, 1024, s, side) for side in ('start', 'end')
-                        for s in range(12)] + [sliding_windows(sigs + msigs, 333, seed=5)])
+def unsaturated_windows(name):
+    """The committed unsaturated population of tests/golden/unsaturated_windows.npz (made by
+    tests/golden/make_unsaturated.py): z-scored windows of the fixture reads + fp64 oracle rows."""
+    from conftest import GOLDEN
+    u = np.load(GOLDEN / 'unsaturated_windows.npz')
+    z = np.load(GOLDEN / 'fixture_reads.npz')
+    reads = [str(r) for r in u['reads']]
+    x = np.stack([orc.normalise(z[reads[r]][o:o + 1024]) for r, o in zip(u[name + '|read'], u[name + '|offset'])])
+    return x, u[name + '|probs']
+
+
+def test_parity_on_unsaturated_windows(models):
+    """The parity statistic where it matters: >= 500 windows per model whose oracle top-1 is below
+    0.99 (>= 100 of them in [0.3, 0.7]) - a saturated softmax hides operand-precision errors (SURVEY
+    Appendix C).  Floors are asserted, max / p99 per model and engine are printed (profiles/r02_parity.txt)."""
     for name, model in models.items():
-        try:
-            model.set_engine('tcgen05-split')
-        except Exception as e:  # noqa: BLE001
-            pytest.skip('split engine unavailable: {}'.format(e))
-        ref = orc.forward(oracle_weights[name], x.astype(np.float32))
-        for n in (len(x), 1, 2, 3, 5):
-            got = model.predict(x[:n, :, None], batch_size=256)
-            err = np.abs(got - ref[:n]).max(axis=1)
-            print('{} [split] n={}: max {:.2e}'.format(name, n, err.max()))
+        x, ref = unsaturated_windows(name)
+        top = ref.max(axis=1)
+        assert len(x) >= 500 and (top < 0.99).all() and ((top >= 0.3) & (top <= 0.7)).sum() >= 100
+        for eng in engines(model):
+            model.set_engine(eng)
+            got = model.predict(x[:, :, None], batch_size=256)
+            err = np.abs(got - ref).max(axis=1)
+            print('PARITY {} [{}]: unsaturated {} (mid {}), max {:.3e} p99 {:.3e} mean {:.3e} argmax flips {}'.format(
+                name, eng, len(x), int(((top >= 0.3) & (top <= 0.7)).sum()), err.max(), np.percentile(err, 99),
+                err.mean(), int((got.argmax(axis=1) != ref.argmax(axis=1)).sum())))
             assert err.max() <= TOL
-            assert np.array_equal(got.argmax(axis=1), ref[:n].argmax(axis=1))
-        side = 'end' if name.endswith('ends') else 'start'
-        calls, probs = cls.call_batch(1024, 13, ids, sigs, model, make_args(), side)
-        ocalls, oprobs = orc.call_batch(oracle_weights[name], sigs, side, 6144, 0.5)
-        assert calls == ocalls
-        assert np.abs(np.array(probs) - np.array(oprobs, dtype=float)).max() <= TOL
-        model.set_engine('tcgen05')
+            # an argmax flip needs two classes within 2 x err of each other in the oracle row
+            flips = np.nonzero(got.argmax(axis=1) != ref.argmax(axis=1))[0]
+            for i in flips:
+                srt = np.sort(ref[i])
+                assert srt[-1] - srt[-2] <= 2 * TOL
 
 
 def test_predict_accepts_f32_f64_and_returns_fresh_arrays(models, fixture_reads):
@@ -423,7 +432,7 @@ def test_other_class_counts_with_random_weights(n_classes, tmp_path, fixture_rea
         with pytest.raises(_native.NativeError):
             model.set_engine('tcgen05')
     else:
-        assert 'tcgen05' in names
+        assert names[-1] == 'tcgen05' 
     for eng in names:
         model.set_engine(eng)
         got = model.predict(x)

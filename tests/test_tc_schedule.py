@@ -1,8 +1,10 @@
-"""Host-side checks of the tcgen05 engine's MMA job tables (csrc/dbn_tc.cu build_jobs /
-build_tail_jobs), dumped through the C ABI without a GPU (db_tc_job_table).
+"""Host-side checks of the tcgen05 engine's MMA job tables (csrc/dbn_tc.cu build_jobs - pair kernel,
+which = 0 - and build_solo_jobs - solo kernel, which = 1), dumped through the C ABI without a GPU
+(db_tc_job_table).
 
-The joint phase lets the MMA issuer run ahead of the epilogue warps: every joint job carries `need`,
-the number of joint epilogues that must have completed before its MMAs may be issued.  These tests
+The MMA issuer runs ahead of the epilogue warps: a job carries `need`, the number of epilogues of the
+hand-off sequence that must have completed before its MMAs may be issued (pair kernel: the joint jobs,
+numbered from 0; solo kernel: every job, with conv1d_1's CUDA-core stage as epilogue 0).  These tests
 re-derive the hazards from the table itself - shared-memory tensors (who wrote what a job reads),
 accumulator slots (who drained the slot a job overwrites), the 4-deep mbarrier rings - so that an edit
 of the job order or of the buffer layout that forgets a dependency fails here, on the CPU."""
@@ -40,34 +42,43 @@ def out_extent(job):
     return job['out_off'], job['out_off'] + 2 * job['out_lo']
 
 
-@pytest.mark.parametrize('which,njobs', [(0, 21), (1, 18)])
+@pytest.mark.parametrize('which,njobs', [(0, 21), (1, 21)])
 @pytest.mark.parametrize('name', MODELS)
 def test_joint_schedule_is_hazard_free(name, which, njobs):
     jobs = job_table(name, which)
+    solo = which == 1
     assert len(jobs) == njobs
     joint = [j for j in jobs if j['joint'] != JOINT_NONE]
     assert jobs.index(joint[0]) + len(joint) == len(jobs), 'joint jobs form the tail of the table'
     assert all(j['first'] and j['last'] for j in jobs if j['joint'] == JOINT_NONE)
 
-    # weights of every job fit the two-part buffer; every part is a whole number of 16-byte rows
     for j in jobs:
-        assert 0 < j['wp0'] <= W_PART0 and 0 < j['wp1'] <= W_PART1
-        assert j['w_goff'] % 128 == 0 and j['wp0'] % 16 == 0 and j['wp1'] % 16 == 0
         nkb = j['ntaps'] * j['ncb']
-        assert nkb in (3, 9)
-        assert j['wp0'] + j['wp1'] == nkb * 2 * 2 * j['n'] * 16   # K blocks x (hi, lo) x 2 chunks x n rows
+        assert nkb in (3, 9) and j['w_goff'] % 128 == 0
+        if solo:   # K-block major: wp0 = bytes of one K block ((hi, lo) x 2 chunks x n rows x 16 B), wp1 = K blocks
+            assert j['wp0'] == 2 * 2 * j['n'] * 16 <= 3072 and j['wp1'] == nkb
+        else:      # weights of every job fit the two-part buffer; every part is a whole number of 16-byte rows
+            assert 0 < j['wp0'] <= W_PART0 and 0 < j['wp1'] <= W_PART1
+            assert j['wp0'] % 16 == 0 and j['wp1'] % 16 == 0
+            assert j['wp0'] + j['wp1'] == nkb * 2 * 2 * j['n'] * 16   # K blocks x (hi, lo) x 2 chunks x n rows
 
+    # hand-off sequence: the joint jobs (pair kernel) / every job, after conv1d_1's stage = epilogue 0 (solo)
+    seq = jobs if solo else joint
+    e0 = 1 if solo else 0
     # epilogue sequence numbers: consecutive over the jobs that have an epilogue; need never decreases
-    eseq = [j['eseq'] for j in joint if j['last']]
-    assert eseq == list(range(len(eseq)))
-    assert all(j['eseq'] == -1 for j in joint if not j['last'])
-    needs = [j['need'] for j in joint]
-    assert needs == sorted(needs) and needs[0] == 0
+    eseq = [j['eseq'] for j in seq if j['last']]
+    assert eseq == list(range(e0, e0 + len(eseq)))
+    assert all(j['eseq'] == -1 for j in seq if not j['last'])
+    needs = [j['need'] for j in seq]
+    assert needs == sorted(needs) and needs[0] == e0
+    if solo:   # conv1d_2 .. conv1d_9 form a chain: each waits for every earlier epilogue, columns from 0
+        assert all(j['need'] == j['eseq'] and j['tcol'] == 0 for j in jobs if j['joint'] == JOINT_NONE)
+        assert all(j['tcol'] + 64 <= 256 for j in jobs) and all(j['ntiles'] <= 4 for j in jobs)
 
     slot_drained_by = {}     # accumulator slot -> eseq of the epilogue that last read it
-    writer_of = []           # (extent, eseq, is_parity) of tensors written by joint epilogues
-    done_epilogues = 0
-    for k, j in enumerate(joint):
+    writer_of = []           # (extent, eseq, is_parity) of tensors written by epilogues of the sequence
+    done_epilogues = e0
+    for k, j in enumerate(seq):
         # (a) the tensor the job reads was written by an epilogue that `need` covers
         if j['joint'] == JOINT_STACK and j['kind'] == EPI_N48_BN and j['ntaps'] == 3 and j['ncb'] == 3 and \
                 j['lo16'] * 16 > 8192:
@@ -77,24 +88,27 @@ def test_joint_schedule_is_hazard_free(name, which, njobs):
             producers = [e for ((a, b), e, parity) in writer_of if not parity and a < hi and lo < b]
         if producers:
             assert j['need'] >= max(producers) + 1, (k, j, producers)
-        # (b) the accumulator slot was drained
-        if j['first'] and j['tcol'] in slot_drained_by:
-            assert j['need'] >= slot_drained_by[j['tcol']] + 1, (k, j)
+        # (b) the accumulator slot(s) were drained
+        cols = [j['tcol'] + 64 * t for t in range(j['ntiles'])]
+        for c in cols:
+            if j['first'] and c in slot_drained_by:
+                assert j['need'] >= slot_drained_by[c] + 1, (k, j)
         # (c) the 4-deep mbarrier rings never hold more than three unconsumed phases
         if j['last']:
             done_epilogues += 1
         assert done_epilogues - j['need'] <= RING - 1, (k, j)
         if j['last']:
-            slot_drained_by[j['tcol']] = j['eseq']
+            for c in cols:
+                slot_drained_by[c] = j['eseq']
             if j['kind'] != EPI_HEAD:
                 writer_of.append((out_extent(j), j['eseq'], j['kind'] == EPI_PARITY))
     # the head is the last epilogue and waits for everything before it
-    assert joint[-1]['kind'] == EPI_HEAD and joint[-1]['need'] == len(eseq) - 1
+    assert joint[-1]['kind'] == EPI_HEAD and joint[-1]['need'] == eseq[-1]
 
 
 @pytest.mark.parametrize('name', MODELS)
 def test_parameter_blocks_fit(name):
-    for which, cap in ((0, 1664), (1, 1424)):
+    for which, cap in ((0, 1664), (1, 1 << 20)):   # (the solo kernel reads its parameters from global memory)
         jobs = job_table(name, which)
         used = max(max(j['bias'] + j['n'], j['bn'] + 96 if j['bn'] else 0) for j in jobs)
         assert used <= cap
@@ -107,9 +121,6 @@ def test_parameter_blocks_fit(name):
 FUSED_LAYERS = [((2,), 0), ((3,), 0), ((4,), 2), ((5,), 0), ((6,), 0), ((7,), 3), ((8,), 0), ((9,), 4),
                 ((12, 14), 0), ((11,), 5), ((15,), 0), ((13,), 5), ((10,), 5), ((16,), 5),
                 ((17,), 0), ((17,), 0), ((17,), 0), ((17,), 6), ((18,), 0), ((19,), 7), ((20,), 0)]
-TAIL_LAYERS = [((5,), 0), ((6,), 0), ((7,), 3), ((8,), 0), ((9,), 4),
-               ((12, 14), 0), ((11,), 5), ((10,), 5), ((15,), 0), ((13,), 5), ((16,), 5),
-               ((17,), 0), ((17,), 0), ((17,), 0), ((17,), 6), ((18,), 0), ((19,), 7), ((20,), 0)]
 
 
 def packed(name, which):
@@ -130,7 +141,7 @@ def bf16_pairs_to_f32(buf):
     return (buf.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
 
 
-@pytest.mark.parametrize('which,layers', [(0, FUSED_LAYERS), (1, TAIL_LAYERS)])
+@pytest.mark.parametrize('which,layers', [(0, FUSED_LAYERS), (1, FUSED_LAYERS)])
 @pytest.mark.parametrize('name', MODELS)
 def test_packed_weights_and_parameters_match_the_model(name, which, layers):
     from oracle import deepbinner_oracle as orc
@@ -155,10 +166,12 @@ def test_packed_weights_and_parameters_match_the_model(name, which, layers):
             expect[:, :, col:col + kk.shape[2]] = kk
             col += kk.shape[2]
         # unpack [part 0 | part 1], part = [hi blocks | lo blocks], block = [2 chunks][n rows][8]
+        # (solo kernel: one part per K block)
         got = np.zeros((ntaps, cin_total, n))
         seen = np.zeros((ntaps, cin_total), bool)
         off = j['w_goff']
-        for kb0, kb1 in ((0, split), (split, nkb)):
+        parts = [(kb, kb + 1) for kb in range(nkb)] if which == 1 else [(0, split), (split, nkb)]
+        for kb0, kb1 in parts:
             cnt = kb1 - kb0
             part = bf16_pairs_to_f32(w[off:off + 2 * cnt * 2 * n * 8 * 2]).astype(np.float64)
             hi, lo = part[:cnt * 2 * n * 8], part[cnt * 2 * n * 8:]
@@ -171,7 +184,7 @@ def test_packed_weights_and_parameters_match_the_model(name, which, layers):
                     got[t, c0:c0 + 8, :] = both[kb - kb0, chunk].T
                     seen[t, c0:c0 + 8] = True
             off += 2 * cnt * 2 * n * 8 * 2
-        assert off - j['w_goff'] == j['wp0'] + j['wp1']
+        assert off - j['w_goff'] == (j['wp0'] * j['wp1'] if which == 1 else j['wp0'] + j['wp1'])
         scale = np.abs(expect).max()
         assert np.abs(got[seen] - expect[seen]).max() <= scale * 2.0 ** -15, (j, convs)
         if convs != (17,):
