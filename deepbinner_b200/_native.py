@@ -80,6 +80,11 @@ def load_library():
         'db_fast5_batch_read': (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int,
                                                ctypes.c_int, ctypes.c_int64,
                                                ctypes.POINTER(ctypes.c_void_p)]),
+        'db_fast5_batch_read_reads': (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int,
+                                                     ctypes.c_int, ctypes.c_int64,
+                                                     ctypes.POINTER(ctypes.c_void_p)]),
+        'db_fast5_batch_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
+                                               ctypes.POINTER(ctypes.c_void_p)]),
         'db_fast5_batch_get': (ctypes.c_int, [ctypes.c_void_p] + [ctypes.POINTER(ctypes.c_void_p)] * 5),
         'db_fast5_batch_free': (None, [ctypes.c_void_p]),
         'db_tc_num_jobs': (ctypes.c_int, [ctypes.c_void_p]),
@@ -110,7 +115,8 @@ EXPORTED_SYMBOLS = ['db_abi_version', 'db_last_error', 'db_create', 'db_destroy'
                     'db_predict_windows_f64', 'db_predict_windows_device', 'db_call_batch',
                     'db_call_batch_device', 'db_last_gpu_ms', 'db_kernel_launches',
                     'db_tc_num_jobs', 'db_tc_job_table', 'db_tc_packed', 'db_tc_debug_dump', 'db_tc_trace', 'db_fast5_read',
-                    'db_fast5_list_root', 'db_fast5_batch_read', 'db_fast5_batch_get',
+                    'db_fast5_list_root', 'db_fast5_batch_read', 'db_fast5_batch_read_reads', 'db_fast5_batch_rows',
+                    'db_fast5_batch_get',
                     'db_fast5_batch_free']
 
 

@@ -77,11 +77,17 @@ def load_trained_model(model_file, out_dest=sys.stderr, device=0):
     if not pathlib.Path(model_file).is_file():
         sys.exit('Error: {} does not exist'.format(model_file))
     print('Loading {}... '.format(model_file), file=out_dest, end='', flush=True)
+    # (B200 engines: input size 1024 - what every shipped model has - and at most 32 classes; the
+    # native layer rejects anything else with DBN_EFORMAT, reported like any other invalid model file.
+    # The reference accepts any even input size, check_input_size below.)
+    from ._native import NativeError
     try:
         model = B200Model(str(model_file), device=device)
     except (weights.ModelFormatError, hdf5_lite.Hdf5Error, KeyError):
         sys.exit('Error: model input has incorrect shape - are you sure that {} is a valid '
                  'model file?'.format(model_file))
+    except NativeError as e:
+        sys.exit('Error: could not load {} on the B200 engine: {}'.format(model_file, e))
     print('done', file=out_dest)
     input_size = int(model.inputs[0].shape[1])
     output_size = int(model.outputs[0].shape[1])
@@ -97,10 +103,10 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
         sys.exit('Error: no fast5 files found')
     out_dest = sys.stderr if full_output else sys.stdout
 
-    if not verified_single_read:
-        if determine_single_or_multi_fast5s(fast5_files) == 'multi':
-            sys.exit('Error: deepbinner classify requires one-read-per-file fast5s - convert with '
-                     'multi_to_single_fast5 before running')
+    # Multi-read fast5 files are read natively, every read straight out of the file (the reference
+    # needs them unpacked to one file per read first, realtime.py:183-196); a batch is then one file
+    # (thousands of reads in a MinKNOW file) instead of `batch_size` files.
+    multi = (not verified_single_read) and determine_single_or_multi_fast5s(fast5_files) == 'multi'
 
     use_start, use_end = start_model is not None, end_model is not None
     print_classification_progress(0, len(fast5_files), 'fast5s', out_dest=out_dest)
@@ -110,10 +116,11 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
     input_size = start_input_size if use_start else end_input_size
     keep = int(args.scan_size) + input_size // 2
     classifications, read_id_to_fast5_file = {}, {}
+    files_done = 0
     # Each batch is parsed on native host threads (only the samples call_batch can look at - the
     # first / last scan_size + input_size/2 - are kept, which gives identical calls); the parse of
     # batch i+1 runs in the background (the C call releases the GIL) while batch i is on the GPU.
-    batches = list(chunker(fast5_files, args.batch_size))
+    batches = list(chunker(fast5_files, 1 if multi else args.batch_size))
     prefetcher = concurrent.futures.ThreadPoolExecutor(max_workers=1)
     pending = prefetcher.submit(load_batch, batches[0], keep)
     for index, batch in enumerate(batches):
@@ -151,7 +158,8 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
                         row.append(end_calls[i])
             print('\t'.join(row))
 
-        print_classification_progress(len(classifications), len(fast5_files), 'fast5s',
+        files_done += len(batch)
+        print_classification_progress(files_done if multi else len(classifications), len(fast5_files), 'fast5s',
                                       out_dest=out_dest)
 
     prefetcher.shutdown()

@@ -465,41 +465,62 @@ bool read_file(const char* path, std::vector<uint8_t>* data) {
     return got == data->size();
 }
 
-// status: 0 ok, 1 unreadable / not HDF5 / no read (-> (None, None) in the reference), 2 multi-read file
-int read_one(const char* path, std::string* read_id, std::vector<int16_t>* signal) {
+struct ReadRec {
+    std::string id;
+    std::vector<int16_t> signal;
+};
+
+// One read group (`/Raw/Reads/Read_<n>` of the old layout, `/read_<uuid>/Raw` of the new one):
+// `read_id` attribute + `Signal` dataset (load_fast5s.py:33-44).
+bool read_group(const File& f, uint64_t group, ReadRec* r) {
+    if (!f.string_attr(group, "read_id", &r->id)) return false;
+    uint64_t sig;
+    if (!f.find(group, "Signal", &sig)) return false;
+    f.read_i16(sig, &r->signal);
+    return true;
+}
+
+// All reads of a fast5 file.  Single-read layouts give one read; a multi-read file (several
+// `/read_<uuid>` groups in the root, load_fast5s.py:67-98) gives every read, ordered by group name -
+// read straight from the file, where the reference unpacks it to one file per read with ONT's
+// `multi_to_single_fast5` first (realtime.py:183-196).  A read that cannot be parsed is skipped, as
+// an unreadable unpacked file would be (load_fast5s.py:48-49).
+// status: 0 ok, 1 unreadable / not HDF5 / no read.  *multi = the root holds more than one read group.
+int read_all(const char* path, std::vector<ReadRec>* reads, bool* multi, bool want_multi) {
+    *multi = false;
     std::vector<uint8_t> data;
     if (!read_file(path, &data)) return 1;
     try {
         File f(data);
         const std::vector<Link> root = f.links(f.root());
-        uint64_t group = 0;
-        bool found = false;
         for (const Link& l : root)
             if (l.name == "Raw") {   // old single-read layout: /Raw/Reads/<first child>
-                uint64_t reads;
-                if (!f.find(l.addr, "Reads", &reads)) return 1;
-                const std::vector<Link> kids = f.links(reads);
+                uint64_t rg;
+                if (!f.find(l.addr, "Reads", &rg)) return 1;
+                const std::vector<Link> kids = f.links(rg);
                 if (kids.empty()) return 1;
-                group = kids[0].addr;
-                found = true;
+                ReadRec r;
+                if (!read_group(f, kids[0].addr, &r)) return 1;
+                reads->push_back(std::move(r));
+                return 0;
             }
-        if (!found) {                // new layout: /read_<uuid>/Raw
-            int count = 0;
-            uint64_t read_group = 0;
-            for (const Link& l : root)
-                if (l.name.compare(0, 5, "read_") == 0) {
-                    ++count;
-                    read_group = l.addr;
-                }
-            if (count > 1) return 2;
-            if (count == 0) return 1;
-            if (!f.find(read_group, "Raw", &group)) return 1;
+        std::vector<const Link*> groups;   // new layout: /read_<uuid>/Raw
+        for (const Link& l : root)
+            if (l.name.compare(0, 5, "read_") == 0) groups.push_back(&l);
+        if (groups.empty()) return 1;
+        *multi = groups.size() > 1;
+        if (*multi && !want_multi) return 0;
+        std::sort(groups.begin(), groups.end(), [](const Link* a, const Link* b) { return a->name < b->name; });
+        for (const Link* l : groups) {
+            ReadRec r;
+            uint64_t raw;
+            try {
+                if (f.find(l->addr, "Raw", &raw) && read_group(f, raw, &r)) reads->push_back(std::move(r));
+            } catch (const ParseError&) {
+                if (!*multi) return 1;
+            }
         }
-        if (!f.string_attr(group, "read_id", read_id)) return 1;
-        uint64_t sig;
-        if (!f.find(group, "Signal", &sig)) return 1;
-        f.read_i16(sig, signal);
-        return 0;
+        return reads->empty() ? 1 : 0;
     } catch (const ParseError&) {
         return 1;
     } catch (const std::exception&) {
@@ -507,14 +528,27 @@ int read_one(const char* path, std::string* read_id, std::vector<int16_t>* signa
     }
 }
 
+// status: 0 ok, 1 unreadable / not HDF5 / no read (-> (None, None) in the reference), 2 multi-read file
+int read_one(const char* path, std::string* read_id, std::vector<int16_t>* signal) {
+    std::vector<ReadRec> reads;
+    bool multi = false;
+    const int st = read_all(path, &reads, &multi, false);
+    if (st) return st;
+    if (multi) return 2;
+    *read_id = std::move(reads[0].id);
+    *signal = std::move(reads[0].signal);
+    return 0;
+}
+
 }  // namespace
 
 struct db_fast5_batch {
     std::vector<int16_t> samples;
-    std::vector<int64_t> offsets;      // n + 1
-    std::vector<int64_t> full_length;  // untruncated signal length per file
-    std::vector<char> read_ids;        // n x 64, NUL padded
-    std::vector<int32_t> status;       // per file: 0 ok, 1 unreadable, 2 multi-read
+    std::vector<int64_t> offsets;      // rows + 1
+    std::vector<int64_t> full_length;  // untruncated signal length per row
+    std::vector<char> read_ids;        // rows x 64, NUL padded
+    std::vector<int32_t> status;       // per row: 0 ok, 1 unreadable, 2 multi-read (rejected)
+    std::vector<int32_t> row_file;     // per row: index of the file it came from
 };
 
 #pragma GCC visibility push(default)
@@ -556,26 +590,32 @@ int db_fast5_list_root(const char* path, char* names, int64_t capacity, int* cou
     }
 }
 
-int db_fast5_batch_read(const char* const* paths, int n, int threads, int64_t keep, db_fast5_batch** out) {
+// multi = 0: one row per file (a multi-read file is a row with status 2);
+// multi = 1: one row per READ - a multi-read file contributes all its reads, an unreadable file one
+// row with status 1.  Rows are in file order (reads of a file ordered by group name).
+static int batch_read(const char* const* paths, int n, int threads, int64_t keep, int multi, db_fast5_batch** out) {
     if (!paths || n < 0 || !out) return dbn::fail(DBN_EINVAL, "db_fast5_batch_read: bad argument");
     db_fast5_batch* b = new db_fast5_batch();
-    std::vector<std::vector<int16_t>> sigs(n);
-    std::vector<std::string> ids(n);
-    b->status.assign(n, 1);
-    b->full_length.assign(n, 0);
+    std::vector<std::vector<ReadRec>> per_file(n);
+    std::vector<int32_t> file_status(n, 1);
+    std::vector<std::vector<int64_t>> full(n);
     std::atomic<int> next{0};
     auto work = [&]() {
         for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
-            std::vector<int16_t> sig;
-            b->status[i] = read_one(paths[i], &ids[i], &sig);
-            if (b->status[i]) continue;
-            b->full_length[i] = static_cast<int64_t>(sig.size());
-            // keep only what call_batch can ever look at: the first and last `keep` samples
-            if (keep > 0 && static_cast<int64_t>(sig.size()) > 2 * keep) {
-                sigs[i].assign(sig.begin(), sig.begin() + keep);
-                sigs[i].insert(sigs[i].end(), sig.end() - keep, sig.end());
-            } else {
-                sigs[i].swap(sig);
+            bool is_multi = false;
+            file_status[i] = read_all(paths[i], &per_file[i], &is_multi, multi != 0);
+            if (file_status[i] == 0 && is_multi && !multi) file_status[i] = 2;
+            if (file_status[i]) {
+                per_file[i].clear();
+                continue;
+            }
+            for (ReadRec& r : per_file[i]) {
+                full[i].push_back(static_cast<int64_t>(r.signal.size()));
+                // keep only what call_batch can ever look at: the first and last `keep` samples
+                if (keep > 0 && static_cast<int64_t>(r.signal.size()) > 2 * keep) {
+                    r.signal.erase(r.signal.begin() + keep, r.signal.end() - keep);
+                    r.signal.shrink_to_fit();
+                }
             }
         }
     };
@@ -584,16 +624,53 @@ int db_fast5_batch_read(const char* const* paths, int n, int threads, int64_t ke
     for (int t = 1; t < nt; ++t) pool.emplace_back(work);
     work();
     for (std::thread& t : pool) t.join();
-    b->offsets.assign(n + 1, 0);
-    for (int i = 0; i < n; ++i) b->offsets[i + 1] = b->offsets[i] + static_cast<int64_t>(sigs[i].size());
-    b->samples.resize(std::max<int64_t>(b->offsets[n], 1));
-    b->read_ids.assign(static_cast<size_t>(n) * 64, 0);
+    b->offsets.assign(1, 0);
     for (int i = 0; i < n; ++i) {
-        std::memcpy(b->samples.data() + b->offsets[i], sigs[i].data(), sigs[i].size() * 2);
-        std::memcpy(b->read_ids.data() + static_cast<size_t>(i) * 64, ids[i].data(),
-                    std::min<size_t>(ids[i].size(), 63));
+        if (file_status[i]) {   // one placeholder row so that every file is represented
+            b->status.push_back(file_status[i]);
+            b->row_file.push_back(i);
+            b->full_length.push_back(0);
+            b->offsets.push_back(b->offsets.back());
+            continue;
+        }
+        for (size_t k = 0; k < per_file[i].size(); ++k) {
+            b->status.push_back(0);
+            b->row_file.push_back(i);
+            b->full_length.push_back(full[i][k]);
+            b->offsets.push_back(b->offsets.back() + static_cast<int64_t>(per_file[i][k].signal.size()));
+        }
+    }
+    const size_t rows = b->status.size();
+    b->samples.resize(std::max<int64_t>(b->offsets.back(), 1));
+    b->read_ids.assign(rows * 64, 0);
+    size_t row = 0;
+    for (int i = 0; i < n; ++i) {
+        if (file_status[i]) {
+            ++row;
+            continue;
+        }
+        for (const ReadRec& r : per_file[i]) {
+            std::memcpy(b->samples.data() + b->offsets[row], r.signal.data(), r.signal.size() * 2);
+            std::memcpy(b->read_ids.data() + row * 64, r.id.data(), std::min<size_t>(r.id.size(), 63));
+            ++row;
+        }
     }
     *out = b;
+    return 0;
+}
+
+int db_fast5_batch_read(const char* const* paths, int n, int threads, int64_t keep, db_fast5_batch** out) {
+    return batch_read(paths, n, threads, keep, 0, out);
+}
+
+int db_fast5_batch_read_reads(const char* const* paths, int n, int threads, int64_t keep, db_fast5_batch** out) {
+    return batch_read(paths, n, threads, keep, 1, out);
+}
+
+int db_fast5_batch_rows(const db_fast5_batch* b, int64_t* rows, const int32_t** row_file) {
+    if (!b || !rows) return dbn::fail(DBN_EINVAL, "db_fast5_batch_rows: NULL argument");
+    *rows = static_cast<int64_t>(b->status.size());
+    if (row_file) *row_file = b->row_file.data();
     return 0;
 }
 

@@ -74,9 +74,15 @@ inline std::string parse_blob(const void* data, size_t n, Blob* out) {
     for (uint32_t i = 0; i < h.n_tensors; ++i) {
         Entry e;
         std::memcpy(&e, base + sizeof(Header) + i * sizeof(Entry), sizeof e);
-        if (e.ndim > 3 || e.offset + e.count > payload_floats) return "corrupt DBNW tensor entry";
-        size_t prod = 1;
-        for (uint32_t d = 0; d < e.ndim; ++d) prod *= e.dims[d];
+        // (written so that a crafted offset / count / dims cannot wrap around the comparisons)
+        if (e.ndim > 3 || e.offset > payload_floats || e.count > payload_floats - e.offset)
+            return "corrupt DBNW tensor entry";
+        uint64_t prod = 1;
+        for (uint32_t d = 0; d < e.ndim; ++d) {
+            if (e.dims[d] > (1u << 24)) return "DBNW tensor entry: implausible dimension";
+            prod *= e.dims[d];                       // <= 2^72 would overflow: check after every factor
+            if (prod > payload_floats) return "DBNW tensor entry: dims do not match count";
+        }
         if (prod != e.count) return "DBNW tensor entry: dims do not match count";
         BlobTensor t;
         t.data = reinterpret_cast<const float*>(base + table_end) + e.offset;

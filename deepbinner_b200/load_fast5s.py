@@ -36,23 +36,66 @@ class PackedSignals(list):
 
 
 def read_fast5_batch_packed(fast5_files, keep, threads=None):
-    """-> (read_ids, PackedSignals) of the readable files, in input order, plus the list of kept file
-    indices: (read_ids, signals, kept)."""
-    loaded = read_fast5_batch(fast5_files, keep=keep, threads=threads, _packed=True)
-    if not isinstance(loaded, tuple):     # pure-Python reader: plain lists
-        kept = [i for i, (_, sig) in enumerate(loaded) if sig is not None]
-        return [loaded[i][0] for i in kept], [loaded[i][1] for i in kept], kept
-    ids, samples, offsets, status = loaded
-    kept = [i for i in range(len(ids)) if status[i] == 0]
-    views = [samples[offsets[i]:offsets[i + 1]] for i in kept]
-    return [ids[i] for i in kept], PackedSignals(views, samples, offsets, np.asarray(kept, dtype=np.int64)), kept
+    """Every read of every readable file, in input order (a multi-read fast5 contributes all its
+    reads, ordered by group name): -> (read_ids, signals, kept) with `signals` a PackedSignals and
+    `kept[i]` the index of the file read i came from."""
+    lib = _native_lib()
+    files = [str(f) for f in fast5_files]
+    if lib is None:     # pure-Python reader: plain lists
+        ids, sigs, kept = [], [], []
+        for i, f in enumerate(files):
+            for rid, sig in get_reads_python(f):
+                if keep > 0 and len(sig) > 2 * keep:
+                    sig = np.concatenate([sig[:keep], sig[-keep:]])
+                ids.append(rid)
+                sigs.append(sig)
+                kept.append(i)
+        return ids, sigs, kept
+    if not files:
+        return [], PackedSignals([], np.zeros(0, np.int16), np.zeros(1, np.int64), np.zeros(0, np.int64)), []
+    ids, samples, offsets, status, row_file = _native_batch(lib, files, keep, threads, reads=True)
+    ok = [r for r in range(len(ids)) if status[r] == 0]
+    views = [samples[offsets[r]:offsets[r + 1]] for r in ok]
+    return ([ids[r] for r in ok], PackedSignals(views, samples, offsets, np.asarray(ok, dtype=np.int64)),
+            [int(row_file[r]) for r in ok])
 
 
-def read_fast5_batch(fast5_files, keep=0, threads=None, _packed=False):
+def _native_batch(lib, files, keep, threads, reads):
+    """db_fast5_batch_read (one row per file) / db_fast5_batch_read_reads (one row per read) ->
+    (read_ids, samples, offsets, status, row_file) with one entry per row."""
+    n = len(files)
+    arr = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(f) for f in files])
+    handle = ctypes.c_void_p()
+    threads = threads or min(16, os.cpu_count() or 1)
+    entry = lib.db_fast5_batch_read_reads if reads else lib.db_fast5_batch_read
+    if entry(arr, n, int(threads), int(keep), ctypes.byref(handle)) != 0:
+        raise RuntimeError('db_fast5_batch_read failed')
+    try:
+        rows, rf = ctypes.c_int64(), ctypes.c_void_p()
+        lib.db_fast5_batch_rows(handle, ctypes.byref(rows), ctypes.byref(rf))
+        rows = rows.value
+        ptrs = [ctypes.c_void_p() for _ in range(5)]
+        lib.db_fast5_batch_get(handle, *[ctypes.byref(p) for p in ptrs])
+        offsets = np.ctypeslib.as_array(ctypes.cast(ptrs[1], ctypes.POINTER(ctypes.c_int64)), (rows + 1,)).copy()
+        total = int(offsets[-1])
+        samples = np.ctypeslib.as_array(ctypes.cast(ptrs[0], ctypes.POINTER(ctypes.c_int16)),
+                                        (max(total, 1),))[:total].copy()
+        ids = ctypes.string_at(ptrs[3], rows * 64)
+        status = np.ctypeslib.as_array(ctypes.cast(ptrs[4], ctypes.POINTER(ctypes.c_int32)), (max(rows, 1),))[:rows].copy()
+        row_file = np.ctypeslib.as_array(ctypes.cast(rf, ctypes.POINTER(ctypes.c_int32)), (max(rows, 1),))[:rows].copy()
+    finally:
+        lib.db_fast5_batch_free(handle)
+    read_ids = [ids[i * 64:(i + 1) * 64].split(b'\x00')[0].decode() if status[i] == 0 else None
+                for i in range(rows)]
+    return read_ids, samples, offsets, status, row_file
+
+
+def read_fast5_batch(fast5_files, keep=0, threads=None):
     """Parse many single-read fast5 files on native host threads.
     -> list of (read_id, int16 signal) or (None, None) per file, in input order.  If keep > 0 only the
     first and last `keep` samples of longer signals are returned (concatenated) - everything
-    call_batch can ever look at when keep >= scan_size + input_size/2."""
+    call_batch can ever look at when keep >= scan_size + input_size/2.  (A multi-read file exits like
+    the reference's get_read_id_and_signal; read_fast5_batch_packed returns all reads of such files.)"""
     lib = _native_lib()
     files = [str(f) for f in fast5_files]
     if lib is None:
@@ -63,33 +106,14 @@ def read_fast5_batch(fast5_files, keep=0, threads=None, _packed=False):
                 sig = np.concatenate([sig[:keep], sig[-keep:]])
             out.append((rid, sig))
         return out
-    n = len(files)
-    if n == 0:
+    if not files:
         return []
-    arr = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(f) for f in files])
-    handle = ctypes.c_void_p()
-    threads = threads or min(16, os.cpu_count() or 1)
-    if lib.db_fast5_batch_read(arr, n, int(threads), int(keep), ctypes.byref(handle)) != 0:
-        raise RuntimeError('db_fast5_batch_read failed')
-    try:
-        ptrs = [ctypes.c_void_p() for _ in range(5)]
-        lib.db_fast5_batch_get(handle, *[ctypes.byref(p) for p in ptrs])
-        offsets = np.ctypeslib.as_array(ctypes.cast(ptrs[1], ctypes.POINTER(ctypes.c_int64)), (n + 1,)).copy()
-        total = int(offsets[-1])
-        samples = np.ctypeslib.as_array(ctypes.cast(ptrs[0], ctypes.POINTER(ctypes.c_int16)),
-                                        (max(total, 1),))[:total].copy()
-        ids = ctypes.string_at(ptrs[3], n * 64)
-        status = np.ctypeslib.as_array(ctypes.cast(ptrs[4], ctypes.POINTER(ctypes.c_int32)), (max(n, 1),))[:n].copy()
-    finally:
-        lib.db_fast5_batch_free(handle)
+    read_ids, samples, offsets, status, _ = _native_batch(lib, files, keep, threads, reads=False)
     if (status == 2).any():
-        sys.exit('Error: Deepbinner does not (yet) support multi-read fast5 files')
-    read_ids = [ids[i * 64:(i + 1) * 64].split(b'\x00')[0].decode() if status[i] == 0 else None
-                for i in range(n)]
-    if _packed:
-        return read_ids, samples, offsets, status
+        sys.exit('Error: this entry point reads one-read-per-file fast5s; multi-read files go through '
+                 'read_fast5_batch_packed / classify_fast5_files')
     return [(read_ids[i], samples[offsets[i]:offsets[i + 1]]) if status[i] == 0 else (None, None)
-            for i in range(n)]
+            for i in range(len(files))]
 
 
 def get_read_id_and_signal(fast5_file):
@@ -118,6 +142,27 @@ def get_read_id_and_signal_python(fast5_file):
         return str(read_id), signal
     except (OSError, KeyError, IndexError, ValueError):
         return None, None
+
+
+def get_reads_python(fast5_file):
+    """Pure-Python twin of db_fast5_batch_read_reads for one file: [(read_id, signal), ...] - every
+    read of a multi-read file (ordered by group name), one read of a single-read file, [] if unreadable."""
+    try:
+        with hdf5_lite.open_file(fast5_file) as h:
+            keys = h.keys()
+            if 'Raw' in keys:
+                groups = [h['Raw/Reads'].values()[0]]
+            else:
+                groups = [h[k + '/Raw'] for k in sorted(k for k in keys if k.startswith('read_'))]
+            out = []
+            for group in groups:
+                read_id = group.attrs['read_id']
+                if isinstance(read_id, bytes):
+                    read_id = read_id.decode()
+                out.append((str(read_id), group['Signal'].read()))
+            return out
+    except (OSError, KeyError, IndexError, ValueError):
+        return []
 
 
 def find_all_fast5s(directory, verbose=False):

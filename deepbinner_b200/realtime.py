@@ -6,8 +6,15 @@ on the GPU and move them into per-barcode directories.  Behaviour follows refere
 20 000 single-read files per round, files whose destination already exists are ignored from then
 on, `--stop` ends the loop when nothing is waiting, Ctrl-C exits cleanly.
 
-Multi-read fast5 files: the reference shells out to ONT's `multi_to_single_fast5`; here they are
-rejected with the reference's `classify` message (unpacking is outside the accelerated path).
+Multi-read fast5 files.  The reference (`classify_and_move` :93-101, `unpack_multi_read_fast5s`
+:183-196) takes at most 5 such files per round, adds them to `ignore_files` (they stay where they
+are), unpacks them with ONT's `multi_to_single_fast5` into a temporary directory and bins the
+unpacked one-read files.  Here every read is classified straight out of the multi-read file (native
+reader, no unpacking, no ONT tool).  The rule matched: same 5-files-per-round limit, the multi-read
+file is left in place and ignored from then on, and the per-read result - which the reference
+materialises as one-read files under barcodeNN/ - is appended as `read_ID<TAB>barcode_call<TAB>file`
+rows to `<out_dir>/multi_read_classifications.tsv` (the first two columns are what `deepbinner bin`
+consumes).  Writing one-read fast5 files needs an HDF5 writer and is outside this path.
 """
 
 import os
@@ -21,6 +28,8 @@ from .load_fast5s import determine_single_or_multi_fast5s
 from .misc import print_summary_table
 
 MAX_FILES_PER_ROUND = 20000
+MAX_MULTI_FILES_PER_ROUND = 5
+MULTI_TSV = 'multi_read_classifications.tsv'
 POLL_SECONDS = 5
 
 
@@ -46,13 +55,11 @@ def realtime(args, poll_seconds=POLL_SECONDS):
                 if waiting_dots:
                     print('', flush=True)
                     waiting_dots = 0
-                if determine_single_or_multi_fast5s(fast5s) == 'multi':
-                    sys.exit('Error: deepbinner realtime on the B200 engine requires one-read-per-'
-                             'file fast5s - convert with multi_to_single_fast5 before running')
+                single_or_multi = determine_single_or_multi_fast5s(fast5s)
                 print('\nFound {:,} fast5 files'.format(len(fast5s)), flush=True)
                 time.sleep(poll_seconds)   # let files that are still being written settle
                 classify_and_move(fast5s, args, start_model, start_input_size, end_model,
-                                  end_input_size, output_size, out_dir, ignore_files)
+                                  end_input_size, output_size, out_dir, ignore_files, single_or_multi)
                 print('\nLooking for new fast5 files in {}'.format(in_dir), flush=True)
             elif args.stop:
                 break
@@ -84,35 +91,83 @@ def look_for_new_fast5s(in_dir, out_dir, nested_out_dir):
 
 
 def classify_and_move(fast5s, args, start_model, start_input_size, end_model, end_input_size,
-                      output_size, out_dir, ignore_files):
-    if len(fast5s) > MAX_FILES_PER_ROUND:
-        fast5s = fast5s[:MAX_FILES_PER_ROUND]
-        print('Limiting this round to {:,} files'.format(MAX_FILES_PER_ROUND), flush=True)
+                      output_size, out_dir, ignore_files, single_or_multi='single'):
+    limit = MAX_FILES_PER_ROUND if single_or_multi == 'single' else MAX_MULTI_FILES_PER_ROUND
+    if len(fast5s) > limit:       # reference realtime.py:89-94: lots of one-read files, a few multi-read ones
+        fast5s = fast5s[:limit]
+        print('Limiting this round to {:,} files'.format(limit), flush=True)
+    if single_or_multi == 'multi':
+        ignore_files.update(fast5s)     # reference :99: the multi-read files themselves stay where they are
     classifications, read_id_to_fast5_file = \
         classify_fast5_files(fast5s, start_model, start_input_size, end_model, end_input_size,
-                             output_size, args, full_output=False, verified_single_read=True)
+                             output_size, args, full_output=False,
+                             verified_single_read=(single_or_multi == 'single'))
     print('', flush=True)
-    move_classified_fast5s(classifications, read_id_to_fast5_file, out_dir, ignore_files)
+    if single_or_multi == 'multi':
+        record_multi_read_classifications(classifications, read_id_to_fast5_file, out_dir)
+    else:
+        move_classified_fast5s(classifications, read_id_to_fast5_file, out_dir, fast5s, ignore_files)
     print_summary_table(classifications, output=sys.stdout)
 
 
-def move_classified_fast5s(classifications, read_id_to_fast5_file, out_dir, ignore_files):
-    moved = 0
-    total = len(classifications)
+def record_multi_read_classifications(classifications, read_id_to_fast5_file, out_dir):
+    """Per-read result of multi-read input: rows appended to <out_dir>/multi_read_classifications.tsv."""
+    path = pathlib.Path(out_dir) / MULTI_TSV
+    new = not path.exists()
+    with open(str(path), 'at') as f:
+        if new:
+            f.write('read_ID\tbarcode_call\tfast5_file\n')
+        for read_id, call in classifications.items():
+            f.write('{}\t{}\t{}\n'.format(read_id, call, read_id_to_fast5_file[read_id]))
+    print('Recorded {:,} reads of {:,} multi-read fast5 files in {}'.format(
+        len(classifications), len(set(read_id_to_fast5_file.values())), path), flush=True)
+
+
+def move_classified_fast5s(classifications, read_id_to_fast5_file, out_dir, fast5s, ignore_files):
+    """Reference realtime.py:111-143: a file whose destination exists is ignored from then on (and
+    counted), a failed move is counted; the watcher only gives up when EVERY file of the round failed
+    to move for another reason than an existing destination."""
+    move_count, fail_move_already_exists, fail_move_other_reason = 0, 0, 0
     for read_id, barcode_call in classifications.items():
         source = read_id_to_fast5_file[read_id]
         dest_dir = pathlib.Path(out_dir) / get_directory_name(barcode_call)
-        dest_dir.mkdir(parents=True, exist_ok=True)
+        if not dest_dir.is_dir():
+            try:
+                os.makedirs(str(dest_dir))
+            except OSError:
+                sys.exit('Error: unable to create output directory {}'.format(dest_dir))
         dest = dest_dir / pathlib.Path(source).name
-        if dest.exists():
+        if dest.is_file():
+            fail_move_already_exists += 1
             ignore_files.add(source)
-            continue
-        shutil.move(source, str(dest))
-        moved += 1
-        print('\rMoving fast5s: {:,} / {:,}'.format(moved, total), end='', flush=True)
+        else:
+            try:
+                shutil.move(source, str(dest_dir))
+                move_count += 1
+            except OSError:
+                fail_move_other_reason += 1
+        print_moving_progress(move_count, len(fast5s))
     print('', flush=True)
-    if total and not moved:
-        sys.exit('Error: no files could be moved (do they already exist in the output directory?)')
+    print_moving_error_messages(fail_move_already_exists, fail_move_other_reason, out_dir)
+    if fast5s and fail_move_other_reason == len(fast5s):
+        sys.exit('Error: no files were successfully moved to {}'.format(out_dir))
+
+
+def print_moving_progress(completed, total):
+    print('\rMoving fast5s:      {} / {} ({:.1f}%)'.format(completed, total, 100.0 * completed / max(total, 1)),
+          end='', flush=True)
+
+
+def print_moving_error_messages(already_exists, other_reason, out_dir):
+    if already_exists == 1:
+        print('Error: could not move 1 fast5 file because it already exists in {}'.format(out_dir))
+    elif already_exists > 1:
+        print('Error: could not move {} fast5 files because they already exist '
+              'in {}'.format(already_exists, out_dir))
+    if other_reason == 1:
+        print('Error: failed to move 1 fast5 file to {}'.format(out_dir))
+    elif other_reason > 1:
+        print('Error: failed to move {} fast5 files to {}'.format(other_reason, out_dir))
 
 
 def get_directory_name(barcode_call):

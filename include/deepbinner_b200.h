@@ -156,6 +156,14 @@ DBN_API int db_fast5_read(const char *path, char *read_id, int16_t *signal, int6
 DBN_API int db_fast5_list_root(const char *path, char *names, int64_t capacity, int *count);
 DBN_API int db_fast5_batch_read(const char *const *paths, int n, int threads, int64_t keep,
                                 db_fast5_batch **out);
+/* One row per READ instead of one per file: a multi-read fast5 (several /read_<uuid> groups in the
+ * root, load_fast5s.py:67-98) contributes every read, read straight from the file - where the
+ * reference unpacks it with ONT's multi_to_single_fast5 first (realtime.py:183-196).  An unreadable
+ * file is one row with status 1.  db_fast5_batch_rows gives the row count and, per row, the index of
+ * the file it came from; db_fast5_batch_get's arrays are then per row. */
+DBN_API int db_fast5_batch_read_reads(const char *const *paths, int n, int threads, int64_t keep,
+                                      db_fast5_batch **out);
+DBN_API int db_fast5_batch_rows(const db_fast5_batch *batch, int64_t *rows, const int32_t **row_file);
 DBN_API int db_fast5_batch_get(const db_fast5_batch *batch, const int16_t **samples,
                                const int64_t **offsets, const int64_t **full_length,
                                const char **read_ids, const int32_t **status);

@@ -82,13 +82,60 @@ def test_realtime_round_moves_files(tmp_path, monkeypatch, capsys):
     assert rt.get_directory_name('none') == 'unclassified' and rt.get_directory_name('7') == 'barcode07'
 
 
-def test_realtime_existing_destination_is_ignored(tmp_path):
+def test_realtime_existing_destination_is_ignored(tmp_path, capsys):
+    """Reference realtime.py:111-143: a file whose destination exists is reported, put on the ignore
+    list and the watcher carries on; only a round in which EVERY move failed for another reason ends it."""
     out = tmp_path / 'out'
     (out / 'barcode03').mkdir(parents=True)
     (out / 'barcode03' / 'x.fast5').write_bytes(b'old')
     src = tmp_path / 'x.fast5'
     src.write_bytes(b'new')
     ignore = set()
-    with pytest.raises(SystemExit):       # nothing could be moved in this round
-        rt.move_classified_fast5s({'r': '3'}, {'r': str(src)}, out, ignore)
+    rt.move_classified_fast5s({'r': '3'}, {'r': str(src)}, out, [str(src)], ignore)   # no SystemExit
     assert str(src) in ignore and src.exists()
+    assert (out / 'barcode03' / 'x.fast5').read_bytes() == b'old'
+    assert 'could not move 1 fast5 file because it already exists' in capsys.readouterr().out
+    # a move that fails for another reason (source vanished) is counted; all failed -> exit
+    gone = tmp_path / 'gone.fast5'
+    with pytest.raises(SystemExit) as e:
+        rt.move_classified_fast5s({'g': '1'}, {'g': str(gone)}, out, [str(gone)], ignore)
+    assert 'no files were successfully moved' in str(e.value)
+    # one of two fails: reported, no exit
+    ok = tmp_path / 'ok.fast5'
+    ok.write_bytes(b'x')
+    rt.move_classified_fast5s({'g': '1', 'k': 'none'}, {'g': str(gone), 'k': str(ok)}, out,
+                              [str(gone), str(ok)], ignore)
+    assert (out / 'unclassified' / 'ok.fast5').exists()
+    assert 'failed to move 1 fast5 file' in capsys.readouterr().out
+
+
+def test_realtime_multi_read_round_records_reads_and_ignores_the_files(tmp_path, monkeypatch, capsys):
+    """Multi-read input (reference realtime.py:89-101): at most 5 files per round, the files stay in
+    place and are ignored from then on; the per-read calls go to multi_read_classifications.tsv."""
+    in_dir, out_dir = tmp_path / 'in', tmp_path / 'out'
+    in_dir.mkdir()
+    for i in range(7):
+        (in_dir / 'm{}.fast5'.format(i)).write_bytes(b'x')
+    rounds = []
+
+    def fake_classify(fast5s, *a, **k):
+        rounds.append(list(fast5s))
+        assert k['verified_single_read'] is False
+        calls, where = {}, {}
+        for f in fast5s:
+            for r in range(3):
+                rid = '{}_read{}'.format(os.path.basename(f), r)
+                calls[rid] = str(r + 1) if r else 'none'
+                where[rid] = f
+        return calls, where
+
+    monkeypatch.setattr(rt, 'classify_fast5_files', fake_classify)
+    monkeypatch.setattr(rt, 'load_and_check_models', lambda *a, **k: (object(), 1024, None, None, 13, 1))
+    monkeypatch.setattr(rt, 'determine_single_or_multi_fast5s', lambda f: 'multi')
+    args = make_args(in_dir=str(in_dir), out_dir=str(out_dir), start_model='m', end_model=None)
+    rt.realtime(args, poll_seconds=0)
+    assert [len(r) for r in rounds] == [5, 2]                      # 5 files per round, then the rest
+    assert len(list(in_dir.glob('*.fast5'))) == 7                  # nothing is moved
+    rows = (out_dir / rt.MULTI_TSV).read_text().splitlines()
+    assert rows[0] == 'read_ID\tbarcode_call\tfast5_file' and len(rows) == 1 + 7 * 3
+    assert rows[1].split('\t')[:2] == ['m0.fast5_read0', 'none']

@@ -44,6 +44,34 @@ def test_single_and_multi_detection(fast5_dir):
         lf.get_read_id_and_signal(multi[0])
 
 
+def test_multi_read_files_are_read_natively(fast5_dir, multi_reads):
+    """Every read of a multi-read fast5 straight out of the file (native reader and Python twin):
+    ids and signals equal the reference fixture's reads (tests/golden/fixture_reads.npz holds the 30
+    reads of the reference's three multi-read files), ordered by group name; mixed batches keep file
+    order and map every read to its file."""
+    ids, sigs = multi_reads
+    by_id = dict(zip(ids, sigs))
+    multi = sorted(str(p) for p in (fast5_dir / 'multi_read_fast5_files').glob('*.fast5'))
+    assert len(multi) == 1
+    single = singles(fast5_dir)[0]
+    python = lf.get_reads_python(multi[0])
+    assert len(python) == 10 and [r for r, _ in python] == sorted(r for r, _ in python)
+    for keep in (0, 6144 + 512):
+        read_ids, signals, kept = lf.read_fast5_batch_packed([single, multi[0], str(fast5_dir / 'nope.fast5'), multi[0]],
+                                                             keep=keep)
+        assert len(read_ids) == 21 and kept == [0] + [1] * 10 + [3] * 10
+        assert read_ids[1:11] == [r for r, _ in python] == read_ids[11:]
+        assert isinstance(signals, lf.PackedSignals) and len(signals.offsets) == 22 + 1   # + the unreadable file's row
+        for rid, s, (prid, ps) in zip(read_ids[1:11], signals[1:11], python):
+            ref = by_id[rid]
+            assert ps.dtype == np.int16 and np.array_equal(ps, ref)
+            if keep:
+                assert len(s) == min(len(ref), 2 * keep)
+                assert np.array_equal(s[:keep], ref[:keep]) and np.array_equal(s[-keep:], ref[-keep:])
+            else:
+                assert np.array_equal(s, ref)
+
+
 def test_batch_reader_truncation_keeps_the_scan_regions(fast5_dir, fixture_reads):
     ids, sigs, names = fixture_reads
     files = [str(fast5_dir / 'fast5_files' / n) for n in names] + [str(fast5_dir / 'nope.fast5')]

@@ -210,7 +210,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(lib_path)
     header = (ROOT / 'include' / 'deepbinner_b200.h').read_text()
     declared = re.findall(r'DBN_API\s+[\w\s\*]+?\b(db_\w+)\s*\(', header)
-    assert sorted(declared) == sorted(_native.EXPORTED_SYMBOLS) and len(declared) == 24
+    assert sorted(declared) == sorted(_native.EXPORTED_SYMBOLS) and len(declared) == 26
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib.db_abi_version.restype = ctypes.c_int
@@ -221,3 +221,25 @@ def test_product_never_imports_the_oracle():
     for path in (ROOT / 'deepbinner_b200').rglob('*.py'):
         text = path.read_text()
         assert 'import oracle' not in text and 'from oracle' not in text, path
+
+
+def test_crafted_weight_blobs_are_rejected_not_read_out_of_bounds():
+    """parse_blob (csrc/dbn_weights.h) on hostile input, through a host-only entry of the C ABI: an
+    offset / count / dims that would wrap around the bounds checks must give DBN_EFORMAT."""
+    import ctypes
+    import struct
+    from deepbinner_b200 import _native
+    lib = _native.load_library()
+    good = bytearray(open(model_path(MODELS[0]), 'rb').read())
+    out = np.zeros((32, 32), np.int32)
+    assert lib.db_tc_job_table(bytes(good), len(good), 1, _native.as_ptr(out), 32) == 21
+    entry = struct.Struct('<48sI3IQQ')
+    name, ndim, d0, d1, d2, off, count = entry.unpack_from(good, 24)
+    for bad in ((name, ndim, d0, d1, d2, 2 ** 64 - 8, count),              # offset + count wraps to a small value
+                (name, ndim, d0, d1, d2, off, 2 ** 64 - 1),                 # count alone is absurd
+                (name, 3, 2 ** 31, 2 ** 31, 4, off, 0),                     # dims product wraps to 0 == count
+                (name, 3, 2 ** 24 + 1, 1, 1, off, 2 ** 24 + 1)):            # implausible dimension
+        blob = bytearray(good)
+        entry.pack_into(blob, 24, *bad)
+        rc = lib.db_tc_job_table(bytes(blob), len(blob), 1, _native.as_ptr(out), 32)
+        assert rc == -2, (bad[1:], rc, lib.db_last_error())
