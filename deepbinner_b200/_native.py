@@ -69,6 +69,13 @@ def load_library():
         'db_call_batch': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                          ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
                                          ctypes.c_void_p, ctypes.c_void_p]),
+        'db_call_batch_submit': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                ctypes.POINTER(ctypes.c_int)]),
+        'db_call_batch_submit_packed': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
+                                                       ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_double,
+                                                       ctypes.POINTER(ctypes.c_int)]),
+        'db_call_batch_wait': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]),
         'db_call_batch_device': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
@@ -113,6 +120,7 @@ def load_library():
 EXPORTED_SYMBOLS = ['db_abi_version', 'db_last_error', 'db_create', 'db_destroy', 'db_info',
                     'db_set_engine', 'db_get_engine', 'db_predict_windows',
                     'db_predict_windows_f64', 'db_predict_windows_device', 'db_call_batch',
+                    'db_call_batch_submit', 'db_call_batch_submit_packed', 'db_call_batch_wait',
                     'db_call_batch_device', 'db_last_gpu_ms', 'db_kernel_launches',
                     'db_tc_num_jobs', 'db_tc_job_table', 'db_tc_packed', 'db_tc_debug_dump', 'db_tc_trace', 'db_fast5_read',
                     'db_fast5_list_root', 'db_fast5_batch_read', 'db_fast5_batch_read_reads', 'db_fast5_batch_rows',

@@ -152,11 +152,34 @@ struct db_model {
     size_t d_step_bytes = 0;
     int8_t* d_calls = nullptr;
     size_t d_calls_bytes = 0;
-    // pinned host staging for call_batch gathers
-    int16_t* h_samples = nullptr;
-    size_t h_samples_bytes = 0;
-    int64_t* h_offsets = nullptr;
-    size_t h_offsets_bytes = 0;
+    // in-flight call_batch jobs (db_call_batch_submit .. db_call_batch_wait): every slot owns its pinned
+    // staging, device buffers and completion event, so that the host can prepare batch i+1 (or the other
+    // model's side of the same batch) while batch i is on the GPU
+    static constexpr int kJobSlots = 4;
+    struct CallJob {
+        bool busy = false;
+        int n_reads = 0;
+        int16_t* h_samples = nullptr;   // pinned: gathered scan regions of the whole job
+        size_t h_samples_bytes = 0;
+        int64_t* h_offsets = nullptr;   // pinned: per chunk, cnt + 1 offsets relative to the chunk's samples
+        size_t h_offsets_bytes = 0;
+        float* h_probs = nullptr;       // pinned results
+        size_t h_probs_bytes = 0;
+        int8_t* h_calls = nullptr;
+        size_t h_calls_bytes = 0;
+        int16_t* d_samples = nullptr;
+        size_t d_samples_bytes = 0;
+        int64_t* d_offsets = nullptr;
+        size_t d_offsets_bytes = 0;
+        float* d_step = nullptr;
+        size_t d_step_bytes = 0;
+        float* d_probs = nullptr;
+        size_t d_probs_bytes = 0;
+        int8_t* d_calls = nullptr;
+        size_t d_calls_bytes = 0;
+        cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_join = nullptr;
+    } jobs[kJobSlots];
+    int call_chunk = 64;                // reads per pipelined chunk of a job (DEEPBINNER_B200_CALL_CHUNK)
 };
 
 namespace dbn {
@@ -245,6 +268,103 @@ static int check_scan(const db_model* m, int scan_size, int* steps) {
 
 using namespace dbn;
 
+// ---- pipelined host entry of seam b2 -------------------------------------------------------------
+// A job = one call_batch over n_reads host reads.  submit() cuts it into chunks of `call_chunk` reads;
+// for every chunk the host gathers the scan regions (the only samples call_batch ever looks at: the
+// first / last scan_size + input_size/2 of each read, classify.py:337-349) into the job's pinned
+// staging and enqueues H2D copy -> network kernel -> merge/call kernel -> D2H of the results on one of
+// two streams (chunks alternate), so the gather and the copy of chunk i+1 run under the kernels of chunk
+// i.  submit() returns once everything is enqueued - the caller's buffers are no longer referenced - and
+// wait() blocks on the job's completion event and hands the results out.  Up to kJobSlots jobs per
+// handle may be in flight (next batch, or several jobs queued by a driver loop).
+template <typename GetRead>
+static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int scan_size, double score_diff,
+                      int* job_out) {
+    if (!m) return fail(DBN_EINVAL, "call_batch: model is NULL");
+    if (!job_out) return fail(DBN_EINVAL, "call_batch: job is NULL");
+    if (n_reads < 0) return fail(DBN_EINVAL, "call_batch: n_reads < 0");
+    if (side != DBN_SIDE_START && side != DBN_SIDE_END) return fail(DBN_EINVAL, "call_batch: bad side");
+    int steps = 0;
+    int rc = check_scan(m, scan_size, &steps);
+    if (rc) return rc;
+    int slot = -1;
+    for (int i = 0; i < db_model::kJobSlots; ++i)
+        if (!m->jobs[i].busy) {
+            slot = i;
+            break;
+        }
+    if (slot < 0) return fail(DBN_EINVAL, "call_batch: %d jobs already in flight on this handle", db_model::kJobSlots);
+    db_model::CallJob& J = m->jobs[slot];
+    J.n_reads = n_reads;
+    *job_out = slot;
+    if (n_reads == 0) {
+        J.busy = true;
+        return DBN_OK;
+    }
+    DBN_CUDA(cudaSetDevice(m->device));
+    const int64_t region_max = static_cast<int64_t>(scan_size) + m->input_size / 2;
+    const int chunk = m->call_chunk;
+    const int nchunks = (n_reads + chunk - 1) / chunk;
+    const size_t nc = m->n_classes;
+    // sizes: regions are bounded by region_max per read
+    int64_t bound = 0;
+    for (int i = 0; i < n_reads; ++i) {
+        const int16_t* p;
+        int64_t len;
+        get_read(i, &p, &len);
+        if (len < 0) return fail(DBN_EINVAL, "call_batch: negative read length");
+        bound += std::min(len, region_max);
+    }
+    const size_t sample_bytes = sizeof(int16_t) * std::max<int64_t>(bound, 1);
+    const size_t offset_bytes = sizeof(int64_t) * (static_cast<size_t>(n_reads) + nchunks);
+    if ((rc = grow_host(&J.h_samples, &J.h_samples_bytes, sample_bytes))) return rc;
+    if ((rc = grow_host(&J.h_offsets, &J.h_offsets_bytes, offset_bytes))) return rc;
+    if ((rc = grow_host(&J.h_probs, &J.h_probs_bytes, sizeof(float) * nc * n_reads))) return rc;
+    if ((rc = grow_host(&J.h_calls, &J.h_calls_bytes, static_cast<size_t>(n_reads)))) return rc;
+    if ((rc = grow(&J.d_samples, &J.d_samples_bytes, sample_bytes))) return rc;
+    if ((rc = grow(&J.d_offsets, &J.d_offsets_bytes, offset_bytes))) return rc;
+    if ((rc = grow(&J.d_step, &J.d_step_bytes, sizeof(float) * nc * n_reads * steps))) return rc;
+    if ((rc = grow(&J.d_probs, &J.d_probs_bytes, sizeof(float) * nc * n_reads))) return rc;
+    if ((rc = grow(&J.d_calls, &J.d_calls_bytes, static_cast<size_t>(n_reads)))) return rc;
+    DBN_CUDA(cudaEventRecord(J.ev_start, m->streams[0]));
+    DBN_CUDA(cudaStreamWaitEvent(m->streams[1], J.ev_start, 0));
+    int64_t base = 0;   // samples gathered so far
+    for (int c = 0; c < nchunks; ++c) {
+        const int r0 = c * chunk, cnt = std::min(chunk, n_reads - r0);
+        cudaStream_t st = m->streams[c & 1];
+        int64_t* offs = J.h_offsets + r0 + c;   // cnt + 1 entries, relative to this chunk's samples
+        int64_t total = 0;
+        for (int i = 0; i < cnt; ++i) {
+            const int16_t* p;
+            int64_t len;
+            get_read(r0 + i, &p, &len);
+            const int64_t r = std::min(len, region_max);
+            offs[i] = total;
+            if (r > 0) std::memcpy(J.h_samples + base + total, p + (side == DBN_SIDE_START ? 0 : len - r), sizeof(int16_t) * r);
+            total += r;
+        }
+        offs[cnt] = total;
+        if (total > 0)
+            DBN_CUDA(cudaMemcpyAsync(J.d_samples + base, J.h_samples + base, sizeof(int16_t) * total,
+                                     cudaMemcpyHostToDevice, st));
+        DBN_CUDA(cudaMemcpyAsync(J.d_offsets + r0 + c, offs, sizeof(int64_t) * (cnt + 1), cudaMemcpyHostToDevice, st));
+        rc = launch_call_batch(m, J.d_samples + base, J.d_offsets + r0 + c, cnt, side, steps, score_diff,
+                               J.d_step + static_cast<size_t>(r0) * steps * nc, J.d_probs + r0 * nc, J.d_calls + r0, st);
+        if (rc) return rc;
+        DBN_CUDA(cudaMemcpyAsync(J.h_probs + r0 * nc, J.d_probs + r0 * nc, sizeof(float) * nc * cnt,
+                                 cudaMemcpyDeviceToHost, st));
+        DBN_CUDA(cudaMemcpyAsync(J.h_calls + r0, J.d_calls + r0, static_cast<size_t>(cnt), cudaMemcpyDeviceToHost, st));
+        base += total;
+    }
+    // completion: stream 0 joins stream 1, then records the job's stop event
+    DBN_CUDA(cudaEventRecord(J.ev_join, m->streams[1]));
+    DBN_CUDA(cudaStreamWaitEvent(m->streams[0], J.ev_join, 0));
+    DBN_CUDA(cudaEventRecord(J.ev_stop, m->streams[0]));
+    J.busy = true;
+    return DBN_OK;
+}
+
+
 // =================================================================================================
 // C ABI
 // =================================================================================================
@@ -268,8 +388,20 @@ void db_destroy(db_model* m) {
     cudaFree(m->d_offsets);
     cudaFree(m->d_step);
     cudaFree(m->d_calls);
-    if (m->h_samples) cudaFreeHost(m->h_samples);
-    if (m->h_offsets) cudaFreeHost(m->h_offsets);
+    for (db_model::CallJob& j : m->jobs) {
+        if (j.h_samples) cudaFreeHost(j.h_samples);
+        if (j.h_offsets) cudaFreeHost(j.h_offsets);
+        if (j.h_probs) cudaFreeHost(j.h_probs);
+        if (j.h_calls) cudaFreeHost(j.h_calls);
+        cudaFree(j.d_samples);
+        cudaFree(j.d_offsets);
+        cudaFree(j.d_step);
+        cudaFree(j.d_probs);
+        cudaFree(j.d_calls);
+        if (j.ev_start) cudaEventDestroy(j.ev_start);
+        if (j.ev_stop) cudaEventDestroy(j.ev_stop);
+        if (j.ev_join) cudaEventDestroy(j.ev_join);
+    }
     for (int i = 0; i < 2; ++i) {
         if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
         if (m->h_out[i]) cudaFreeHost(m->h_out[i]);
@@ -325,6 +457,12 @@ int db_create(const void* weights_blob, size_t blob_bytes, int device, db_model*
             DBN_CUDA(cudaEventCreateWithFlags(&m->ev_slot[i], cudaEventDisableTiming));
             DBN_CUDA(cudaEventRecord(m->ev_slot[i], m->streams[i]));   // so that a first wait never blocks
         }
+        for (db_model::CallJob& j : m->jobs) {
+            DBN_CUDA(cudaEventCreate(&j.ev_start));
+            DBN_CUDA(cudaEventCreate(&j.ev_stop));
+            DBN_CUDA(cudaEventCreateWithFlags(&j.ev_join, cudaEventDisableTiming));
+        }
+        if (const char* v = getenv("DEEPBINNER_B200_CALL_CHUNK")) m->call_chunk = std::max(1, atoi(v));
         return 0;
     }();
     if (rc) {
@@ -457,66 +595,44 @@ int db_predict_windows_device(db_model* m, const float* d_x, int64_t n, float* d
     return launch_predict(m, d_x, false, n, d_probs, static_cast<cudaStream_t>(stream));
 }
 
+int db_call_batch_submit(db_model* m, const int16_t* const* signals, const int64_t* lengths, int n_reads, int side,
+                         int scan_size, double score_diff, int* job) {
+    if (n_reads > 0 && (!signals || !lengths)) return fail(DBN_EINVAL, "call_batch: NULL buffer");
+    return submit_job(m, [&](int i, const int16_t** p, int64_t* len) { *p = signals[i]; *len = lengths[i]; },
+                      n_reads, side, scan_size, score_diff, job);
+}
+
+int db_call_batch_submit_packed(db_model* m, const int16_t* samples, const int64_t* offsets, int n_reads, int side,
+                                int scan_size, double score_diff, int* job) {
+    if (n_reads > 0 && (!samples || !offsets)) return fail(DBN_EINVAL, "call_batch: NULL buffer");
+    return submit_job(m, [&](int i, const int16_t** p, int64_t* len) { *p = samples + offsets[i]; *len = offsets[i + 1] - offsets[i]; },
+                      n_reads, side, scan_size, score_diff, job);
+}
+
+int db_call_batch_wait(db_model* m, int job, float* probs, int8_t* calls) {
+    if (!m) return fail(DBN_EINVAL, "call_batch: model is NULL");
+    if (job < 0 || job >= db_model::kJobSlots || !m->jobs[job].busy) return fail(DBN_EINVAL, "call_batch: no such job in flight");
+    db_model::CallJob& J = m->jobs[job];
+    J.busy = false;
+    if (J.n_reads == 0) return DBN_OK;
+    if (!probs || !calls) return fail(DBN_EINVAL, "call_batch: NULL buffer");
+    DBN_CUDA(cudaSetDevice(m->device));
+    DBN_CUDA(cudaEventSynchronize(J.ev_stop));
+    std::memcpy(probs, J.h_probs, sizeof(float) * m->n_classes * J.n_reads);
+    std::memcpy(calls, J.h_calls, static_cast<size_t>(J.n_reads));
+    DBN_CUDA(cudaEventElapsedTime(&m->last_ms, J.ev_start, J.ev_stop));
+    return DBN_OK;
+}
+
 int db_call_batch(db_model* m, const int16_t* samples, const int64_t* offsets, int n_reads,
                   int side, int scan_size, double score_diff, float* probs, int8_t* calls) {
-    if (!m) return fail(DBN_EINVAL, "call_batch: model is NULL");
-    if (n_reads < 0) return fail(DBN_EINVAL, "call_batch: n_reads < 0");
-    if (side != DBN_SIDE_START && side != DBN_SIDE_END) return fail(DBN_EINVAL, "call_batch: bad side");
-    int steps = 0;
-    int rc = check_scan(m, scan_size, &steps);
+    if (n_reads > 0 && (!samples || !offsets || !probs || !calls)) return fail(DBN_EINVAL, "call_batch: NULL buffer");
+    for (int i = 0; i < n_reads; ++i)
+        if (offsets[i + 1] < offsets[i]) return fail(DBN_EINVAL, "call_batch: offsets must be non-decreasing");
+    int job = -1;
+    int rc = db_call_batch_submit_packed(m, samples, offsets, n_reads, side, scan_size, score_diff, &job);
     if (rc) return rc;
-    if (n_reads == 0) return DBN_OK;
-    if (!samples || !offsets || !probs || !calls) return fail(DBN_EINVAL, "call_batch: NULL buffer");
-    DBN_CUDA(cudaSetDevice(m->device));
-    // Gather each read's scan region (the only samples call_batch ever looks at: the first / last
-    // scan_size + input_size/2 samples, classify.py:337-349) into pinned staging.
-    const int64_t region_max = static_cast<int64_t>(scan_size) + m->input_size / 2;
-    rc = grow_host(&m->h_offsets, &m->h_offsets_bytes, sizeof(int64_t) * (n_reads + 1));
-    if (rc) return rc;
-    int64_t total = 0;
-    for (int i = 0; i < n_reads; ++i) {
-        const int64_t len = offsets[i + 1] - offsets[i];
-        if (len < 0) return fail(DBN_EINVAL, "call_batch: offsets must be non-decreasing");
-        m->h_offsets[i] = total;
-        total += std::min(len, region_max);
-    }
-    m->h_offsets[n_reads] = total;
-    rc = grow_host(&m->h_samples, &m->h_samples_bytes, sizeof(int16_t) * std::max<int64_t>(total, 1));
-    if (rc) return rc;
-    for (int i = 0; i < n_reads; ++i) {
-        const int64_t len = offsets[i + 1] - offsets[i];
-        const int64_t r = std::min(len, region_max);
-        const int16_t* src = samples + offsets[i] + (side == DBN_SIDE_START ? 0 : len - r);
-        std::memcpy(m->h_samples + m->h_offsets[i], src, sizeof(int16_t) * r);
-    }
-    cudaStream_t st = m->streams[0];
-    const size_t nc = m->n_classes;
-    rc = grow(&m->d_in[0], &m->d_in_bytes[0], sizeof(int16_t) * std::max<int64_t>(total, 1));
-    if (rc) return rc;
-    rc = grow(&m->d_offsets, &m->d_offsets_bytes, sizeof(int64_t) * (n_reads + 1));
-    if (rc) return rc;
-    rc = grow(&m->d_step, &m->d_step_bytes, sizeof(float) * nc * n_reads * steps);
-    if (rc) return rc;
-    rc = grow(&m->d_out[0], &m->d_out_bytes[0], sizeof(float) * nc * n_reads);
-    if (rc) return rc;
-    rc = grow(&m->d_calls, &m->d_calls_bytes, static_cast<size_t>(n_reads));
-    if (rc) return rc;
-    DBN_CUDA(cudaMemcpyAsync(m->d_in[0], m->h_samples, sizeof(int16_t) * total,
-                             cudaMemcpyHostToDevice, st));
-    DBN_CUDA(cudaMemcpyAsync(m->d_offsets, m->h_offsets, sizeof(int64_t) * (n_reads + 1),
-                             cudaMemcpyHostToDevice, st));
-    DBN_CUDA(cudaEventRecord(m->ev_start, st));
-    rc = launch_call_batch(m, static_cast<const int16_t*>(m->d_in[0]), m->d_offsets, n_reads, side,
-                           steps, score_diff, m->d_step, m->d_out[0], m->d_calls, st);
-    if (rc) return rc;
-    DBN_CUDA(cudaEventRecord(m->ev_stop, st));
-    DBN_CUDA(cudaMemcpyAsync(probs, m->d_out[0], sizeof(float) * nc * n_reads,
-                             cudaMemcpyDeviceToHost, st));
-    DBN_CUDA(cudaMemcpyAsync(calls, m->d_calls, static_cast<size_t>(n_reads),
-                             cudaMemcpyDeviceToHost, st));
-    DBN_CUDA(cudaStreamSynchronize(st));
-    DBN_CUDA(cudaEventElapsedTime(&m->last_ms, m->ev_start, m->ev_stop));
-    return DBN_OK;
+    return db_call_batch_wait(m, job, probs, calls);
 }
 
 int db_call_batch_device(db_model* m, const int16_t* d_samples, const int64_t* d_offsets,

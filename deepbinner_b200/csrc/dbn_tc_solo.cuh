@@ -398,6 +398,9 @@ __global__ void __launch_bounds__(kTcThreads, 2)
             mbar_arrive(bar0 + kSBarFullA + 8 * i);
             mbar_arrive(bar0 + kSBarFreeA + 8 * i);
         }
+        // epilogue 0 (conv1d_1's CUDA-core stage) has no MMAs: complete its phase of bar_mma[0] here, so
+        // that entry e & 3 of both rings is in phase e >> 2 for every e
+        mbar_arrive(bar_mma);
         fence_barrier_init();
     }
     if (warp == kMmaWarp) tmem_alloc(sbase + kSBar + kSTmemPtr, kSoloTmemCols);

@@ -100,27 +100,38 @@ class B200Model:
     def call_batch(self, signals, side, scan_size, score_diff):
         """signals: list of 1-D integer arrays.  Returns (calls int8 [n] with 0 = 'none',
         probabilities float32 [n, n_classes] after make_sum_to_one)."""
+        return self.call_batch_async(signals, side, scan_size, score_diff).result()
+
+    def call_batch_async(self, signals, side, scan_size, score_diff):
+        """Submit a call_batch job (db_call_batch_submit: the scan regions are gathered into pinned
+        staging and all GPU work is enqueued) and return a PendingCalls; `.result()` waits and returns
+        what call_batch returns.  `signals` may be freed / reused as soon as this returns.  Up to four
+        jobs per model may be pending."""
+        side_code = _native.SIDE_START if side == 'start' else _native.SIDE_END
+        job = ctypes.c_int(-1)
         rows = None
         if hasattr(signals, 'samples') and hasattr(signals, 'offsets'):
-            # already packed by the native fast5 reader (load_fast5s.PackedSignals): the C ABI takes
-            # whole reads and cuts the scan regions itself; rows of unreadable files are empty reads
+            # already packed by the native fast5 reader (load_fast5s.PackedSignals): whole reads in one
+            # buffer; rows of unreadable files are empty reads
             samples, offsets, rows = signals.samples, signals.offsets, signals.rows
             if samples.size == 0:
                 samples = np.zeros(1, dtype=np.int16)
             n = len(offsets) - 1
+            rc = self._lib.db_call_batch_submit_packed(self._handle, _native.as_ptr(samples), _native.as_ptr(offsets),
+                                                       n, side_code, int(scan_size), float(score_diff),
+                                                       ctypes.byref(job))
+            if len(rows) == n:
+                rows = None
         else:
-            samples, offsets = pack_scan_regions(signals, side, int(scan_size), self.input_size)
             n = len(signals)
-        probs = np.empty((n, self.n_classes), dtype=np.float32)
-        calls = np.empty(n, dtype=np.int8)
-        rc = self._lib.db_call_batch(self._handle, _native.as_ptr(samples), _native.as_ptr(offsets),
-                                     n, _native.SIDE_START if side == 'start' else _native.SIDE_END,
-                                     int(scan_size), float(score_diff), _native.as_ptr(probs),
-                                     _native.as_ptr(calls))
-        _native.check(rc, 'db_call_batch')
-        if rows is not None and len(rows) != n:
-            return calls[rows], probs[rows]
-        return calls, probs
+            arrays = [s if (type(s) is np.ndarray and s.dtype == np.int16 and s.flags.c_contiguous)
+                      else np.ascontiguousarray(s, dtype=np.int16) for s in signals]
+            ptrs = np.fromiter((a.ctypes.data for a in arrays), dtype=np.uint64, count=n)
+            lens = np.fromiter((a.size for a in arrays), dtype=np.int64, count=n)
+            rc = self._lib.db_call_batch_submit(self._handle, _native.as_ptr(ptrs), _native.as_ptr(lens), n,
+                                                side_code, int(scan_size), float(score_diff), ctypes.byref(job))
+        _native.check(rc, 'db_call_batch_submit')
+        return PendingCalls(self, job.value, n, rows)
 
     # -- device-resident entry points (used by bench.py for kernel-only timing) --------------------
     def predict_device(self, d_x_ptr, n, d_probs_ptr, stream_ptr=0):
@@ -145,6 +156,26 @@ class B200Model:
     @property
     def kernel_launches(self):
         return int(self._lib.db_kernel_launches(self._handle))
+
+
+class PendingCalls:
+    """An in-flight call_batch job of a B200Model (db_call_batch_submit .. db_call_batch_wait)."""
+
+    def __init__(self, model, job, n, rows):
+        self._model, self._job, self._n, self._rows = model, job, n, rows
+        self._out = None
+
+    def result(self):
+        if self._out is None:
+            m = self._model
+            probs = np.empty((self._n, m.n_classes), dtype=np.float32)
+            calls = np.empty(self._n, dtype=np.int8)
+            rc = m._lib.db_call_batch_wait(m._handle, self._job, _native.as_ptr(probs), _native.as_ptr(calls))
+            _native.check(rc, 'db_call_batch_wait')
+            if self._rows is not None:
+                calls, probs = calls[self._rows], probs[self._rows]
+            self._out = (calls, probs)
+        return self._out
 
 
 def signals_fit_int16(signals):

@@ -116,6 +116,23 @@ DBN_API int db_call_batch(db_model *model, const int16_t *samples, const int64_t
                   int side, int scan_size, double score_diff, float *probs, int8_t *calls);
 
 /*
+ * The same call split in two, so that the host can overlap its own work with the GPU's (prepare the
+ * next batch, submit the other model's side of this batch, format results): submit() gathers the scan
+ * regions chunk by chunk into pinned staging and enqueues copy -> kernels -> copy-back for every chunk
+ * on two alternating streams; it returns as soon as everything is enqueued and no longer references the
+ * caller's buffers.  wait() blocks until the job is complete and fills probs / calls as db_call_batch
+ * does.  *job receives a small index; up to 4 jobs per handle may be in flight; every submitted job must
+ * be waited for exactly once.  db_call_batch == submit_packed + wait.
+ *   db_call_batch_submit:        read i = signals[i][0 .. lengths[i])   (ragged host arrays)
+ *   db_call_batch_submit_packed: read i = samples[offsets[i] .. offsets[i+1])
+ */
+DBN_API int db_call_batch_submit(db_model *model, const int16_t *const *signals, const int64_t *lengths,
+                                 int n_reads, int side, int scan_size, double score_diff, int *job);
+DBN_API int db_call_batch_submit_packed(db_model *model, const int16_t *samples, const int64_t *offsets,
+                                        int n_reads, int side, int scan_size, double score_diff, int *job);
+DBN_API int db_call_batch_wait(db_model *model, int job, float *probs, int8_t *calls);
+
+/*
  * Device-resident variant: d_samples holds, for read i, its scan region (first/last
  * min(len_i, scan_size + input_size/2) samples) at d_samples[d_offsets[i] .. d_offsets[i+1]).
  * Asynchronous on `stream`.  d_step_probs receives the per-step softmax rows
