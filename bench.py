@@ -200,7 +200,7 @@ def main():
     ap.add_argument('--steps', type=int, default=40)
     ap.add_argument('--warmup', type=int, default=3)
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
-    ap.add_argument('--engine', default=None, choices=[None, 'fp32', 'tcgen05', 'tcgen05-pair'])
+    ap.add_argument('--engine', default=None, choices=[None, 'fp32', 'tcgen05'])
     ap.add_argument('--shard', type=int, default=SHARD)
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')

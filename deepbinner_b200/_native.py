@@ -19,8 +19,8 @@ LIB_PATH = pathlib.Path(os.environ.get('DEEPBINNER_B200_LIB') or _PKG / 'libdeep
 
 DBN_OK = 0
 SIDE_START, SIDE_END = 0, 1
-ENGINE_FP32, ENGINE_TCGEN05, ENGINE_TCGEN05_PAIR = 0, 1, 2
-ENGINE_NAMES = {ENGINE_FP32: 'fp32', ENGINE_TCGEN05: 'tcgen05', ENGINE_TCGEN05_PAIR: 'tcgen05-pair'}
+ENGINE_FP32, ENGINE_TCGEN05 = 0, 1
+ENGINE_NAMES = {ENGINE_FP32: 'fp32', ENGINE_TCGEN05: 'tcgen05'}
 ABI_VERSION = 1
 
 _lib = None

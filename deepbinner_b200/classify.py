@@ -123,21 +123,12 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
     batches = list(chunker(fast5_files, 1 if multi else args.batch_size))
     prefetcher = concurrent.futures.ThreadPoolExecutor(max_workers=1)
     pending = prefetcher.submit(load_batch, batches[0], keep)
-    for index, batch in enumerate(batches):
-        read_ids, signals, kept = pending.result()   # unreadable files are skipped (reference :135-136)
-        if index + 1 < len(batches):
-            pending = prefetcher.submit(load_batch, batches[index + 1], keep)
-        for read_id, file_index in zip(read_ids, kept):
-            read_id_to_fast5_file[read_id] = batch[file_index]
 
-        start_calls = start_probs = end_calls = end_probs = None
-        if use_start:
-            start_calls, start_probs = call_batch(start_input_size, output_size, read_ids, signals,
-                                                  start_model, args, 'start')
-        if use_end:
-            end_calls, end_probs = call_batch(end_input_size, output_size, read_ids, signals,
-                                              end_model, args, 'end')
-
+    def finish(read_ids, start_job, end_job, n_files):
+        """Collect the two sides of a batch, combine, print its TSV rows (reference :150-171)."""
+        nonlocal files_done
+        start_calls, start_probs = start_job() if use_start else (None, None)
+        end_calls, end_probs = end_job() if use_end else (None, None)
         for i, read_id in enumerate(read_ids):
             if use_start and use_end:
                 final_call = combine_calls(start_calls[i], end_calls[i], args)
@@ -157,10 +148,29 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
                     if use_start:
                         row.append(end_calls[i])
             print('\t'.join(row))
-
-        files_done += len(batch)
+        files_done += n_files
         print_classification_progress(files_done if multi else len(classifications), len(fast5_files), 'fast5s',
                                       out_dest=out_dest)
+
+    # Software pipeline over the batches: the GPU jobs of batch i (start and end side, submitted back to
+    # back so that the host gathers the end side while the start side computes) are in flight while the
+    # results of batch i-1 are collected and printed and batch i+1 is parsed.
+    in_flight = None
+    for index, batch in enumerate(batches):
+        read_ids, signals, kept = pending.result()   # unreadable files are skipped (reference :135-136)
+        if index + 1 < len(batches):
+            pending = prefetcher.submit(load_batch, batches[index + 1], keep)
+        for read_id, file_index in zip(read_ids, kept):
+            read_id_to_fast5_file[read_id] = batch[file_index]
+        start_job = submit_call_batch(start_input_size, output_size, read_ids, signals, start_model, args,
+                                      'start') if use_start else None
+        end_job = submit_call_batch(end_input_size, output_size, read_ids, signals, end_model, args,
+                                    'end') if use_end else None
+        if in_flight is not None:
+            finish(*in_flight)
+        in_flight = (read_ids, start_job, end_job, len(batch))
+    if in_flight is not None:
+        finish(*in_flight)
 
     prefetcher.shutdown()
     if full_output:
@@ -292,6 +302,26 @@ def _steps_for(input_size, scan_size):
     return step_size, steps
 
 
+_CALL_NAMES = ['none'] + [str(i) for i in range(1, 128)]
+
+
+def submit_call_batch(input_size, output_size, read_ids, signals, model, args, side):
+    """call_batch in two halves: submits the GPU job of one side of a batch (B200Model.call_batch_async)
+    and returns a function that waits for it and returns what call_batch returns.  A foreign model
+    (seam b1) is evaluated on the spot."""
+    assert side in ('start', 'end')
+    _steps_for(input_size, args.scan_size)
+    if read_ids and isinstance(model, B200Model) and signals_fit_int16(signals):
+        job = model.call_batch_async(signals, side, int(args.scan_size), args.score_diff)
+
+        def collect():
+            calls, probs = job.result()
+            return [_CALL_NAMES[c] for c in calls.tolist()], list(probs.astype(np.float64))
+        return collect
+    out = call_batch(input_size, output_size, read_ids, signals, model, args, side)
+    return lambda: out
+
+
 def call_batch(input_size, output_size, read_ids, signals, model, args, side):
     """-> (barcode_calls: list[str], probabilities: list of per-class sequences), index-aligned
     with read_ids (reference classify.py:325-384)."""
@@ -301,9 +331,7 @@ def call_batch(input_size, output_size, read_ids, signals, model, args, side):
         return [], []
 
     if isinstance(model, B200Model) and signals_fit_int16(signals):
-        calls, probs = model.call_batch(signals, side, int(args.scan_size), args.score_diff)
-        barcode_calls = ['none' if c == 0 else str(int(c)) for c in calls]
-        return barcode_calls, [row for row in probs.astype(np.float64)]
+        return submit_call_batch(input_size, output_size, read_ids, signals, model, args, side)()
 
     # Generic path for any object with .predict (seam b1): host windowing, device/foreign predict.
     merged = None

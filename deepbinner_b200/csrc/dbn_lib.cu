@@ -214,10 +214,9 @@ static int launch_predict(db_model* m, const void* d_x, bool is_f64, int64_t n, 
                           cudaStream_t st) {
     if (n <= 0) return 0;
     if (n > 0x7fffffff) return fail(DBN_EINVAL, "too many windows in one launch");
-    if (m->engine == DBN_ENGINE_TCGEN05 || m->engine == DBN_ENGINE_TCGEN05_PAIR) {
+    if (m->engine == DBN_ENGINE_TCGEN05) {
         int rc = tc_predict(m->tc, is_f64 ? nullptr : static_cast<const float*>(d_x),
-                            is_f64 ? static_cast<const double*>(d_x) : nullptr, n, d_probs, st,
-                            m->engine == DBN_ENGINE_TCGEN05_PAIR);
+                            is_f64 ? static_cast<const double*>(d_x) : nullptr, n, d_probs, st);
         if (rc) return rc;
         m->launches += 1;
         return 0;
@@ -240,9 +239,8 @@ static int launch_call_batch(db_model* m, const int16_t* d_samples, const int64_
     if (n_reads <= 0) return 0;
     const int64_t windows = static_cast<int64_t>(n_reads) * steps;
     if (windows > 0x7fffffff) return fail(DBN_EINVAL, "too many windows in one launch");
-    if (m->engine == DBN_ENGINE_TCGEN05 || m->engine == DBN_ENGINE_TCGEN05_PAIR) {
-        int rc = tc_call_windows(m->tc, d_samples, d_offsets, n_reads, side, steps, d_step, st,
-                                 m->engine == DBN_ENGINE_TCGEN05_PAIR);
+    if (m->engine == DBN_ENGINE_TCGEN05) {
+        int rc = tc_call_windows(m->tc, d_samples, d_offsets, n_reads, side, steps, d_step, st);
         if (rc) return rc;
     } else {
         k_fp32_call_windows<<<static_cast<unsigned>(windows), kThreads, kFp32SmemBytes, st>>>(
@@ -473,11 +471,10 @@ int db_create(const void* weights_blob, size_t blob_bytes, int device, db_model*
     // if it cannot be set up); selected by default when available.
     m->tc = tc_create(m->blob);
     m->tc_available = (m->tc != nullptr);
-    m->engine = tc_solo_available(m->tc) ? DBN_ENGINE_TCGEN05 : m->tc_available ? DBN_ENGINE_TCGEN05_PAIR : DBN_ENGINE_FP32;
-    // DEEPBINNER_B200_ENGINE = fp32 | tcgen05 | tcgen05-pair overrides the default engine of new handles
+    m->engine = m->tc_available ? DBN_ENGINE_TCGEN05 : DBN_ENGINE_FP32;
+    // DEEPBINNER_B200_ENGINE = fp32 | tcgen05 overrides the default engine of new handles
     if (const char* want = getenv("DEEPBINNER_B200_ENGINE")) {
         if (!std::strcmp(want, "fp32")) m->engine = DBN_ENGINE_FP32;
-        else if (!std::strcmp(want, "tcgen05-pair") && m->tc_available) m->engine = DBN_ENGINE_TCGEN05_PAIR;
     }
     *out = m;
     return DBN_OK;
@@ -497,12 +494,7 @@ int db_set_engine(db_model* m, int engine) {
         return DBN_OK;
     }
     if (engine == DBN_ENGINE_TCGEN05) {
-        if (!tc_solo_available(m->tc)) return fail(DBN_EINVAL, "tcgen05 engine is not available in this build");
-        m->engine = engine;
-        return DBN_OK;
-    }
-    if (engine == DBN_ENGINE_TCGEN05_PAIR) {
-        if (!m->tc_available) return fail(DBN_EINVAL, "tcgen05 pair kernel is not available in this build");
+        if (!m->tc_available) return fail(DBN_EINVAL, "tcgen05 engine is not available in this build");
         m->engine = engine;
         return DBN_OK;
     }
@@ -658,9 +650,7 @@ int db_call_batch_device(db_model* m, const int16_t* d_samples, const int64_t* d
                              d_probs, d_calls, static_cast<cudaStream_t>(stream));
 }
 
-int db_tc_num_jobs(const db_model* m) {
-    return (m && m->tc) ? tc_num_jobs(m->tc, m->engine == DBN_ENGINE_TCGEN05_PAIR) : 0;
-}
+int db_tc_num_jobs(const db_model* m) { return (m && m->tc) ? tc_num_jobs(m->tc) : 0; }
 
 int db_tc_job_table(const void* weights_blob, size_t blob_bytes, int which, int32_t* out, int max_jobs) {
     if (!weights_blob || !out) return fail(DBN_EINVAL, "db_tc_job_table: NULL buffer");
@@ -695,7 +685,7 @@ int db_tc_debug_dump(db_model* m, const float* x, int job, unsigned char* out) {
     cudaStream_t st = m->streams[0];
     DBN_CUDA(cudaMemcpyAsync(m->d_in[0], x, 2 * 1024 * sizeof(float), cudaMemcpyHostToDevice, st));
     rc = tc_debug_dump(m->tc, static_cast<const float*>(m->d_in[0]), job,
-                       reinterpret_cast<unsigned char*>(m->d_out[0]), st, m->engine == DBN_ENGINE_TCGEN05_PAIR);
+                       reinterpret_cast<unsigned char*>(m->d_out[0]), st);
     if (rc) return rc;
     DBN_CUDA(cudaMemcpyAsync(out, m->d_out[0], dump, cudaMemcpyDeviceToHost, st));
     DBN_CUDA(cudaStreamSynchronize(st));
@@ -710,8 +700,7 @@ int db_tc_trace(db_model* m, const float* d_x, int n, float* d_probs, int64_t* t
     if (rc) return rc;
     cudaStream_t st = m->streams[0];
     DBN_CUDA(cudaMemsetAsync(m->d_step, 0, bytes, st));
-    rc = tc_trace(m->tc, d_x, n, d_probs, reinterpret_cast<long long*>(m->d_step), st,
-                  m->engine == DBN_ENGINE_TCGEN05_PAIR);
+    rc = tc_trace(m->tc, d_x, n, d_probs, reinterpret_cast<long long*>(m->d_step), st);
     if (rc) return rc;
     DBN_CUDA(cudaMemcpyAsync(trace, m->d_step, bytes, cudaMemcpyDeviceToHost, st));
     DBN_CUDA(cudaStreamSynchronize(st));

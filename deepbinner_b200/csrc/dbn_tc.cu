@@ -1171,12 +1171,6 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
 }
 
-}  // namespace dbn
-
-#include "dbn_tc_solo.cuh"
-
-namespace dbn {
-
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -1187,13 +1181,6 @@ struct TcEngine {
     TcParams params{};
     int njobs = 0;
     std::vector<TcJob> jobs;   // uploaded to constant memory (identical for every model of this topology)
-    // solo kernel (one window per CTA, two CTAs per SM; dbn_tc_solo.cuh): own job table / weight packing
-    bool solo_ok = false;
-    unsigned char* d_sw = nullptr;
-    TcJob* d_sjobs = nullptr;
-    float* d_sprm = nullptr;
-    SoloParams sparams{};
-    std::vector<TcJob> sjobs;
 };
 
 static uint16_t bf16_rn(float f) {
@@ -1216,7 +1203,6 @@ struct JobBuilder {
     std::vector<unsigned char> w;
     std::vector<float> prm;        // smem-resident block: per job bias[n] (+ scale[48] shift[48])
     std::vector<float> bn_scale[8], bn_shift[8];
-    bool kb_major = false;         // solo kernel: weights packed K block by K block ([hi | lo] each)
 
     explicit JobBuilder(const Blob& b) : blob(b) {
         for (int i = 1; i <= 7; ++i) fold_bn(blob, i, &bn_scale[i], &bn_shift[i]);
@@ -1241,9 +1227,8 @@ struct JobBuilder {
         while (w.size() % 128) w.push_back(0);
         J->w_goff = static_cast<int>(w.size());
         const int range[3] = {0, split, nkb};
-        // kb_major: nkb parts of one K block each; w_part = {bytes per K block, number of K blocks}
-        for (int part = 0; part < (kb_major ? nkb : 2); ++part) {
-            const int kb0 = kb_major ? part : range[part], kb1 = kb_major ? part + 1 : range[part + 1], cnt = kb1 - kb0;
+        for (int part = 0; part < 2; ++part) {
+            const int kb0 = range[part], kb1 = range[part + 1], cnt = kb1 - kb0;
             std::vector<uint16_t> buf(2 * cnt * blk, 0);
             for (int kb = kb0; kb < kb1; ++kb) {
                 const int t = kb / ncb, cb = kb % ncb;
@@ -1262,13 +1247,9 @@ struct JobBuilder {
                             buf[cnt * blk + idx] = lo;
                         }
             }
-            if (!kb_major) J->w_part[part] = static_cast<int>(buf.size() * 2);
+            J->w_part[part] = static_cast<int>(buf.size() * 2);
             const unsigned char* p = reinterpret_cast<const unsigned char*>(buf.data());
             w.insert(w.end(), p, p + buf.size() * 2);
-        }
-        if (kb_major) {
-            J->w_part[0] = static_cast<int>(2 * blk * 2);
-            J->w_part[1] = nkb;
         }
     }
 
@@ -1333,19 +1314,16 @@ struct JobBuilder {
     // Mark the jobs from index `j0` on as the joint phase: accumulator slots rotate over three 64-column
     // slots (K-slices of one conv share a slot) and `need` is derived from the data flow: `producer[j]`
     // = job whose epilogue writes this job's input (-1: available before the joint phase).
-    // `eseq0`: index of the first joint epilogue in the hand-off sequence, `need0`: epilogues that every
-    // joint job waits for at least (both 0 for the pair kernel, whose joint phase has its own rings).
-    void finish_joint(int j0, const std::vector<int>& producer, int slot_cols = kTmemTileCols, int eseq0 = 0,
-                      int need0 = 0) {
+    void finish_joint(int j0, const std::vector<int>& producer, int slot_cols = kTmemTileCols) {
         std::vector<int> eseq_of(jobs.size(), -1), slot_of(jobs.size(), 0);
-        int e = eseq0, slot = -1;
+        int e = 0, slot = -1;
         std::vector<int> last_user(3, -1);   // job with the epilogue that last drained the slot
         for (size_t j = j0; j < jobs.size(); ++j) {
             TcJob& J = jobs[j];
             if (J.first) slot = (slot + 1) % 3;
             slot_of[j] = slot;
             J.tcol = slot * slot_cols;
-            int need = need0;
+            int need = 0;
             const int prod = producer[j - j0];
             if (prod >= 0) need = std::max(need, eseq_of[prod] + 1);
             if (J.first && last_user[slot] >= 0) need = std::max(need, eseq_of[last_user[slot]] + 1);
@@ -1441,91 +1419,6 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     return true;
 }
 
-// Job table of the solo kernel (dbn_tc_solo.cuh): the same layers for ONE window.  Hand-off sequence:
-// epilogue 0 = conv1d_1's CUDA-core stage, epilogue k = conv1d_(k+1) for the chain conv1d_2 .. conv1d_9
-// (accumulator columns 0.., whole layer in TMEM), then the inception / tail jobs rotating over three
-// 64-column slots like the pair kernel's joint phase.
-static bool build_solo_jobs(const Blob& blob, JobBuilder* B, SoloParams* P) {
-    if (blob.n_classes > 16) return false;
-    B->kb_major = true;
-    B->add(2, 512, 0, 514, 49344, EPI_N48, 0, 0, 0);
-    B->add(3, 512, 0, 514, 49344, EPI_N48, 0, 0, 0);
-    B->add(4, 512, 0, 514, 49344, EPI_N48_POOL_BN, 2, 0, 0);      // -> [6][258][8], lo +24768
-    P->ring_b_job = static_cast<int>(B->jobs.size());
-    P->ring_a_blocks = 27;
-    B->add(5, 256, 0, 258, 24768, EPI_N16, 0, 0, 0);              // -> [2][258][8], lo +8256
-    B->add(6, 256, 0, 258, 8256, EPI_N48, 0, 0, 0);               // -> [6][258][8]
-    B->add(7, 256, 0, 258, 24768, EPI_N48_POOL_BN, 3, 0, 0);      // -> [6][130][8], lo +12480
-    B->add(8, 128, 0, 130, 12480, EPI_N48, 0, 0, 0);
-    B->add(9, 128, 0, 130, 12480, EPI_N48_POOL_BN, 4, 0, 0);      // X [6][66][8], lo +6336
-    const int j0 = static_cast<int>(B->jobs.size());
-    for (int j = 0; j < j0; ++j) {   // chain: job j waits for epilogues 0 .. j, its own is j + 1
-        B->jobs[j].need = j + 1;
-        B->jobs[j].eseq = j + 1;
-        B->jobs[j].tcol = 0;
-    }
-    std::vector<int> producer;
-    auto joint = [&](TcJob& J, int kind, int prod) {
-        J.joint = kind;
-        J.idesc = 64;
-        J.ntiles = 1;
-        producer.push_back(prod);
-    };
-    // inception block (M=64 accumulators, one window): X @0, T15 @12672, T1214 @25344, Y @kSYOff
-    joint(B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 25344, 0, 14), JOINT_PAIR, -1);              // j0
-    joint(B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6), JOINT_PAIR, -1);                   // j0+1
-    B->jobs.back().zero_y = 1;
-    joint(B->add(15, 64, 25344 + 2 * 66 * 16, 66, 4224, EPI_N48, 0, 12672, 0), JOINT_PAIR, j0);   // j0+2
-    joint(B->add(13, 64, 25344, 66, 4224, EPI_PARITY, 5, 0, 12), JOINT_PAIR, j0);              // j0+3
-    joint(B->add(10, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 0, 0, true), JOINT_PAIR, -1);          // j0+4
-    joint(B->add(16, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 18), JOINT_PAIR, j0 + 2);          // j0+5
-    // conv1d_17 (stride 2 on the parity-split Y: taps Ye[i], Yo[i], Ye[i+1]) as four K slices
-    for (int s = 0; s < 4; ++s) {
-        TcJob J{};
-        J.n = 48; J.idesc = 64; J.ntiles = 1; J.L = 16; J.lp = kSYRows; J.ntaps = 3;
-        J.tap16[0] = kSYOff; J.tap16[1] = kSYOff + 2 * kSYArray; J.tap16[2] = kSYOff + 16;
-        J.lo16 = kSYArray; J.ncb = 3; J.cb0 = 3 * s;
-        J.first = (s == 0); J.last = (s == 3);
-        J.joint = JOINT_STACK;
-        J.kind = EPI_N48_BN;
-        J.out_L = 16; J.out_off = 0; J.out_lp = 18; J.out_ncg = 6; J.out_lo_delta = 6 * 18 * 16;
-        J.out_cg_base = 0;
-        B->pack_weights(17, 48, 3 * s, 3, &J);
-        if (J.last) B->pack_params(17, 48, 6, 0, &J);
-        B->jobs.push_back(J);
-        producer.push_back(s == 0 ? j0 + 5 : -1);
-    }
-    joint(B->add(18, 16, 0, 18, 1728, EPI_N48, 0, 0, 0), JOINT_STACK, j0 + 9);
-    joint(B->add(19, 16, 0, 18, 1728, EPI_N48_POOL_BN, 7, 0, 0), JOINT_STACK, j0 + 10);   // -> [6][10][8], lo +960
-    joint(B->add(20, 8, 0, 10, 960, EPI_HEAD, 0, 0, 0), JOINT_STACK, j0 + 11);
-    B->jobs.back().idesc = 128;   // the head epilogue reads its 8 rows from TMEM lane quadrant 0
-    B->finish_joint(j0, producer, kTmemTileCols, j0 + 1, j0 + 1);
-    B->finalize_jobs();
-    if (B->jobs.size() > static_cast<size_t>(kMaxJobs)) return false;
-    for (const TcJob& J : B->jobs)
-        if (J.w_part[0] > kSSlotBytes) return false;
-    auto push = [&](const float* p, size_t n) {
-        while (B->prm.size() % 4) B->prm.push_back(0.f);
-        const int off = static_cast<int>(B->prm.size());
-        B->prm.insert(B->prm.end(), p, p + n);
-        return off;
-    };
-    P->conv1_w = push(blob.find("conv1d_1/kernel")->data, 144);
-    P->conv1_b = push(blob.find("conv1d_1/bias")->data, 48);
-    P->bn1_s = push(B->bn_scale[1].data(), 48);
-    P->bn1_h = push(B->bn_shift[1].data(), 48);
-    while (B->prm.size() % 4) B->prm.push_back(0.f);
-    P->n_classes = blob.n_classes;
-    P->njobs = static_cast<int>(B->jobs.size());
-    return true;
-}
-
-template <typename K>
-static bool solo_func_attributes(K kernel) {
-    return cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSoloSmemBytes) == cudaSuccess &&
-           cudaFuncSetAttribute(kernel, cudaFuncAttributePreferredSharedMemoryCarveout, 100) == cudaSuccess;
-}
-
 TcEngine* tc_create(const Blob& blob) {
     if (getenv("DBN_DISABLE_TC")) return nullptr;
     JobBuilder B(blob);
@@ -1556,33 +1449,6 @@ TcEngine* tc_create(const Blob& blob) {
     P.dbg_out = nullptr;
     P.trace = nullptr;
     e->params = P;
-    // solo kernel: own packing of the same weights
-    JobBuilder S(blob);
-    SoloParams SP{};
-    if (build_solo_jobs(blob, &S, &SP)) {
-        e->sjobs = S.jobs;
-        const bool sok =
-            cudaMalloc(&e->d_sw, S.w.size()) == cudaSuccess &&
-            cudaMalloc(&e->d_sprm, S.prm.size() * sizeof(float)) == cudaSuccess &&
-            cudaMalloc(&e->d_sjobs, S.jobs.size() * sizeof(TcJob)) == cudaSuccess &&
-            cudaMemcpy(e->d_sw, S.w.data(), S.w.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
-            cudaMemcpy(e->d_sprm, S.prm.data(), S.prm.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
-            cudaMemcpy(e->d_sjobs, S.jobs.data(), S.jobs.size() * sizeof(TcJob), cudaMemcpyHostToDevice) == cudaSuccess &&
-            solo_func_attributes(k_tc_solo<false, false>) && solo_func_attributes(k_tc_solo<true, false>) &&
-            solo_func_attributes(k_tc_solo<false, true>);
-        if (sok) {
-            SP.jobs = e->d_sjobs;
-            SP.w = e->d_sw;
-            SP.prm = e->d_sprm;
-            SP.trace = nullptr;
-            SP.dbg_job = -1;
-            SP.dbg_out = nullptr;
-            e->sparams = SP;
-            e->solo_ok = true;
-        } else {
-            cudaGetLastError();
-        }
-    }
     return e;
 }
 
@@ -1591,9 +1457,6 @@ void tc_destroy(TcEngine* e) {
     cudaFree(e->d_w);
     cudaFree(e->d_jobs);
     cudaFree(e->d_prm);
-    cudaFree(e->d_sw);
-    cudaFree(e->d_sjobs);
-    cudaFree(e->d_sprm);
     delete e;
 }
 
@@ -1603,23 +1466,20 @@ void tc_destroy(TcEngine* e) {
 // threads).  If a model with a different table shows up, the device is drained before the table is
 // replaced (kernels of the previous model may still be reading it).
 static std::mutex g_table_mutex;
-static std::map<std::pair<int, int>, std::vector<TcJob>> g_uploaded;   // (device, kernel) -> table
-static int sync_table(const std::vector<TcJob>& jobs, int kernel) {
+static std::map<int, std::vector<TcJob>> g_uploaded;   // device -> table
+static int sync_table(const std::vector<TcJob>& jobs) {
     int dev = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return fail(DBN_ECUDA, "cudaGetDevice failed");
     const size_t bytes = jobs.size() * sizeof(TcJob);
     std::lock_guard<std::mutex> lock(g_table_mutex);
-    std::vector<TcJob>& have = g_uploaded[std::make_pair(dev, kernel)];
+    std::vector<TcJob>& have = g_uploaded[dev];
     if (have.size() == jobs.size() && std::memcmp(have.data(), jobs.data(), bytes) == 0) return 0;
     if (cudaDeviceSynchronize() != cudaSuccess ||
-        (kernel == 0 ? cudaMemcpyToSymbol(c_jobs, jobs.data(), bytes) : cudaMemcpyToSymbol(c_sjobs, jobs.data(), bytes)) !=
-            cudaSuccess)
+        cudaMemcpyToSymbol(c_jobs, jobs.data(), bytes) != cudaSuccess)
         return fail(DBN_ECUDA, "uploading the tcgen05 job table failed");
     have = jobs;
     return 0;
 }
-
-bool tc_solo_available(const TcEngine* e) { return e && e->solo_ok; }
 
 static int launch_check(const char* what) {
     cudaError_t err = cudaGetLastError();
@@ -1628,52 +1488,32 @@ static int launch_check(const char* what) {
 }
 
 int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, float* d_probs,
-               cudaStream_t st, bool pair) {
-    if (!pair) {
-        if (!e->solo_ok) return fail(DBN_EINVAL, "solo tcgen05 kernel is not available");
-        if (int rc = sync_table(e->sjobs, 1)) return rc;
-        k_tc_solo<false, false><<<static_cast<unsigned>(n), kTcThreads, kSoloSmemBytes, st>>>(
-            e->sparams, d_x, d_xd, nullptr, nullptr, 0, 0, static_cast<int>(n), d_probs);
-        return launch_check("tcgen05 kernel");
-    }
-    if (int rc = sync_table(e->jobs, 0)) return rc;
+               cudaStream_t st) {
+    if (int rc = sync_table(e->jobs)) return rc;
     const int grid = static_cast<int>((n + 1) / 2);
     k_tc_forward<false, false><<<grid, kTcThreads, kTcSmemBytes, st>>>(e->params, d_x, d_xd, nullptr, nullptr,
                                                                0, 0, static_cast<int>(n), d_probs);
-    return launch_check("tcgen05 pair kernel");
+    return launch_check("tcgen05 kernel");
 }
 
 int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offsets, int n_reads,
-                    int side, int steps, float* d_step_probs, cudaStream_t st, bool pair) {
+                    int side, int steps, float* d_step_probs, cudaStream_t st) {
     const int n = n_reads * steps;
-    if (!pair) {
-        if (!e->solo_ok) return fail(DBN_EINVAL, "solo tcgen05 kernel is not available");
-        if (int rc = sync_table(e->sjobs, 1)) return rc;
-        k_tc_solo<true, false><<<static_cast<unsigned>(n), kTcThreads, kSoloSmemBytes, st>>>(
-            e->sparams, nullptr, nullptr, d_samples, d_offsets, n_reads, side, n, d_step_probs);
-        return launch_check("tcgen05 kernel");
-    }
-    if (int rc = sync_table(e->jobs, 0)) return rc;
+    if (int rc = sync_table(e->jobs)) return rc;
     k_tc_forward<true, false><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(e->params, nullptr, nullptr, d_samples,
                                                                       d_offsets, n_reads, side, n,
                                                                       d_step_probs);
-    return launch_check("tcgen05 pair kernel");
+    return launch_check("tcgen05 kernel");
 }
 
-int tc_num_jobs(const TcEngine* e, bool pair) { return e ? static_cast<int>(pair ? e->jobs.size() : e->sjobs.size()) : 0; }
+int tc_num_jobs(const TcEngine* e) { return e ? static_cast<int>(e->jobs.size()) : 0; }
 
 // Host only (no CUDA call): the MMA job table the engine would use for this model, 32 ints per job in
-// the order of struct TcJob.  which = 0: pair kernel (two windows per CTA), 1: solo kernel.
+// the order of struct TcJob (`which` must be 0: there is one kernel).
 static bool build_table(const Blob& blob, int which, JobBuilder* B) {
-    if (which == 0) {
-        TcParams P{};
-        return build_jobs(blob, B, &P);
-    }
-    if (which == 1) {
-        SoloParams P{};
-        return build_solo_jobs(blob, B, &P);
-    }
-    return false;
+    if (which != 0) return false;
+    TcParams P{};
+    return build_jobs(blob, B, &P);
 }
 
 int tc_job_table(const Blob& blob, int which, int32_t* out, int max_jobs) {
@@ -1697,19 +1537,10 @@ int tc_packed(const Blob& blob, int which, unsigned char* w_out, int64_t w_cap, 
     return 0;
 }
 
-// Diagnostics: run `n` windows with CTA 0 recording clock64 stamps.  Pair kernel: [job][window][16];
-// solo kernel: [job][16] ([0] MMA issue start, [1] issue end, [2] accumulators ready, [3] epilogue end,
-// [11] issuer reached the job) and row 31: [0] epilogue warps start, [1] conv1d_1 done.
-int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st, bool pair) {
-    if (!pair) {
-        if (!e->solo_ok) return fail(DBN_EINVAL, "solo tcgen05 kernel is not available");
-        if (int rc = sync_table(e->sjobs, 1)) return rc;
-        SoloParams P = e->sparams;
-        P.trace = d_trace;
-        k_tc_solo<false, true><<<n, kTcThreads, kSoloSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0, n, d_probs);
-        return launch_check("tcgen05 trace");
-    }
-    if (int rc = sync_table(e->jobs, 0)) return rc;
+// Diagnostics: run `n` windows with CTA 0 recording clock64 stamps per (job, window):
+// [0] MMA issue start, [1] MMA issue end, [2] epilogue start (accumulators ready), [3] epilogue end.
+int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st) {
+    if (int rc = sync_table(e->jobs)) return rc;
     TcParams P = e->params;
     P.trace = d_trace;
     k_tc_forward<false, true><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0,
@@ -1717,19 +1548,9 @@ int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_
     return launch_check("tcgen05 trace");
 }
 
-// Debug: pair kernel - run windows d_x[0..1] up to and including job `job`, dump both ACT regions
-// (2 x 98688 B); solo kernel - window d_x[0], one region.
-int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, cudaStream_t st, bool pair) {
-    if (!pair) {
-        if (!e->solo_ok) return fail(DBN_EINVAL, "solo tcgen05 kernel is not available");
-        if (int rc = sync_table(e->sjobs, 1)) return rc;
-        SoloParams P = e->sparams;
-        P.dbg_job = job;
-        P.dbg_out = d_out;
-        k_tc_solo<false, true><<<1, kTcThreads, kSoloSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0, 1, nullptr);
-        return launch_check("tcgen05 debug");
-    }
-    if (int rc = sync_table(e->jobs, 0)) return rc;
+// Debug: run windows d_x[0..1] up to and including job `job`, dump both ACT regions (2*98688 B).
+int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, cudaStream_t st) {
+    if (int rc = sync_table(e->jobs)) return rc;
     TcParams P = e->params;
     P.dbg_job = job;
     P.dbg_out = d_out;

@@ -208,9 +208,8 @@ def pack_scan_regions(signals, side, scan_size, input_size):
 
 
 def tc_debug_dump(model, x2, job):
-    """Diagnostics for tests: run two windows (pair kernel; the default solo kernel: the first one)
-    through tcgen05 jobs 0..job and return the raw bytes of the shared-memory activation region(s)
-    (uint8 [2, 98688]; the second row stays zero for the solo kernel)."""
+    """Diagnostics for tests: run two windows through tcgen05 jobs 0..job and return the raw bytes of
+    both shared-memory activation regions (uint8 [2, 98688])."""
     x2 = _native.require(np.asarray(x2).reshape(2, model.input_size), np.float32)
     out = np.zeros((2, 98688), dtype=np.uint8)
     rc = model._lib.db_tc_debug_dump(model._handle, _native.as_ptr(x2), int(job), _native.as_ptr(out))

@@ -45,10 +45,7 @@ extern "C" {
 
 /* Engines (db_set_engine).  Both are hand-written sm_100a CUDA; results agree to ~1e-4. */
 #define DBN_ENGINE_FP32 0    /* CUDA-core fp32 fused per-window kernel (parity anchor) */
-#define DBN_ENGINE_TCGEN05 1 /* tcgen05/TMEM split-bf16 tensor-core kernel, one window per CTA and two CTAs
-                              * per SM (default) */
-#define DBN_ENGINE_TCGEN05_PAIR 2 /* the same arithmetic with two windows per CTA and one CTA per SM
-                                   * (round-1 kernel, kept for A/B measurements) */
+#define DBN_ENGINE_TCGEN05 1 /* tcgen05/TMEM split-bf16 tensor-core kernel (default) */
 
 typedef struct db_model db_model;
 
@@ -192,8 +189,7 @@ DBN_API void db_fast5_batch_free(db_fast5_batch *batch);
  * csrc/dbn_tc.cu) after running host windows x[0..1] through jobs 0..job.
  */
 DBN_API int db_tc_num_jobs(const db_model *model);
-/* Host only, no GPU needed: the MMA job table built for a weight blob (which = 0: tcgen05 engine,
- * 1: tail kernel of the split engine), 32 int32 per job in the field order of struct TcJob
+/* Host only, no GPU needed: the MMA job table built for a weight blob (which = 0), 32 int32 per job in the field order of struct TcJob
  * (csrc/dbn_tc.cu).  Returns the number of jobs or a negative DBN_E* code.  Used by the CPU tests that
  * check the schedule (accumulator-slot reuse, hand-off counts, buffer sizes). */
 DBN_API int db_tc_job_table(const void *weights_blob, size_t blob_bytes, int which, int32_t *out,

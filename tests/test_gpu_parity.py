@@ -21,9 +21,8 @@ def engines(model):
     tensor-core head does not handle) - never a silent fp32-only run."""
     names = ['fp32']
     if model.n_classes <= 16:
-        for name in ('tcgen05-pair', 'tcgen05'):
-            model.set_engine(name)     # raises NativeError if unavailable
-            names.append(name)
+        model.set_engine('tcgen05')     # raises NativeError if unavailable
+        names.append('tcgen05')
     return names
 
 

@@ -74,50 +74,20 @@ JOBS = [
 ]
 
 
-def decode_parity_solo(act, cg0, ncg):
-    """Solo kernel: parity-split concat buffer of the one window, 4 arrays [24][18][8] at 33 792; rows
-    16/17 must be zero."""
-    arr_bytes = 24 * 18 * 16
-    off = 33792
-    def arr(o):
-        return bf16_to_f32(act[o:o + arr_bytes].view(np.uint16).reshape(24, 18, 8))
-    ye = arr(off) + arr(off + arr_bytes)
-    yo = arr(off + 2 * arr_bytes) + arr(off + 3 * arr_bytes)
-    y = np.zeros((32, ncg * 8), np.float32)
-    y[0::2] = ye[cg0:cg0 + ncg, 0:16].transpose(1, 0, 2).reshape(16, ncg * 8)
-    y[1::2] = yo[cg0:cg0 + ncg, 0:16].transpose(1, 0, 2).reshape(16, ncg * 8)
-    return y, ye[:, 16:18, :], None
-
-
-# the solo kernel (one window per CTA): same job order, single-window layouts from the inception block on
-SOLO_JOBS = JOBS[:9] + [
-    (9, 'bn5:48', lambda d, w: decode_parity_solo(d[0], 6, 6)),
-    (10, 'conv15', lambda d, w: decode(d[0], 12672, 6, 66, 64, 6336)),
-    (11, 'bn5:96', lambda d, w: decode_parity_solo(d[0], 12, 6)),
-    (12, 'bn5:0', lambda d, w: decode_parity_solo(d[0], 0, 6)),
-    (13, 'bn5:144', lambda d, w: decode_parity_solo(d[0], 18, 6)),
-    (17, 'bn6', lambda d, w: decode(d[0], 0, 6, 18, 16, 1728)),
-    (18, 'conv18', lambda d, w: decode(d[0], 0, 6, 18, 16, 1728)),
-    (19, 'bn7', lambda d, w: decode(d[0], 0, 6, 10, 8, 960)),
-]
-
-
-@pytest.mark.parametrize('engine', ['tcgen05-pair', 'tcgen05'])
-def test_every_job_against_oracle(fixture_reads, engine):
+def test_every_job_against_oracle(fixture_reads, engine='tcgen05'):
     from deepbinner_b200.model import B200Model, tc_debug_dump, tc_num_jobs
     _, sigs, _ = fixture_reads
     name = 'EXP-NBD103_read_starts'
     model = B200Model(model_path(name))
     model.set_engine(engine)      # a tensor-core engine that cannot be selected on a B200 is a failure
     assert tc_num_jobs(model) == 21
-    solo = engine == 'tcgen05'
     x = orc.make_windows(sigs[2:4], 1024, 1, 'start').astype(np.float32)
     taps = {}
     orc.forward(orc.load_weights(model_path(name)), x, taps=taps)
     failures = []
-    for job, tap, dec in (SOLO_JOBS if solo else JOBS):
+    for job, tap, dec in JOBS:
         dump = tc_debug_dump(model, x, job)
-        for w in range(1 if solo else 2):
+        for w in range(2):
             got, halo_a, halo_b = dec(dump, w)
             if tap.startswith('bn5:'):
                 c0 = int(tap.split(':')[1])

@@ -232,7 +232,7 @@ def test_crafted_weight_blobs_are_rejected_not_read_out_of_bounds():
     lib = _native.load_library()
     good = bytearray(open(model_path(MODELS[0]), 'rb').read())
     out = np.zeros((32, 32), np.int32)
-    assert lib.db_tc_job_table(bytes(good), len(good), 1, _native.as_ptr(out), 32) == 21
+    assert lib.db_tc_job_table(bytes(good), len(good), 0, _native.as_ptr(out), 32) == 21
     entry = struct.Struct('<48sI3IQQ')
     name, ndim, d0, d1, d2, off, count = entry.unpack_from(good, 24)
     for bad in ((name, ndim, d0, d1, d2, 2 ** 64 - 8, count),              # offset + count wraps to a small value
@@ -241,5 +241,5 @@ def test_crafted_weight_blobs_are_rejected_not_read_out_of_bounds():
                 (name, 3, 2 ** 24 + 1, 1, 1, off, 2 ** 24 + 1)):            # implausible dimension
         blob = bytearray(good)
         entry.pack_into(blob, 24, *bad)
-        rc = lib.db_tc_job_table(bytes(blob), len(blob), 1, _native.as_ptr(out), 32)
+        rc = lib.db_tc_job_table(bytes(blob), len(blob), 0, _native.as_ptr(out), 32)
         assert rc == -2, (bad[1:], rc, lib.db_last_error())

@@ -1,10 +1,8 @@
-"""Host-side checks of the tcgen05 engine's MMA job tables (csrc/dbn_tc.cu build_jobs - pair kernel,
-which = 0 - and build_solo_jobs - solo kernel, which = 1), dumped through the C ABI without a GPU
-(db_tc_job_table).
+"""Host-side checks of the tcgen05 engine's MMA job table (csrc/dbn_tc.cu build_jobs), dumped through
+the C ABI without a GPU (db_tc_job_table).
 
-The MMA issuer runs ahead of the epilogue warps: a job carries `need`, the number of epilogues of the
-hand-off sequence that must have completed before its MMAs may be issued (pair kernel: the joint jobs,
-numbered from 0; solo kernel: every job, with conv1d_1's CUDA-core stage as epilogue 0).  These tests
+The joint phase lets the MMA issuer run ahead of the epilogue warps: every joint job carries `need`,
+the number of joint epilogues that must have completed before its MMAs may be issued.  These tests
 re-derive the hazards from the table itself - shared-memory tensors (who wrote what a job reads),
 accumulator slots (who drained the slot a job overwrites), the 4-deep mbarrier rings - so that an edit
 of the job order or of the buffer layout that forgets a dependency fails here, on the CPU."""
@@ -42,7 +40,7 @@ def out_extent(job):
     return job['out_off'], job['out_off'] + 2 * job['out_lo']
 
 
-@pytest.mark.parametrize('which,njobs', [(0, 21), (1, 21)])
+@pytest.mark.parametrize('which,njobs', [(0, 21)])
 @pytest.mark.parametrize('name', MODELS)
 def test_joint_schedule_is_hazard_free(name, which, njobs):
     jobs = job_table(name, which)
@@ -108,7 +106,7 @@ def test_joint_schedule_is_hazard_free(name, which, njobs):
 
 @pytest.mark.parametrize('name', MODELS)
 def test_parameter_blocks_fit(name):
-    for which, cap in ((0, 1664), (1, 1 << 20)):   # (the solo kernel reads its parameters from global memory)
+    for which, cap in ((0, 1664),):
         jobs = job_table(name, which)
         used = max(max(j['bias'] + j['n'], j['bn'] + 96 if j['bn'] else 0) for j in jobs)
         assert used <= cap
@@ -141,7 +139,7 @@ def bf16_pairs_to_f32(buf):
     return (buf.view(np.uint16).astype(np.uint32) << 16).view(np.float32)
 
 
-@pytest.mark.parametrize('which,layers', [(0, FUSED_LAYERS), (1, FUSED_LAYERS)])
+@pytest.mark.parametrize('which,layers', [(0, FUSED_LAYERS)])
 @pytest.mark.parametrize('name', MODELS)
 def test_packed_weights_and_parameters_match_the_model(name, which, layers):
     from oracle import deepbinner_oracle as orc

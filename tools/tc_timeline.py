@@ -17,35 +17,11 @@ NAMES = ['conv2', 'conv3', 'conv4', 'conv5', 'conv6', 'conv7', 'conv8', 'conv9',
          'conv19', 'conv20']
 
 
-def solo_timeline(m, x, p, n):
-    """Solo kernel: trace[job][16] - [0] MMA issue start, [1] issue end, [2] accumulators ready,
-    [3] epilogue end, [11] issuer reached the job; row 31: [0] epilogue warps start, [1] conv1d_1 done."""
-    trace = np.zeros((32, 2, 16), dtype=np.int64)
-    for _ in range(3):
-        rc = m._lib.db_tc_trace(m._handle, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(p.data_ptr()),
-                                _native.as_ptr(trace))
-        _native.check(rc, 'db_tc_trace')
-    tr = trace.reshape(-1)[:32 * 16].reshape(32, 16)
-    nj = tc_num_jobs(m)
-    t0 = tr[31, 0]
-    print('solo kernel, {} CTAs | epilogue warps start 0 | conv1 done {}'.format(n, int(tr[31, 1] - t0)))
-    print('job      | top    issue_start issue_end | acc_ready epi_end | wait   issue_dur  mma_tail  epi_dur')
-    prev_end = 0
-    for j in range(nj):
-        top, a, b, c, d = [int(v - t0) if v > 0 else -1 for v in (tr[j, 11], tr[j, 0], tr[j, 1], tr[j, 2], tr[j, 3])]
-        print('{:8s} | {:6d} {:8d} {:8d} | {:8d} {:8d} | {:6d} {:8d} {:8d} {:8d}'.format(
-            NAMES[j], top, a, b, c, d, a - top, b - a, (c - b) if c >= 0 else -1, (d - c) if c >= 0 else -1))
-    print('total', int(tr[:nj, :4].max() - t0))
-
-
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 296
-    engine = sys.argv[2] if len(sys.argv) > 2 else 'tcgen05'
     m = B200Model(str(ROOT / 'deepbinner_b200/models/EXP-NBD103_read_starts.dbnw'))
-    m.set_engine(engine)
+    m.set_engine('tcgen05')
     x = torch.randn(n, 1024, device='cuda')
-    if engine == 'tcgen05':
-        return solo_timeline(m, x, torch.zeros(n, 13, device='cuda'), n)
     p = torch.zeros(n, 13, device='cuda')
     trace = np.zeros((32, 2, 16), dtype=np.int64)
     for _ in range(3):
