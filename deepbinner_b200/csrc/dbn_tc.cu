@@ -1061,6 +1061,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     const uint32_t jw1_16 = jw0_16 + (J.ntaps * J.ncb == 9 ? 10u : 4u) * blk16;   // behind part 0
                     mbar_wait(bar_jwfull0 + 8 * slot, (jk / 3) & 1);
                     if (tracing) trace[(j * 2) * 16 + 12] = clock64();
+                    if (tracing) {   // in-situ cost of a poll of a barrier whose phase is known to be complete
+                        const long long t0 = clock64();
+                        mbar_wait(bar_jwfull0 + 8 * slot, (jk / 3) & 1);
+                        trace[(j * 2 + 1) * 16 + 14] = clock64() - t0;
+                        trace[(j * 2 + 1) * 16 + 13] = mbar_test(bar_jwfull0 + 8 * slot, (jk / 3) & 1) ? clock64() - t0 : -1;
+                    }
                     if (first && J.eseq == 0) {   // first joint job: the per-window epilogues of the last
 #pragma unroll
                         for (int w = 0; w < 2; ++w) {   // single-window job must be done
@@ -1150,6 +1156,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 // loader gets here only after conv1d_9's weights were requested, i.e. after conv1d_8's
                 // MMAs - and with them conv1d_7's epilogue, the last user of that space - completed)
                 const uint32_t bytes = J.w_part[0] + J.w_part[1];
+                if (trace && blockIdx.x == 0) trace[(j * 2 + 1) * 16 + 15] = clock64();   // when the load was issued
                 mbar_expect_tx(bar_jwfull0 + 8 * slot, bytes);
                 bulk_g2s(slot == 0 ? wbuf : slot == 1 ? jwslot1 : jwslot2, src, bytes, bar_jwfull0 + 8 * slot);
                 ++jk;

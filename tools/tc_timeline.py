@@ -40,7 +40,13 @@ def main():
             print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d} | {:5d} {:5d} {:5d} {:5d} {:5d} | {:5d} {:5d} {:5d} {:5d} | top {:6d} waited {:6d} need {:6d}'.format(
                 NAMES[j], w, a, b, c, d, b - a, (d - c) if c >= 0 else -1,
                 e4 - c, e5 - e4, e6 - e5, e7 - e6, d - e7, x8 - a, x9 - x8, x10 - x9, b - x10, x11, x12, x13))
-    print('total', int(trace[:nj].max() - t0))
+    print('joint-phase weight loads: job | load issued by the loader | issuer reached the job | weights seen (latency if the issuer waited)')
+    for j in range(8, nj):
+        ld, top, seen = int(trace[j, 1, 15] - t0), int(trace[j, 0, 11] - t0), int(trace[j, 0, 12] - t0)
+        print('  {:8s} | {:7d} | {:7d} | {:7d}  ({}) | repeat poll {} cycles, + test_wait {}'.format(NAMES[j], ld, top, seen,
+              'load -> seen {} cycles'.format(seen - ld) if seen - top > 150 else 'ready',
+              int(trace[j, 1, 14]), int(trace[j, 1, 13])))
+    print('total', int(trace[:nj, :, :14].max() - t0))
 
 
 if __name__ == '__main__':
