@@ -26,8 +26,74 @@ from .model import B200Model, signals_fit_int16
 from .trim_signal import normalise
 
 
+def world():
+    """(rank, local_rank, world_size) of this process (torchrun environment; 1 process if unset)."""
+    return (int(os.environ.get('RANK', 0)), int(os.environ.get('LOCAL_RANK', 0)),
+            int(os.environ.get('WORLD_SIZE', 1)))
+
+
+def classify_distributed(args):
+    """`classify --gpus N` inside one of the N ranks (one process per GPU): rank 0 reads the model files
+    and lists the input, the weights and the file list are broadcast (the one collective of the data
+    path), every rank classifies a contiguous shard of the files on its own GPU, and rank 0
+    prints header, rows in rank order (= the order of a one-GPU run) and the summary table."""
+    import contextlib
+    import io
+    from . import parallel
+    rank, local_rank, world_size = parallel.init()
+    device = parallel.device_for(local_rank)
+    parallel.bind_to_numa_node_of_gpu(device)
+    quiet = open(os.devnull, 'w')
+    log = sys.stderr if rank == 0 else quiet
+    set_tensorflow_threads(args)
+    start_model, start_input_size, end_model, end_input_size, output_size, model_count = \
+        load_and_check_models(args.start_model, args.end_model, args.scan_size, out_dest=log, device=device,
+                              distributed=True)
+    input_type = parallel.broadcast_object(determine_input_type(args.input) if rank == 0 else None)
+    if input_type == 'training_data':      # a text file read sequentially: not sharded, rank 0 does it
+        if rank == 0:
+            if model_count == 2:
+                sys.exit('Error: training data can only be classified using a single model')
+            print('', file=sys.stderr)
+            classify_training_data(args.input, start_model, start_input_size, end_model, end_input_size,
+                                   output_size, args)
+        parallel.barrier()
+        return
+    print('', file=log)
+    files, multi = None, None
+    if rank == 0:
+        files = find_all_fast5s(args.input, verbose=True) if input_type == 'directory' else [args.input]
+        if not files:
+            files = None
+        else:
+            multi = determine_single_or_multi_fast5s(files)
+    files, multi = parallel.broadcast_object((files, multi))
+    if files is None:
+        sys.exit('Error: no fast5 files found')
+    lo, hi = parallel.shard_range(len(files), rank, world_size)
+    rows, calls = io.StringIO(), {}
+    if hi > lo:
+        with contextlib.redirect_stdout(rows), contextlib.redirect_stderr(log):
+            calls, _ = classify_fast5_files(files[lo:hi], start_model, start_input_size, end_model, end_input_size,
+                                            output_size, args, summary_table=False, print_header=False,
+                                            known_layout=multi)
+    parts = parallel.gather_objects((rows.getvalue(), calls))
+    if rank == 0:
+        print_output_header(args.verbose, start_model is not None, end_model is not None, output_size)
+        merged = {}
+        for text, part in parts:
+            sys.stdout.write(text)
+            merged.update(part)
+        sys.stdout.flush()
+        print('', file=sys.stderr)
+        print_summary_table(merged)
+    parallel.barrier()
+
+
 def classify(args):
     """Entry point of the `classify` command (reference classify.py:32-55)."""
+    if world()[2] > 1:
+        return classify_distributed(args)
     set_tensorflow_threads(args)
     start_model, start_input_size, end_model, end_input_size, output_size, model_count = \
         load_and_check_models(args.start_model, args.end_model, args.scan_size,
@@ -50,16 +116,17 @@ def classify(args):
 
 
 def load_and_check_models(start_model_filename, end_model_filename, scan_size, out_dest=sys.stderr,
-                          device=0):
+                          device=0, distributed=False):
     """-> (start_model, start_input_size, end_model, end_input_size, output_size, model_count),
-    as reference classify.py:58-83."""
+    as reference classify.py:58-83.  `distributed`: rank 0 reads the files, the packed weights are
+    broadcast to the other ranks."""
     loaded = {}
     for side, filename in (('start', start_model_filename), ('end', end_model_filename)):
         if filename is None:
             loaded[side] = (None, None, None)
             continue
         model, input_size, output_size = load_trained_model(filename, out_dest=out_dest,
-                                                            device=device)
+                                                            device=device, distributed=distributed)
         check_input_size(input_size, scan_size)
         loaded[side] = (model, input_size, output_size)
     start_model, start_input_size, start_output_size = loaded['start']
@@ -71,9 +138,11 @@ def load_and_check_models(start_model_filename, end_model_filename, scan_size, o
     return start_model, start_input_size, end_model, end_input_size, output_size, model_count
 
 
-def load_trained_model(model_file, out_dest=sys.stderr, device=0):
+def load_trained_model(model_file, out_dest=sys.stderr, device=0, distributed=False):
     """Load a Keras HDF5 model file (or a DBNW blob) onto the GPU -> (model, input_size,
     output_size) (reference classify.py:86-103)."""
+    if distributed and world()[2] > 1:
+        return load_trained_model_broadcast(model_file, out_dest, device)
     if not pathlib.Path(model_file).is_file():
         sys.exit('Error: {} does not exist'.format(model_file))
     print('Loading {}... '.format(model_file), file=out_dest, end='', flush=True)
@@ -94,9 +163,40 @@ def load_trained_model(model_file, out_dest=sys.stderr, device=0):
     return model, input_size, output_size
 
 
+def load_trained_model_broadcast(model_file, out_dest, device):
+    """Multi-GPU: rank 0 parses the model file; the packed weight blob (0.43 MB) is broadcast to the
+    other ranks (NCCL, parallel.broadcast_blob) - the one collective of the data path."""
+    from . import parallel
+    from ._native import NativeError
+    rank = world()[0]
+    blob = None
+    if rank == 0:
+        if not pathlib.Path(model_file).is_file():
+            blob = b'!'
+        else:
+            print('Loading {}... '.format(model_file), file=out_dest, end='', flush=True)
+            try:
+                blob = weights.load_blob(model_file)
+            except (weights.ModelFormatError, hdf5_lite.Hdf5Error, KeyError):
+                blob = b'?'
+    blob = parallel.broadcast_blob(blob if blob is not None else b'')
+    if blob == b'!':
+        sys.exit('Error: {} does not exist'.format(model_file))
+    if blob == b'?':
+        sys.exit('Error: model input has incorrect shape - are you sure that {} is a valid '
+                 'model file?'.format(model_file))
+    try:
+        model = B200Model(blob=blob, device=device)
+    except NativeError as e:
+        sys.exit('Error: could not load {} on the B200 engine: {}'.format(model_file, e))
+    if rank == 0:
+        print('done', file=out_dest)
+    return model, int(model.inputs[0].shape[1]), int(model.outputs[0].shape[1])
+
+
 def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, end_input_size,
                          output_size, args, full_output=True, summary_table=True,
-                         verified_single_read=False):
+                         verified_single_read=False, print_header=True, known_layout=None):
     """Batch driver (reference classify.py:106-180): chunk the file list by `args.batch_size`, load
     signals, call each side, combine, print TSV rows.  -> (classifications, read_id_to_fast5_file)."""
     if not fast5_files:
@@ -106,11 +206,15 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
     # Multi-read fast5 files are read natively, every read straight out of the file (the reference
     # needs them unpacked to one file per read first, realtime.py:183-196); a batch is then one file
     # (thousands of reads in a MinKNOW file) instead of `batch_size` files.
-    multi = (not verified_single_read) and determine_single_or_multi_fast5s(fast5_files) == 'multi'
+    # (`known_layout`: 'single' / 'multi' when the caller has already looked - a shard of a multi-GPU run)
+    if known_layout is not None:
+        multi = known_layout == 'multi'
+    else:
+        multi = (not verified_single_read) and determine_single_or_multi_fast5s(fast5_files) == 'multi'
 
     use_start, use_end = start_model is not None, end_model is not None
     print_classification_progress(0, len(fast5_files), 'fast5s', out_dest=out_dest)
-    if full_output:
+    if full_output and print_header:
         print_output_header(args.verbose, use_start, use_end, output_size)
 
     input_size = start_input_size if use_start else end_input_size

@@ -179,7 +179,7 @@ struct db_model {
         size_t d_calls_bytes = 0;
         cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_join = nullptr;
     } jobs[kJobSlots];
-    int call_chunk = 64;                // reads per pipelined chunk of a job (DEEPBINNER_B200_CALL_CHUNK)
+    int call_chunk_windows = 2048;      // network windows per pipelined chunk of a job (DEEPBINNER_B200_CALL_CHUNK)
 };
 
 namespace dbn {
@@ -267,7 +267,7 @@ static int check_scan(const db_model* m, int scan_size, int* steps) {
 using namespace dbn;
 
 // ---- pipelined host entry of seam b2 -------------------------------------------------------------
-// A job = one call_batch over n_reads host reads.  submit() cuts it into chunks of `call_chunk` reads;
+// A job = one call_batch over n_reads host reads.  submit() cuts it into chunks of ~2048 network windows;
 // for every chunk the host gathers the scan regions (the only samples call_batch ever looks at: the
 // first / last scan_size + input_size/2 of each read, classify.py:337-349) into the job's pinned
 // staging and enqueues H2D copy -> network kernel -> merge/call kernel -> D2H of the results on one of
@@ -301,7 +301,7 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
     }
     DBN_CUDA(cudaSetDevice(m->device));
     const int64_t region_max = static_cast<int64_t>(scan_size) + m->input_size / 2;
-    const int chunk = m->call_chunk;
+    const int chunk = std::max(1, m->call_chunk_windows / steps);   // reads per chunk
     const int nchunks = (n_reads + chunk - 1) / chunk;
     const size_t nc = m->n_classes;
     // sizes: regions are bounded by region_max per read
@@ -460,7 +460,7 @@ int db_create(const void* weights_blob, size_t blob_bytes, int device, db_model*
             DBN_CUDA(cudaEventCreate(&j.ev_stop));
             DBN_CUDA(cudaEventCreateWithFlags(&j.ev_join, cudaEventDisableTiming));
         }
-        if (const char* v = getenv("DEEPBINNER_B200_CALL_CHUNK")) m->call_chunk = std::max(1, atoi(v));
+        if (const char* v = getenv("DEEPBINNER_B200_CALL_CHUNK")) m->call_chunk_windows = std::max(1, atoi(v));
         return 0;
     }();
     if (rc) {

@@ -5,10 +5,14 @@ Command line of the B200 classifier: the `classify` and `realtime` commands of r
 :177-196, `check_classify_and_realtime_arguments` :283-317, `find_model` :320-345).  The reference's
 `bin` (host-side text streaming, bin.py) completes the classify -> bin workflow; the other
 sub-commands (prep, balance, train, refine) are outside the accelerated hot path.
-The four TensorFlow thread knobs are accepted and ignored; `--device` selects the GPU.
+The four TensorFlow thread knobs are accepted and ignored; `--device` selects the GPU and `--gpus N`
+runs `classify` / `realtime` data-parallel on N GPUs of the box: the command re-launches itself as one
+process per GPU (torch.distributed.run, NCCL), rank 0 broadcasts the weights and the file list, every
+rank classifies a contiguous shard of the reads, rank 0 prints the rows in rank (= input) order.
 """
 
 import argparse
+import os
 import pathlib
 import sys
 
@@ -34,6 +38,9 @@ def main(argv=None):
         sys.exit(1)
     args = parser.parse_args(argv)
 
+    if getattr(args, 'gpus', 1) > 1 and int(os.environ.get('WORLD_SIZE', '1')) == 1:
+        sys.exit(relaunch_on_gpus(args.gpus, argv))
+
     if args.subparser_name == 'classify':
         check_classify_and_realtime_arguments(args)
         from .classify import classify
@@ -48,6 +55,19 @@ def main(argv=None):
     else:
         parser.print_help(file=sys.stderr)
         sys.exit(1)
+
+
+def relaunch_on_gpus(n_gpus, argv):
+    """`--gpus N`: run this very command as N ranks (one process per GPU) under torch.distributed.run;
+    returns the exit code."""
+    import socket
+    import subprocess
+    with socket.socket() as sock:
+        sock.bind(('127.0.0.1', 0))
+        port = sock.getsockname()[1]
+    cmd = [sys.executable, '-m', 'torch.distributed.run', '--nnodes=1', '--nproc-per-node', str(n_gpus),
+           '--master-addr', '127.0.0.1', '--master-port', str(port), '-m', 'deepbinner_b200'] + list(argv)
+    return subprocess.call(cmd)
 
 
 def classify_subparser(subparsers):
@@ -120,6 +140,8 @@ def classify_and_realtime_options(group):
     perf = group.add_argument_group('Performance')
     perf.add_argument('--batch_size', type=int, default=256, help='Neural network batch size')
     perf.add_argument('--device', type=int, default=0, help='CUDA device ordinal')
+    perf.add_argument('--gpus', type=int, default=1,
+                      help='Number of GPUs of this machine to spread the reads over (one process per GPU)')
     for knob, default in (('intra_op_parallelism_threads', 12), ('inter_op_parallelism_threads', 1),
                           ('device_count', 1), ('omp_num_threads', 12)):
         perf.add_argument('--' + knob, type=int, default=default,

@@ -25,11 +25,78 @@ def init(backend=None):
         os.environ.setdefault('MASTER_ADDR', '127.0.0.1')
         os.environ.setdefault('MASTER_PORT', '29512')
         if backend is None:
-            backend = 'nccl' if torch.cuda.is_available() else 'gloo'
+            # NCCL needs one GPU per rank; ranks that share a GPU (tests on a one-GPU box) or have none
+            # use gloo for the (tiny) control traffic
+            backend = 'nccl' if torch.cuda.is_available() and torch.cuda.device_count() >= world_size else 'gloo'
         if backend == 'nccl':
             torch.cuda.set_device(local_rank)
         dist.init_process_group(backend=backend, rank=rank, world_size=world_size)
     return rank, local_rank, world_size
+
+
+def device_for(local_rank):
+    """CUDA device ordinal of a rank: its own GPU, or (fewer GPUs than ranks) local_rank modulo the
+    device count."""
+    n = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    return local_rank % n if n else local_rank
+
+
+def _collective_device():
+    return torch.device('cuda', torch.cuda.current_device()) if dist.get_backend() == 'nccl' \
+        else torch.device('cpu')
+
+
+def is_distributed():
+    return dist.is_initialized() and dist.get_world_size() > 1
+
+
+def broadcast_object(obj, src=0):
+    """Broadcast a small picklable object (file list of a round) from `src`."""
+    if not is_distributed():
+        return obj
+    box = [obj if dist.get_rank() == src else None]
+    dist.broadcast_object_list(box, src=src, device=_collective_device())
+    return box[0]
+
+
+def gather_objects(obj, dst=0):
+    """Rank-ordered list of every rank's object on `dst` (None elsewhere): the host-side result
+    collection - each rank's rows stay its own slice, nothing is reduced."""
+    if not is_distributed():
+        return [obj]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out if dist.get_rank() == dst else None
+
+
+def all_gather_objects(obj):
+    if not is_distributed():
+        return [obj]
+    out = [None] * dist.get_world_size()
+    dist.all_gather_object(out, obj)
+    return out
+
+
+def bind_to_numa_node_of_gpu(device):
+    """Pin this process (its fast5-parsing and gather threads, and the pinned staging it allocates
+    afterwards) to the CPUs of the NUMA node its GPU hangs off, so that eight ranks do not all stage
+    through one node.  Best effort: silently does nothing without sysfs / on a single-node box."""
+    try:
+        props = torch.cuda.get_device_properties(device)
+        bus = '{:04x}:{:02x}:{:02x}.0'.format(props.pci_domain_id, props.pci_bus_id, props.pci_device_id)
+        node = int(open('/sys/bus/pci/devices/{}/numa_node'.format(bus)).read())
+        if node < 0:
+            return None
+        cpus = set()
+        for part in open('/sys/devices/system/node/node{}/cpulist'.format(node)).read().strip().split(','):
+            a, _, b = part.partition('-')
+            cpus.update(range(int(a), int(b or a) + 1))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+        return node
+    except Exception:  # noqa: BLE001
+        return None
 
 
 def shard_range(n_items, rank, world_size):

@@ -34,14 +34,29 @@ POLL_SECONDS = 5
 
 
 def realtime(args, poll_seconds=POLL_SECONDS):
+    """`--gpus N` (one process per GPU, see deepbinner.py): rank 0 watches the directory and broadcasts
+    each round's file list; every rank classifies and moves a contiguous shard of it on its own GPU
+    (moves are independent); the calls are gathered on rank 0 for the summary table."""
+    from .classify import world
+    rank, local_rank, world_size = world()
+    par = None
+    device = getattr(args, 'device', 0)
+    if world_size > 1:
+        from . import parallel as par
+        par.init()
+        device = par.device_for(local_rank)
+        par.bind_to_numa_node_of_gpu(device)
+        if rank != 0:
+            sys.stdout = open(os.devnull, 'w')     # rank 0 reports; the other ranks only work
     args.verbose = False
     set_tensorflow_threads(args)
     start_model, start_input_size, end_model, end_input_size, output_size, _ = \
         load_and_check_models(args.start_model, args.end_model, args.scan_size,
-                              out_dest=sys.stdout, device=getattr(args, 'device', 0))
+                              out_dest=sys.stdout, device=device, distributed=world_size > 1)
     in_dir = pathlib.Path(args.in_dir)
     out_dir = pathlib.Path(args.out_dir)
-    make_output_dir(out_dir)
+    if rank == 0:
+        make_output_dir(out_dir)
     nested_out_dir = is_inside(out_dir, in_dir)
 
     print('\nLooking for new fast5 files in {}'.format(in_dir), flush=True)
@@ -49,17 +64,21 @@ def realtime(args, poll_seconds=POLL_SECONDS):
     waiting_dots = 0
     try:
         while True:
-            fast5s = [f for f in look_for_new_fast5s(in_dir, out_dir, nested_out_dir)
-                      if f not in ignore_files]
+            fast5s, single_or_multi = None, None
+            if rank == 0:
+                fast5s = [f for f in look_for_new_fast5s(in_dir, out_dir, nested_out_dir)
+                          if f not in ignore_files]
+                single_or_multi = determine_single_or_multi_fast5s(fast5s) if fast5s else 'single'
+            if par:
+                fast5s, single_or_multi = par.broadcast_object((fast5s, single_or_multi))
             if fast5s:
                 if waiting_dots:
                     print('', flush=True)
                     waiting_dots = 0
-                single_or_multi = determine_single_or_multi_fast5s(fast5s)
                 print('\nFound {:,} fast5 files'.format(len(fast5s)), flush=True)
                 time.sleep(poll_seconds)   # let files that are still being written settle
                 classify_and_move(fast5s, args, start_model, start_input_size, end_model,
-                                  end_input_size, output_size, out_dir, ignore_files, single_or_multi)
+                                  end_input_size, output_size, out_dir, ignore_files, single_or_multi, par)
                 print('\nLooking for new fast5 files in {}'.format(in_dir), flush=True)
             elif args.stop:
                 break
@@ -91,28 +110,50 @@ def look_for_new_fast5s(in_dir, out_dir, nested_out_dir):
 
 
 def classify_and_move(fast5s, args, start_model, start_input_size, end_model, end_input_size,
-                      output_size, out_dir, ignore_files, single_or_multi='single'):
+                      output_size, out_dir, ignore_files, single_or_multi='single', par=None):
+    """One round.  `par` (deepbinner_b200.parallel, multi-GPU runs): this rank takes a contiguous shard
+    of the round's files; calls and newly ignored files are gathered afterwards."""
     limit = MAX_FILES_PER_ROUND if single_or_multi == 'single' else MAX_MULTI_FILES_PER_ROUND
+    if par:
+        limit *= par.world()[2]       # the per-round limit applies per GPU
     if len(fast5s) > limit:       # reference realtime.py:89-94: lots of one-read files, a few multi-read ones
         fast5s = fast5s[:limit]
         print('Limiting this round to {:,} files'.format(limit), flush=True)
     if single_or_multi == 'multi':
         ignore_files.update(fast5s)     # reference :99: the multi-read files themselves stay where they are
-    classifications, read_id_to_fast5_file = \
-        classify_fast5_files(fast5s, start_model, start_input_size, end_model, end_input_size,
-                             output_size, args, full_output=False,
-                             verified_single_read=(single_or_multi == 'single'))
-    print('', flush=True)
-    if single_or_multi == 'multi':
-        record_multi_read_classifications(classifications, read_id_to_fast5_file, out_dir)
+    mine = fast5s
+    if par:
+        rank, _, world_size = par.world()
+        lo, hi = par.shard_range(len(fast5s), rank, world_size)
+        mine = fast5s[lo:hi]
+    classifications, read_id_to_fast5_file = {}, {}
+    newly_ignored = set()
+    if mine:
+        classifications, read_id_to_fast5_file = \
+            classify_fast5_files(mine, start_model, start_input_size, end_model, end_input_size,
+                                 output_size, args, full_output=False,
+                                 verified_single_read=(single_or_multi == 'single'), known_layout=single_or_multi)
+        print('', flush=True)
+        if single_or_multi == 'multi':
+            record_multi_read_classifications(classifications, read_id_to_fast5_file, out_dir,
+                                              suffix='.rank{}'.format(par.world()[0]) if par else '')
+        else:
+            move_classified_fast5s(classifications, read_id_to_fast5_file, out_dir, mine, newly_ignored)
+    if par:
+        merged = {}
+        for calls, ignored in par.all_gather_objects((classifications, newly_ignored)):
+            merged.update(calls)
+            ignore_files.update(ignored)
+        classifications = merged
     else:
-        move_classified_fast5s(classifications, read_id_to_fast5_file, out_dir, fast5s, ignore_files)
+        ignore_files.update(newly_ignored)
     print_summary_table(classifications, output=sys.stdout)
 
 
-def record_multi_read_classifications(classifications, read_id_to_fast5_file, out_dir):
-    """Per-read result of multi-read input: rows appended to <out_dir>/multi_read_classifications.tsv."""
-    path = pathlib.Path(out_dir) / MULTI_TSV
+def record_multi_read_classifications(classifications, read_id_to_fast5_file, out_dir, suffix=''):
+    """Per-read result of multi-read input: rows appended to <out_dir>/multi_read_classifications.tsv
+    (multi-GPU runs: one file per rank, `.rank<r>` appended)."""
+    path = pathlib.Path(out_dir) / (MULTI_TSV + suffix)
     new = not path.exists()
     with open(str(path), 'at') as f:
         if new:

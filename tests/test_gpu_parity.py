@@ -313,9 +313,10 @@ def test_cli_classify_on_real_fast5_files(fast5_dir, reference_goldens, capsys):
     cli.main(['classify', '-s', cli.find_native_start_model(), '--verbose', str(one)])
     lines = capsys.readouterr().out.strip().splitlines()
     assert lines[1] == '\t'.join([g['read_id'], '3'] + g['start'])
-    with pytest.raises(SystemExit) as e:     # multi-read input is rejected like the reference does
-        cli.main(['classify', '--native', str(fast5_dir / 'multi_read_fast5_files')])
-    assert 'one-read-per-file' in str(e.value)
+    # multi-read input: every read of the file is classified (read natively, no multi_to_single_fast5)
+    cli.main(['classify', '--native', str(fast5_dir / 'multi_read_fast5_files')])
+    lines = capsys.readouterr().out.strip().splitlines()
+    assert lines[0] == 'read_ID\tbarcode_call' and len(lines) == 11
 
 
 def test_packed_signals_take_the_same_fused_path(models, fast5_dir, fixture_reads):
@@ -496,3 +497,47 @@ def test_baseline_config3_rapid_model_batch512(models, fixture_reads, multi_read
         calls, probs = model.call_batch(reads, 'start', 6144, 0.5)
         assert ['none' if c == 0 else str(int(c)) for c in calls] == ocalls
         assert np.abs(probs - oprobs).max() <= TOL
+
+
+def test_two_rank_sharded_classify_equals_one_rank(fast5_dir, tmp_path):
+    """`classify --gpus 2` (two ranks, one process each; on a one-GPU box both use GPU 0 and gloo
+    carries the control traffic): the TSV on stdout equals the one-process run row for row."""
+    import subprocess
+    import sys
+    from conftest import ROOT
+    many = tmp_path / 'reads'
+    many.mkdir()
+    import shutil
+    for i in range(3):                      # 21 files so that both shards span several batches
+        for f in (fast5_dir / 'fast5_files').glob('*.fast5'):
+            shutil.copy(f, many / '{}_{}'.format(i, f.name))
+    base = [sys.executable, '-m', 'deepbinner_b200', 'classify', '--native', '--verbose', '--batch_size', '4', str(many)]
+    one = subprocess.run(base, cwd=str(ROOT), capture_output=True, text=True, timeout=600)
+    assert one.returncode == 0, one.stderr[-2000:]
+    two = subprocess.run(base + ['--gpus', '2'], cwd=str(ROOT), capture_output=True, text=True, timeout=900)
+    assert two.returncode == 0, two.stderr[-2000:]
+    rows1, rows2 = one.stdout.strip().splitlines(), two.stdout.strip().splitlines()
+    assert rows1[0] == rows2[0] and rows1[0].startswith('read_ID')
+    # duplicated files share read ids: compare the row multisets and the per-file order of distinct ids
+    assert sorted(rows1[1:]) == sorted(rows2[1:]) and len(rows1) == 22
+    assert 'Barcode     Count' in two.stderr
+
+
+def test_multi_read_fast5_classifies_like_its_reads(models, oracle_weights, fast5_dir, multi_reads, capsys):
+    """A multi-read fast5 goes through `classify` natively: every read of the file is called, and the
+    calls / probabilities equal those of the same reads given as plain signals (and the oracle's)."""
+    from deepbinner_b200 import classify as cls, load_fast5s as lf
+    ids, sigs = multi_reads
+    by_id = dict(zip(ids, sigs))
+    multi = sorted(str(p) for p in (fast5_dir / 'multi_read_fast5_files').glob('*.fast5'))
+    start, end = models['EXP-NBD103_read_starts'], models['EXP-NBD103_read_ends']
+    for m in (start, end):
+        m.set_engine('tcgen05')
+    got, where = cls.classify_fast5_files(multi, start, 1024, end, 1024, 13, make_args(require_either=True),
+                                          full_output=False)
+    assert len(got) == 10 and set(where.values()) == set(multi)
+    reads = [by_id[r] for r in got]
+    oc_s, _ = orc.call_batch(oracle_weights['EXP-NBD103_read_starts'], reads, 'start', 6144, 0.5)
+    oc_e, _ = orc.call_batch(oracle_weights['EXP-NBD103_read_ends'], reads, 'end', 6144, 0.5)
+    assert list(got.values()) == [orc.combine_calls(a, b, require_either=True) for a, b in zip(oc_s, oc_e)]
+    capsys.readouterr()

@@ -29,8 +29,15 @@ def _worker(rank, world_size, port, blob_path, out):
     rows = np.arange(lo, hi, dtype=np.float32)[:, None] * np.ones((1, 13), np.float32)
     allrows = parallel.gather_rows(rows, n_reads)
     slowest = parallel.max_over_ranks(10.0 + r)
+    # product-level sharding of `classify --gpus N`: rank 0's file list is broadcast, every rank formats
+    # the rows of its contiguous shard, rank 0 receives them in rank order
+    files = parallel.broadcast_object(['f%d.fast5' % i for i in range(7)] if r == 0 else None)
+    flo, fhi = parallel.shard_range(len(files), r, w)
+    text = ''.join('{}\t{}\n'.format(f, i % 3) for i, f in enumerate(files[flo:fhi], start=flo))
+    parts = parallel.gather_objects((text, {f: str(i) for i, f in enumerate(files[flo:fhi], start=flo)}))
+    everyone = parallel.all_gather_objects(r)
     parallel.barrier()
-    out[rank] = (len(got), hash(got), (lo, hi), allrows[:, 0].tolist(), slowest)
+    out[rank] = (len(got), hash(got), (lo, hi), allrows[:, 0].tolist(), slowest, parts, everyone)
 
 
 def test_two_rank_broadcast_shard_gather():
@@ -49,6 +56,13 @@ def test_two_rank_broadcast_shard_gather():
     assert out[0][2] == (0, 6) and out[1][2] == (6, 11)
     assert out[0][3] == out[1][3] == [float(i) for i in range(11)]
     assert out[0][4] == out[1][4] == 11.0
+    assert out[1][5] is None and out[0][6] == out[1][6] == [0, 1]
+    text = ''.join(t for t, _ in out[0][5])
+    assert text == ''.join('f{}.fast5\t{}\n'.format(i, i % 3) for i in range(7))      # rank order == input order
+    merged = {}
+    for _, part in out[0][5]:
+        merged.update(part)
+    assert merged == {'f%d.fast5' % i: str(i) for i in range(7)}
 
 
 def test_shard_range_covers_everything():
