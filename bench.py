@@ -15,12 +15,21 @@ The shard (256 MiB of fp32) is larger than the 126 MB L2, so no flush is needed 
 
 value  = reads/s, whole job, inputs already in HBM (device-resident entry of the C ABI),
          CUDA-event timed, max over ranks.
-e2e    = the same through the public host API `B200Model.predict` (C-ABI db_predict_windows) with
-         pinned HOST buffers: H2D of the step's windows and D2H of its probabilities inside the timed
-         region.
-roofline = tensor (dense conv contraction): algorithmic 33,629,952 FLOP per window.
+e2e    = the same metric through the reference-facing entry - the fused `call_batch` (C-ABI
+         db_call_batch_submit_packed / _wait; what classify.call_batch runs) on the raw int16 reads in
+         HOST memory, scan_size 512: gather into pinned staging, H2D of the samples and D2H of the
+         per-read probabilities and calls inside the timed region.  `e2e.predict_f32` is the same through
+         `B200Model.predict` on float32 windows (seam b1), `e2e.predict_n256_f64` the shape the reference's
+         own call_batch produces (pageable float64, 256 windows per call).
+roofline = tensor (dense conv contraction): algorithmic 33,629,952 FLOP per window, against the measured
+         burst bf16 peak (`frac`) and the sustained one (`frac_sustained`).
 cpu_baseline = the torch-CPU fp32 oracle on all host cores, bounded sample (the reference's own
          TensorFlow-CPU model.predict cannot run in this image - no tensorflow/keras/h5py).
+configs = first-class lines for BASELINE configs[1] (EXP-NBD103 start+end, batch 256), configs[2]
+         (SQK-RBK004, batch 512) and configs[4] (realtime streaming, start+end, rounds of 20 000 reads per
+         GPU) through the product's own batch pipeline (classify.classify_read_batches).
+
+`--config strong` runs the strong-scaling form of configs[3]: 1 048 576 reads in total, split over the ranks.
 """
 import argparse
 import json
@@ -48,11 +57,50 @@ def model_path():
 
 
 def measured_peaks():
+    """(burst, sustained, source): the timed region is short (well under a second at full clocks, no
+    power-cap samples), so the burst figure is the roofline denominator; sustained is reported beside it."""
     p = ROOT / 'MEASURED_PEAKS.json'
     if p.exists():
         d = json.loads(p.read_text())
-        return d.get('bf16_tflops_sustained', d.get('bf16_tflops')), 'MEASURED_PEAKS.json bf16_tflops_sustained'
-    return 1400.0, 'fallback (B200_PROFILING.md sustained ~1.4 PFLOP/s)'
+        burst = d.get('bf16_tflops')
+        return burst, d.get('bf16_tflops_sustained', burst), 'MEASURED_PEAKS.json bf16_tflops (burst; measured)'
+    return 1590.0, 1400.0, 'fallback (B200_PROFILING.md: 1.59 PFLOP/s burst, ~1.4 sustained)'
+
+
+def synthetic_reads(n, seed, length=1024):
+    """int16 reads of the reference's gaussian recipe (balance.py:171-174) with 10 % real-fixture cuts:
+    the raw-signal form of synthetic_windows (which z-scores the same values)."""
+    rng = np.random.RandomState(seed)
+    z = np.load(ROOT / 'tests' / 'golden' / 'fixture_reads.npz')
+    real = [z['signal_{}'.format(i)] for i in range(7)]
+    out = np.empty((n, length), dtype=np.int16)
+    block = 8192
+    for s in range(0, n, block):
+        m = min(block, n - s)
+        mean = rng.uniform(300, 600, (m, 1))
+        sd = rng.uniform(10, 500, (m, 1))
+        x = np.trunc(rng.standard_normal((m, length)) * sd + mean)
+        for j in range(m // 10):
+            sig = real[rng.randint(7)]
+            a = rng.randint(0, len(sig) - length)
+            x[j * 10] = sig[a:a + length]
+        out[s:s + m] = np.clip(x, -32768, 32767).astype(np.int16)
+    return out
+
+
+class PackedReads:
+    """Reads of equal length in one int16 buffer, in the form load_fast5s.PackedSignals has (what the
+    native fast5 reader hands to call_batch): `samples`, `offsets`, `rows`."""
+
+    def __init__(self, reads2d):
+        n, length = reads2d.shape
+        self.samples = np.ascontiguousarray(reads2d).reshape(-1)
+        self.offsets = np.arange(n + 1, dtype=np.int64) * length
+        self.rows = np.arange(n, dtype=np.int64)
+        self.n = n
+
+    def __len__(self):
+        return self.n
 
 
 def synthetic_windows(n, seed):
@@ -136,62 +184,111 @@ class ClockSampler:
                 'samples': len(sm), 'reasons': sorted(reasons)}
 
 
-def cpu_baseline(seconds, x_sample):
-    """torch-CPU fp32 oracle on all host cores, batch 256, for ~`seconds` of CPU work."""
+def cpu_model():
     import torch
     from oracle.torch_cpu import TorchCpuModel
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    m = TorchCpuModel(model_path())
+    return TorchCpuModel(model_path()), torch.get_num_threads()
+
+
+CPU_NOTE = ("torch-CPU fp32 restatement of the Keras graph (oracle/torch_cpu.py) - the reference's TensorFlow-CPU "
+            "model.predict is not installable in this image (no tensorflow/keras/h5py wheel, no network); the "
+            "reference README quotes ~15 reads/s on 12 threads at 12-24 windows per read")
+
+
+def cpu_baseline(seconds, x_sample):
+    """torch-CPU fp32 oracle on all host cores, batch 256, for ~`seconds` of CPU work."""
+    m, cores = cpu_model()
     m.predict(x_sample[:BATCH])
     n, t0 = 0, time.perf_counter()
     while time.perf_counter() - t0 < seconds:
         m.predict(x_sample[(n // BATCH * BATCH) % (len(x_sample) - BATCH + 1):][:BATCH])
         n += BATCH
     dt = time.perf_counter() - t0
-    return {'value': n / dt, 'unit': 'reads/s', 'cores': torch.get_num_threads(), 'kind': 'port',
-            'sample': '{} windows (batch {}) of the same synthetic workload in {:.1f} s; torch-CPU fp32 '
-                      'restatement of the Keras graph (oracle/torch_cpu.py) - the reference\'s '
-                      'TensorFlow-CPU model.predict is not installable here; the reference README '
-                      'quotes ~15 reads/s (12 threads, 12-24 windows/read)'.format(n, BATCH, dt)}
+    return {'value': n / dt, 'unit': 'reads/s', 'cores': cores, 'kind': 'port',
+            'sample': '{} windows (batch {}) of the same synthetic workload in {:.1f} s; {}'.format(n, BATCH, dt, CPU_NOTE)}
+
+
+def workload_text(shard):
+    return ('synthetic 1M-read config (per-GPU shard of {} reads x 1024 samples), EXP-NBD103 start model, '
+            'scan_size 512 => 1 window per read, batch {}'.format(shard, BATCH))
 
 
 def run_reference(args, rank, world_size):
     """--impl reference: the CPU implementation of the path on the box's host cores (oracle port,
-    see cpu_baseline) on the same config/metric.  Rank 0 only."""
+    see cpu_baseline) on the same config/metric: a step = one pass over the same 65 536-read shard in
+    batches of 256 (the number of steps is capped so that the run ends within a few minutes).
+    Rank 0 only."""
     if rank != 0:
         return
-    import torch
-    from oracle.torch_cpu import TorchCpuModel
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
-    per_step = 4 * BATCH                      # bounded sample of the workload per step
-    x = synthetic_windows(per_step, seed=1234)
-    m = TorchCpuModel(model_path())
+    shard = (args.shard // BATCH) * BATCH
+    x = synthetic_windows(shard, seed=1000)
+    m, cores = cpu_model()
+    t0 = time.perf_counter()
     for _ in range(max(args.warmup, 1)):
-        m.predict(x[:BATCH])
-    steps = min(args.steps, 40)
+        m.predict(x[:4 * BATCH], batch_size=BATCH)
+    per_read = (time.perf_counter() - t0) / (max(args.warmup, 1) * 4 * BATCH)
+    steps = max(1, min(args.steps, int(150.0 / max(per_read * shard, 1e-9))))
     t0 = time.perf_counter()
     for _ in range(steps):
         m.predict(x, batch_size=BATCH)
     dt = time.perf_counter() - t0
-    value = steps * per_step / dt
+    value = steps * shard / dt
     line = {
         'impl': 'reference', 'metric': 'reads classified/sec', 'value': value, 'unit': 'reads/s',
         'n_gpus': args.gpus, 'steps': steps, 'warmup': args.warmup, 'ms_per_step': 1e3 * dt / steps,
         'higher_is_better': True, 'scaling': 'weak', 'vs_baseline': None, 'dtype': 'f32',
         'data': 'synthetic',
-        'config': {'workload': 'synthetic 1024-sample reads x EXP-NBD103 start model, scan_size 512 '
-                               '(1 window/read), batch 256; CPU sample of {} reads per step'.format(per_step),
-                   'batch': BATCH},
-        'cpu_baseline': {'value': value, 'unit': 'reads/s', 'cores': torch.get_num_threads(),
-                         'kind': 'port',
-                         'sample': '{} steps x {} reads; torch-CPU fp32 restatement (oracle/torch_cpu.py); '
-                                   'the reference TensorFlow/Keras stack is not installable in this '
-                                   'image'.format(steps, per_step)},
+        'config': {'workload': workload_text(shard), 'batch': BATCH, 'reads_per_step_per_gpu': shard,
+                   'windows_per_read': 1,
+                   'note': 'CPU arm: one host, all cores, the whole shard per step; steps capped at {} of the {} '
+                           'requested to keep the run within a few minutes'.format(steps, args.steps)},
+        'cpu_baseline': {'value': value, 'unit': 'reads/s', 'cores': cores, 'kind': 'port',
+                         'sample': '{} steps x {} reads; {}'.format(steps, shard, CPU_NOTE)},
         'e2e': {'value': value, 'unit': 'reads/s', 'h2d_bytes_per_step': 0, 'd2h_bytes_per_step': 0},
     }
     print(json.dumps(line), flush=True)
+
+
+def unsaturated_parity(model):
+    """The parity statistic of the metric on the committed UNSATURATED population (oracle top-1 < 0.99;
+    tests/golden/unsaturated_windows.npz, made by tests/golden/make_unsaturated.py): softmax max-abs-err
+    against the stored fp64 oracle rows."""
+    from oracle import deepbinner_oracle as orc
+    u = np.load(ROOT / 'tests' / 'golden' / 'unsaturated_windows.npz')
+    z = np.load(ROOT / 'tests' / 'golden' / 'fixture_reads.npz')
+    reads = [str(r) for r in u['reads']]
+    x = np.stack([orc.normalise(z[reads[r]][o:o + 1024]) for r, o in zip(u[MODEL + '|read'], u[MODEL + '|offset'])])
+    ref = u[MODEL + '|probs']
+    got = model.predict(x[:, :, None])
+    err = np.abs(got - ref).max(axis=1)
+    top = ref.max(axis=1)
+    return {'max_abs_err': float(err.max()), 'p99': float(np.percentile(err, 99)), 'n': int(len(x)),
+            'unsaturated': int((top < 0.99).sum()), 'top1_in_0.3_0.7': int(((top >= 0.3) & (top <= 0.7)).sum()),
+            'argmax_mismatches': int((got.argmax(axis=1) != ref.argmax(axis=1)).sum()),
+            'vs': 'fp64 oracle (oracle/deepbinner_oracle.py) rows committed in tests/golden/unsaturated_windows.npz',
+            'tolerance': 1e-3}
+
+
+def ragged_reads(n, seed):
+    rng = np.random.RandomState(seed)
+    return [np.clip(rng.normal(rng.uniform(300, 600), rng.uniform(10, 500), rng.randint(3000, 20000)),
+                    -32768, 32767).astype(np.int16) for _ in range(n)]
+
+
+def pipeline_rate(cls, batches, start, end, args_ns, n_classes, reps):
+    """reads/s of classify.classify_read_batches over `reps` passes of `batches` (list of (ids, signals))."""
+    def source():
+        for _ in range(reps):
+            for ids, sigs in batches:
+                yield ids, sigs, None
+    cls.classify_read_batches(((i, s, None) for i, s in batches), start, 1024 if start else None, end,
+                              1024 if end else None, n_classes, args_ns)          # warm-up pass
+    t0 = time.perf_counter()
+    cls.classify_read_batches(source(), start, 1024 if start else None, end, 1024 if end else None,
+                              n_classes, args_ns)
+    return reps * sum(len(i) for i, _ in batches) / (time.perf_counter() - t0)
 
 
 def main():
@@ -202,8 +299,11 @@ def main():
     ap.add_argument('--impl', default='b200', choices=['b200', 'reference'])
     ap.add_argument('--engine', default=None, choices=[None, 'fp32', 'tcgen05'])
     ap.add_argument('--shard', type=int, default=SHARD)
+    ap.add_argument('--config', default='headline', choices=['headline', 'strong'],
+                    help="'strong': 1 048 576 reads in total, split over the ranks (strong scaling)")
     ap.add_argument('--cpu-seconds', type=float, default=12.0)
     ap.add_argument('--no-cpu-baseline', action='store_true')
+    ap.add_argument('--no-configs', action='store_true', help='skip the configs[1]/[2]/[4] lines')
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == 'b200' else args.warmup
 
@@ -213,24 +313,33 @@ def main():
         run_reference(args, rank, world_size)
         return
 
+    import types
     import torch
+    from deepbinner_b200 import classify as cls
     from deepbinner_b200 import parallel, weights
     from deepbinner_b200.model import B200Model
 
     rank, local_rank, world_size = parallel.init()
     torch.cuda.set_device(local_rank)
     dev = torch.device('cuda', local_rank)
+    numa = parallel.bind_to_numa_node_of_gpu(local_rank)
 
     # the one collective of the path: broadcast the packed weights from rank 0 (NCCL)
     blob = weights.load_blob(model_path()) if rank == 0 else None
     blob = parallel.broadcast_blob(blob, dev)
     model = B200Model(blob=blob, device=local_rank, engine=args.engine)
 
+    if args.config == 'strong':
+        args.shard = 1048576 // world_size
     shard = (args.shard // BATCH) * BATCH
     n_batches = shard // BATCH
+    reads_i16 = synthetic_reads(shard, seed=1000 + rank)
     x_host = torch.empty((shard, 1024), dtype=torch.float32).pin_memory()
-    x_host.numpy()[:] = synthetic_windows(shard, seed=1000 + rank)
-    p_host = torch.empty((shard, model.n_classes), dtype=torch.float32).pin_memory()
+    xr = reads_i16.astype(np.float64)
+    mu, sg = xr.mean(axis=1, keepdims=True), xr.std(axis=1, keepdims=True)
+    sg[sg == 0] = 1.0
+    x_host.numpy()[:] = ((xr - mu) / sg).astype(np.float32)     # the same reads, z-scored (seam b1 input)
+    del xr
     d_x = x_host.to(dev)
     d_p = torch.zeros((shard, model.n_classes), dtype=torch.float32, device=dev)
     streams = [torch.cuda.Stream(device=dev) for _ in range(N_STREAMS)]
@@ -286,107 +395,155 @@ def main():
     torch.cuda.synchronize(dev)
     big_ms = s.elapsed_time(e) / max(args.steps // 4, 2)
 
-    # ---- end to end through the public host API (pinned host buffers, H2D + D2H inside) ----
-    xh = x_host.numpy()
+    # ---- end to end, headline: the fused call_batch entry on raw int16 reads in host memory ----
+    E2E_BATCH = 8192
+    packed = [PackedReads(reads_i16[a:a + E2E_BATCH]) for a in range(0, shard, E2E_BATCH)]
+
     def e2e_step():
-        return model.predict(xh, batch_size=BATCH)
+        jobs, out = [], None
+        for pk in packed:                              # up to three jobs in flight
+            jobs.append(model.call_batch_async(pk, 'start', 512, 0.5))
+            if len(jobs) == 3:
+                out = jobs.pop(0).result()
+        for j in jobs:
+            out = j.result()
+        return out
     e2e_step()
     torch.cuda.synchronize(dev)
     parallel.barrier()
     e2e_steps = max(min(args.steps, 10), 3)
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        probs_e2e = e2e_step()
+        last_calls, last_probs = e2e_step()
     torch.cuda.synchronize(dev)
     e2e_s = parallel.max_over_ranks(time.perf_counter() - t0)
     parallel.barrier()
     e2e_value = world_size * shard * e2e_steps / e2e_s
 
-    # ---- informational: BASELINE configs[1] (EXP-NBD103 start+end models, batch 256, default scan
-    # 6144 => 12 windows per read per model) through the fused call_batch entry with host buffers ----
-    native = None
-    if rank == 0:
+    # ---- end to end through seam b1 (float32 windows, pinned host) ----
+    xh = x_host.numpy()
+    model.predict(xh, batch_size=BATCH)
+    torch.cuda.synchronize(dev)
+    parallel.barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        model.predict(xh, batch_size=BATCH)
+    e2e_f32_s = parallel.max_over_ranks(time.perf_counter() - t0)
+    parallel.barrier()
+    e2e_f32 = world_size * shard * e2e_steps / e2e_f32_s
+
+    configs, n256 = None, None
+    if rank == 0 and not args.no_configs:
+        # ---- the shape the reference's call_batch really produces at seam b1: predict() with n = 256
+        #      pageable float64 windows per call (classify.py:340-361) ----
+        x64 = np.ascontiguousarray(xh[:256].astype(np.float64)[:, :, None])
+        model.predict(x64, batch_size=256)
+        t0 = time.perf_counter()
+        reps = 200
+        for _ in range(reps):
+            model.predict(x64, batch_size=256)
+        n256 = reps * 256 / (time.perf_counter() - t0)
+        # ---- BASELINE configs[1], configs[2], configs[4] through the product's batch pipeline ----
         try:
-            from deepbinner_b200 import classify as cls
-            import types
+            configs = {}
             end_model = B200Model(str(ROOT / 'deepbinner_b200' / 'models' / 'EXP-NBD103_read_ends.dbnw'),
                                   device=local_rank, engine=args.engine)
-            rng = np.random.RandomState(7)
-            reads = [np.clip(rng.normal(rng.uniform(300, 600), rng.uniform(10, 500), rng.randint(3000, 20000)),
-                             -32768, 32767).astype(np.int16) for _ in range(BATCH)]
-            ids = ['r%d' % i for i in range(BATCH)]
-            a = types.SimpleNamespace(scan_size=6144.0, batch_size=BATCH, score_diff=0.5, require_either=True,
-                                      require_start=False, require_both=False)
-            def native_step():
-                sc, _ = cls.call_batch(1024, model.n_classes, ids, reads, model, a, 'start')
-                ec, _ = cls.call_batch(1024, model.n_classes, ids, reads, end_model, a, 'end')
-                return [cls.combine_calls(x, y, a) for x, y in zip(sc, ec)]
-            native_step()
-            t0 = time.perf_counter()
-            reps = 10
-            for _ in range(reps):
-                native_step()
-            dt = time.perf_counter() - t0
-            native = {'reads_per_s': reps * BATCH / dt, 'windows_per_s': reps * BATCH * 24 / dt,
-                      'what': 'classify.call_batch x2 + combine_calls on 256 host reads (fused GPU entry, '
-                              'H2D/D2H and Python packing included)'}
-            end_model.close()
-        except Exception as e:  # noqa: BLE001
-            native = {'error': str(e)}
+            rapid = B200Model(str(ROOT / 'deepbinner_b200' / 'models' / 'SQK-RBK004_read_starts.dbnw'),
+                              device=local_rank, engine=args.engine)
+            ns = types.SimpleNamespace(scan_size=6144.0, batch_size=BATCH, score_diff=0.5, require_either=True,
+                                       require_start=False, require_both=False, verbose=False)
+            ids256 = ['r%d' % i for i in range(256)]
+            b256 = [(ids256, ragged_reads(256, 7 + k)) for k in range(4)]
+            r = pipeline_rate(cls, b256, model, end_model, ns, model.n_classes, reps=10)
+            configs['native_start_end_batch256'] = {
+                'reads_per_s': r, 'windows_per_s': 24 * r, 'windows_per_read': 24,
+                'what': 'BASELINE configs[1]: classify.classify_read_batches (both sides submitted per batch, '
+                        'batches software-pipelined) on host lists of 256 ragged int16 reads, scan 6144'}
+            ids512 = ['r%d' % i for i in range(512)]
+            b512 = [(ids512, ragged_reads(512, 11 + k)) for k in range(4)]
+            ns3 = types.SimpleNamespace(**dict(vars(ns), batch_size=512))
+            r = pipeline_rate(cls, b512, rapid, None, ns3, rapid.n_classes, reps=10)
+            configs['rapid_start_batch512'] = {
+                'reads_per_s': r, 'windows_per_s': 12 * r, 'windows_per_read': 12,
+                'what': 'BASELINE configs[2]: SQK-RBK004_read_starts, host lists of 512 ragged int16 reads, scan 6144'}
+            # configs[4] stand-in: a streaming source of already-parsed reads (the realtime loop minus the
+            # file system), rounds of 20 000 reads in batches of 4 096 packed reads, start + end models
+            pool = synthetic_reads(4096, seed=99, length=2 * (6144 + 512))
+            pk = PackedReads(pool)
+            rounds = [([None] * 4096, pk)] * 5                       # ~ one 20 000-read round
+            ns5 = types.SimpleNamespace(**dict(vars(ns), batch_size=4096))
 
-    # ---- parity statistic of the metric: softmax max-abs-err vs the CPU reference ----
-    parity = None
-    cpu = None
+            class Ids(list):                                          # read ids are not needed for the rate
+                pass
+            stream_batches = [(['s%d_%d' % (k, i) for i in range(4096)], pk) for k in range(5)]
+            r = pipeline_rate(cls, stream_batches, model, end_model, ns5, model.n_classes, reps=2)
+            configs['realtime_stream_start_end'] = {
+                'reads_per_s_per_gpu': r, 'windows_per_s_per_gpu': 24 * r, 'windows_per_read': 24,
+                'what': 'BASELINE configs[4] stand-in on ONE GPU: classify.classify_read_batches over a streaming '
+                        'source of packed synthetic reads (13 312 samples each), rounds of 20 480 reads in batches of '
+                        '4 096, start + end models, scan 6144; multiply by the GPU count (reads are sharded, no '
+                        'collective) - the 8-GPU run is `deepbinner realtime --gpus 8`'}
+            end_model.close()
+            rapid.close()
+        except Exception as ex:  # noqa: BLE001
+            configs = {'error': repr(ex)}
+
+    # ---- parity statistic of the metric + CPU baseline ----
+    parity, cpu = None, None
     if rank == 0:
-        from oracle.torch_cpu import TorchCpuModel
-        sample = np.concatenate([xh[:1024:2], xh[::max(shard // 512, 1)][:512]])
-        ref = TorchCpuModel(model_path()).predict(sample)
-        got = model.predict(sample)
-        err = np.abs(got - ref).max(axis=1)
-        parity = {'max_abs_err': float(err.max()), 'p99': float(np.percentile(err, 99)),
-                  'n': int(len(sample)), 'unsaturated': int((ref.max(axis=1) < 0.99).sum()),
-                  'argmax_mismatches': int((got.argmax(axis=1) != ref.argmax(axis=1)).sum()),
-                  'vs': 'oracle/torch_cpu.py fp32'}
+        parity = unsaturated_parity(model)
         if not args.no_cpu_baseline and world_size == 1:
             cpu = cpu_baseline(args.cpu_seconds, xh[:8192])
 
     if rank == 0:
-        peak, peak_src = measured_peaks()
+        burst, sustained, peak_src = measured_peaks()
         avg_launch_ms = ms / max(launches, 1)      # one network pass over a batch = one kernel
         achieved = FLOP_PER_WINDOW * BATCH / (avg_launch_ms * 1e-3) / 1e12
         traffic = None
         tfile = ROOT / 'profiles' / 'traffic_r01.json'
         if tfile.exists():
             traffic = json.loads(tfile.read_text()).get(model.engine)
+        terms = 1 if model.engine == 'fp32' else 3
+        if configs and 'error' not in configs:
+            kernel_wps = value / world_size            # windows/s of the kernel on one GPU (1 window per read)
+            for c in configs.values():
+                wps = c.get('windows_per_s', c.get('windows_per_s_per_gpu'))
+                c['fraction_of_kernel_rate'] = wps / kernel_wps
+                c['roofline_frac'] = wps * FLOP_PER_WINDOW / 1e12 / burst
+                if cpu is not None:
+                    c['cpu_port_reads_per_s'] = cpu['value'] / c['windows_per_read']
         line = {
             'metric': 'reads classified/sec', 'value': value, 'unit': 'reads/s',
             'n_gpus': world_size, 'steps': args.steps, 'warmup': args.warmup,
-            'ms_per_step': ms_max / args.steps, 'higher_is_better': True, 'scaling': 'weak',
+            'ms_per_step': ms_max / args.steps, 'higher_is_better': True,
+            'scaling': 'strong' if args.config == 'strong' else 'weak',
             'vs_baseline': None, 'dtype': 'f32' if model.engine == 'fp32' else 'bf16x3->f32',
             'data': 'synthetic',
             'config': {
-                'workload': 'synthetic 1M-read config (per-GPU shard of {} reads x 1024 float32 '
-                            'samples), EXP-NBD103 start model, scan_size 512 => 1 window per read, '
-                            'launches of batch {} over {} streams'.format(shard, BATCH, N_STREAMS),
-                'batch': BATCH, 'reads_per_step_per_gpu': shard, 'engine': model.engine,
-                'l2': 'inputs per step (256 MiB) exceed L2; no flush needed',
-                'large_batch_reads_per_s': shard / (big_ms * 1e-3),
-                'native_preset_batch256': native,
-                'windows_per_read': 1},
+                'workload': workload_text(shard), 'batch': BATCH, 'reads_per_step_per_gpu': shard,
+                'windows_per_read': 1, 'engine': model.engine, 'streams': N_STREAMS,
+                'l2': 'inputs per step ({} MiB fp32) exceed the 126 MB L2; no flush needed'.format(shard * 4096 >> 20),
+                'large_batch_reads_per_s': world_size * shard / (big_ms * 1e-3),
+                'numa_node_of_rank0': numa,
+                'configs': configs},
             'clocks': clocks,
-            'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': shard * 4096,
-                    'd2h_bytes_per_step': shard * model.n_classes * 4,
-                    'api': 'B200Model.predict(x_pinned_host[{},1024] float32, batch_size=256) -> '
-                           'db_predict_windows'.format(shard)},
+            'e2e': {'value': e2e_value, 'unit': 'reads/s', 'h2d_bytes_per_step': shard * 1024 * 2,
+                    'd2h_bytes_per_step': shard * (model.n_classes * 4 + 1),
+                    'api': 'B200Model.call_batch_async(packed int16 reads, side=start, scan_size=512) in jobs of '
+                           '{} reads, 3 in flight -> db_call_batch_submit_packed / db_call_batch_wait'.format(E2E_BATCH),
+                    'predict_f32': {'value': e2e_f32, 'h2d_bytes_per_step': shard * 4096,
+                                    'd2h_bytes_per_step': shard * model.n_classes * 4,
+                                    'api': 'B200Model.predict(x_pinned_host[{},1024] float32) -> db_predict_windows'.format(shard)},
+                    'predict_n256_f64': n256},
             'gpu_launches': int(launches),
-            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': peak, 'unit': 'TFLOP/s',
-                         'frac': achieved / peak, 'traffic': traffic,
+            'roofline': {'bound': 'tensor', 'achieved': achieved, 'peak': burst, 'unit': 'TFLOP/s',
+                         'frac': achieved / burst, 'frac_sustained': achieved / sustained,
+                         'peak_sustained': sustained, 'traffic': traffic,
                          # split-bf16: three tensor-core MMAs per algorithmic one
-                         'issued': achieved * (1 if model.engine == 'fp32' else 3),
-                         'issued_frac': achieved * (1 if model.engine == 'fp32' else 3) / peak,
-                         'note': 'algorithmic 33,629,952 FLOP/window x {} windows per launch / '
-                                 'average launch duration (timed region / launches; launches on {} '
-                                 'streams overlap); peak = {}'.format(BATCH, N_STREAMS, peak_src)},
+                         'issued': achieved * terms, 'issued_frac': achieved * terms / burst,
+                         'note': 'algorithmic 33,629,952 FLOP/window x {} windows per launch / average launch '
+                                 'duration (timed region / launches; launches on {} streams overlap); peak = {}'
+                                 .format(BATCH, N_STREAMS, peak_src)},
             'parity': parity,
         }
         if cpu is not None:

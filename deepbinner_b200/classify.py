@@ -220,17 +220,55 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
     input_size = start_input_size if use_start else end_input_size
     keep = int(args.scan_size) + input_size // 2
     classifications, read_id_to_fast5_file = {}, {}
-    files_done = 0
     # Each batch is parsed on native host threads (only the samples call_batch can look at - the
     # first / last scan_size + input_size/2 - are kept, which gives identical calls); the parse of
     # batch i+1 runs in the background (the C call releases the GIL) while batch i is on the GPU.
     batches = list(chunker(fast5_files, 1 if multi else args.batch_size))
     prefetcher = concurrent.futures.ThreadPoolExecutor(max_workers=1)
-    pending = prefetcher.submit(load_batch, batches[0], keep)
+    files_done = [0]
 
-    def finish(read_ids, start_job, end_job, n_files):
+    def parsed_batches():
+        pending = prefetcher.submit(load_batch, batches[0], keep)
+        for index, batch in enumerate(batches):
+            read_ids, signals, kept = pending.result()   # unreadable files are skipped (reference :135-136)
+            if index + 1 < len(batches):
+                pending = prefetcher.submit(load_batch, batches[index + 1], keep)
+            for read_id, file_index in zip(read_ids, kept):
+                read_id_to_fast5_file[read_id] = batch[file_index]
+            yield read_ids, signals, len(batch)
+
+    def progress(n_files):
+        files_done[0] += n_files
+        print_classification_progress(files_done[0] if multi else len(classifications), len(fast5_files), 'fast5s',
+                                      out_dest=out_dest)
+
+    classify_read_batches(parsed_batches(), start_model, start_input_size, end_model, end_input_size,
+                          output_size, args, classifications, print_rows=full_output, progress=progress)
+
+    prefetcher.shutdown()
+    if full_output:
+        print('', file=sys.stderr)
+        if summary_table:
+            print_summary_table(classifications)
+    return classifications, read_id_to_fast5_file
+
+
+def classify_read_batches(batches, start_model, start_input_size, end_model, end_input_size, output_size,
+                          args, classifications=None, print_rows=False, progress=None):
+    """The per-batch part of classify_fast5_files (reference classify.py:141-171) for ANY source of
+    reads: `batches` yields (read_ids, signals, tag); each batch is called on both sides, combined and
+    (print_rows) printed as TSV rows; `progress(tag)` is invoked after every batch.  -> classifications.
+    Software pipeline: the GPU jobs of batch i (start and end side, submitted back to back so that the
+    host gathers the end side while the start side computes) are in flight while the results of batch
+    i-1 are collected / printed and the source produces batch i+1.  Used by classify_fast5_files (fast5
+    parsing as the source), by `realtime`, and with a streaming read source (bench.py, config
+    'realtime streaming')."""
+    if classifications is None:
+        classifications = {}
+    use_start, use_end = start_model is not None, end_model is not None
+
+    def finish(read_ids, start_job, end_job, tag):
         """Collect the two sides of a batch, combine, print its TSV rows (reference :150-171)."""
-        nonlocal files_done
         start_calls, start_probs = start_job() if use_start else (None, None)
         end_calls, end_probs = end_job() if use_end else (None, None)
         for i, read_id in enumerate(read_ids):
@@ -239,7 +277,7 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
             else:
                 final_call = start_calls[i] if use_start else end_calls[i]
             classifications[read_id] = final_call
-            if not full_output:
+            if not print_rows:
                 continue
             row = [read_id, final_call]
             if args.verbose:
@@ -252,36 +290,21 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
                     if use_start:
                         row.append(end_calls[i])
             print('\t'.join(row))
-        files_done += n_files
-        print_classification_progress(files_done if multi else len(classifications), len(fast5_files), 'fast5s',
-                                      out_dest=out_dest)
+        if progress is not None:
+            progress(tag)
 
-    # Software pipeline over the batches: the GPU jobs of batch i (start and end side, submitted back to
-    # back so that the host gathers the end side while the start side computes) are in flight while the
-    # results of batch i-1 are collected and printed and batch i+1 is parsed.
     in_flight = None
-    for index, batch in enumerate(batches):
-        read_ids, signals, kept = pending.result()   # unreadable files are skipped (reference :135-136)
-        if index + 1 < len(batches):
-            pending = prefetcher.submit(load_batch, batches[index + 1], keep)
-        for read_id, file_index in zip(read_ids, kept):
-            read_id_to_fast5_file[read_id] = batch[file_index]
+    for read_ids, signals, tag in batches:
         start_job = submit_call_batch(start_input_size, output_size, read_ids, signals, start_model, args,
                                       'start') if use_start else None
         end_job = submit_call_batch(end_input_size, output_size, read_ids, signals, end_model, args,
                                     'end') if use_end else None
         if in_flight is not None:
             finish(*in_flight)
-        in_flight = (read_ids, start_job, end_job, len(batch))
+        in_flight = (read_ids, start_job, end_job, tag)
     if in_flight is not None:
         finish(*in_flight)
-
-    prefetcher.shutdown()
-    if full_output:
-        print('', file=sys.stderr)
-        if summary_table:
-            print_summary_table(classifications)
-    return classifications, read_id_to_fast5_file
+    return classifications
 
 
 def load_batch(fast5_batch, keep):

@@ -179,6 +179,8 @@ class PendingCalls:
 
 
 def signals_fit_int16(signals):
+    if hasattr(signals, 'samples') and hasattr(signals, 'offsets'):   # packed by the native reader
+        return signals.samples.dtype == np.int16
     for s in signals:
         s = np.asarray(s)
         if s.dtype == np.int16:
