@@ -11,6 +11,7 @@ normalisation, CNN, step merge, renormalisation and call (reference classify.py:
 `.predict` (seam b1) still works through the generic host loop.
 """
 
+import collections
 import concurrent.futures
 import os
 import pathlib
@@ -22,7 +23,7 @@ from . import hdf5_lite, weights
 from .load_fast5s import (find_all_fast5s, get_read_id_and_signal, determine_single_or_multi_fast5s,
                           read_fast5_batch, read_fast5_batch_packed)
 from .misc import print_summary_table
-from .model import B200Model, signals_fit_int16
+from .model import B200Model, ReadPointers, signals_fit_int16
 from .trim_signal import normalise
 
 
@@ -260,7 +261,8 @@ def classify_read_batches(batches, start_model, start_input_size, end_model, end
     (print_rows) printed as TSV rows; `progress(tag)` is invoked after every batch.  -> classifications.
     Software pipeline: the GPU jobs of batch i (start and end side, submitted back to back so that the
     host gathers the end side while the start side computes) are in flight while the results of batch
-    i-1 are collected / printed and the source produces batch i+1.  Used by classify_fast5_files (fast5
+    i-2 are collected / printed and the source produces batch i+1 (at most three batches, i.e. three of
+    a model's four job slots, are pending).  Used by classify_fast5_files (fast5
     parsing as the source), by `realtime`, and with a streaming read source (bench.py, config
     'realtime streaming')."""
     if classifications is None:
@@ -293,17 +295,20 @@ def classify_read_batches(batches, start_model, start_input_size, end_model, end
         if progress is not None:
             progress(tag)
 
-    in_flight = None
+    in_flight = collections.deque()       # up to two batches behind the one being submitted
+    both_b200 = all(isinstance(m, B200Model) for m in (start_model, end_model) if m is not None)
     for read_ids, signals, tag in batches:
+        if both_b200 and read_ids and not hasattr(signals, 'samples') and signals_fit_int16(signals):
+            signals = ReadPointers(signals)       # pointer / length arrays built once for both sides
         start_job = submit_call_batch(start_input_size, output_size, read_ids, signals, start_model, args,
                                       'start') if use_start else None
         end_job = submit_call_batch(end_input_size, output_size, read_ids, signals, end_model, args,
                                     'end') if use_end else None
-        if in_flight is not None:
-            finish(*in_flight)
-        in_flight = (read_ids, start_job, end_job, tag)
-    if in_flight is not None:
-        finish(*in_flight)
+        in_flight.append((read_ids, start_job, end_job, tag))
+        if len(in_flight) > PIPELINE_DEPTH:
+            finish(*in_flight.popleft())
+    while in_flight:
+        finish(*in_flight.popleft())
     return classifications
 
 
@@ -430,6 +435,7 @@ def _steps_for(input_size, scan_size):
 
 
 _CALL_NAMES = ['none'] + [str(i) for i in range(1, 128)]
+PIPELINE_DEPTH = int(os.environ.get('DEEPBINNER_B200_PIPELINE_DEPTH', '2'))   # batches in flight behind the one being submitted
 
 
 def submit_call_batch(input_size, output_size, read_ids, signals, model, args, side):

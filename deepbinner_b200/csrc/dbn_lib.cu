@@ -8,8 +8,12 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <condition_variable>
+#include <functional>
+#include <mutex>
 #include <new>
 #include <string>
+#include <thread>
 #include <vector>
 
 #include "../../include/deepbinner_b200.h"
@@ -117,6 +121,64 @@ __global__ void k_merge_call(const float* __restrict__ step_probs, int n_reads, 
 
 }  // namespace dbn
 
+// Small persistent worker pool for the host-side gather of call_batch jobs (copying the scan regions of
+// thousands of reads into pinned staging is a memory-bandwidth job that one core does at ~10 GB/s).
+class GatherPool {
+  public:
+    explicit GatherPool(int workers) {
+        for (int i = 0; i < workers; ++i) threads_.emplace_back([this, i] { run(i + 1); });
+    }
+    ~GatherPool() {
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            stop_ = true;
+        }
+        cv_.notify_all();
+        for (std::thread& t : threads_) t.join();
+    }
+    int parts() const { return static_cast<int>(threads_.size()) + 1; }
+    // fn(part) for part = 0 .. parts()-1; part 0 runs on the calling thread
+    void parallel(const std::function<void(int)>& fn) {
+        if (threads_.empty()) return fn(0);
+        {
+            std::lock_guard<std::mutex> lock(m_);
+            fn_ = &fn;
+            pending_ = static_cast<int>(threads_.size());
+            ++generation_;
+        }
+        cv_.notify_all();
+        fn(0);
+        std::unique_lock<std::mutex> lock(m_);
+        done_.wait(lock, [this] { return pending_ == 0; });
+    }
+
+  private:
+    void run(int part) {
+        int seen = 0;
+        for (;;) {
+            const std::function<void(int)>* fn;
+            {
+                std::unique_lock<std::mutex> lock(m_);
+                cv_.wait(lock, [&] { return stop_ || generation_ != seen; });
+                if (stop_) return;
+                seen = generation_;
+                fn = fn_;
+            }
+            (*fn)(part);
+            {
+                std::lock_guard<std::mutex> lock(m_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    std::vector<std::thread> threads_;
+    std::mutex m_;
+    std::condition_variable cv_, done_;
+    const std::function<void(int)>* fn_ = nullptr;
+    int pending_ = 0, generation_ = 0;
+    bool stop_ = false;
+};
+
 // =================================================================================================
 // handle
 // =================================================================================================
@@ -180,6 +242,7 @@ struct db_model {
         cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_join = nullptr;
     } jobs[kJobSlots];
     int call_chunk_windows = 2048;      // network windows per pipelined chunk of a job (DEEPBINNER_B200_CALL_CHUNK)
+    GatherPool* pool = nullptr;         // host threads of the gather (DEEPBINNER_B200_GATHER_THREADS, default 4)
 };
 
 namespace dbn {
@@ -190,7 +253,8 @@ static int grow(T** p, size_t* cap, size_t need) {
     if (*p) cudaFree(*p);
     *p = nullptr;
     *cap = 0;
-    size_t want = std::max(need, static_cast<size_t>(1) << 20);
+    // grow with 25 % head-room (batches of ragged reads differ in size; re-allocating costs milliseconds)
+    size_t want = std::max(need + need / 4, static_cast<size_t>(1) << 20);
     DBN_CUDA(cudaMalloc(reinterpret_cast<void**>(p), want));
     *cap = want;
     return 0;
@@ -202,7 +266,7 @@ static int grow_host(T** p, size_t* cap, size_t need) {
     if (*p) cudaFreeHost(*p);
     *p = nullptr;
     *cap = 0;
-    size_t want = std::max(need, static_cast<size_t>(1) << 20);
+    size_t want = std::max(need + need / 4, static_cast<size_t>(1) << 20);
     DBN_CUDA(cudaMallocHost(reinterpret_cast<void**>(p), want));
     *cap = want;
     return 0;
@@ -275,9 +339,12 @@ using namespace dbn;
 // i.  submit() returns once everything is enqueued - the caller's buffers are no longer referenced - and
 // wait() blocks on the job's completion event and hands the results out.  Up to kJobSlots jobs per
 // handle may be in flight (next batch, or several jobs queued by a driver loop).
+// `pinned_base`: non-NULL when the reads are consecutive in one PINNED (page-locked / registered) host buffer
+// starting there (packed variant): chunks whose reads all lie inside the scan region are then copied
+// straight from the caller's buffer, without the staging pass.
 template <typename GetRead>
 static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int scan_size, double score_diff,
-                      int* job_out) {
+                      int* job_out, const int16_t* pinned_base = nullptr) {
     if (!m) return fail(DBN_EINVAL, "call_batch: model is NULL");
     if (!job_out) return fail(DBN_EINVAL, "call_batch: job is NULL");
     if (n_reads < 0) return fail(DBN_EINVAL, "call_batch: n_reads < 0");
@@ -301,8 +368,9 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
     }
     DBN_CUDA(cudaSetDevice(m->device));
     const int64_t region_max = static_cast<int64_t>(scan_size) + m->input_size / 2;
-    const int chunk = std::max(1, m->call_chunk_windows / steps);   // reads per chunk
-    const int nchunks = (n_reads + chunk - 1) / chunk;
+    const int chunk_max = std::max(1, m->call_chunk_windows / steps);   // reads per chunk, at most
+    const int nchunks = (n_reads + chunk_max - 1) / chunk_max;
+    const int chunk = (n_reads + nchunks - 1) / std::max(nchunks, 1);   // balanced chunks
     const size_t nc = m->n_classes;
     // sizes: regions are bounded by region_max per read
     int64_t bound = 0;
@@ -324,27 +392,47 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
     if ((rc = grow(&J.d_step, &J.d_step_bytes, sizeof(float) * nc * n_reads * steps))) return rc;
     if ((rc = grow(&J.d_probs, &J.d_probs_bytes, sizeof(float) * nc * n_reads))) return rc;
     if ((rc = grow(&J.d_calls, &J.d_calls_bytes, static_cast<size_t>(n_reads)))) return rc;
+    // (no cross-stream dependency: the chunks of consecutive jobs simply queue behind each other on the two
+    // streams, so the first copy of this job runs under the last kernel of the previous one)
     DBN_CUDA(cudaEventRecord(J.ev_start, m->streams[0]));
-    DBN_CUDA(cudaStreamWaitEvent(m->streams[1], J.ev_start, 0));
     int64_t base = 0;   // samples gathered so far
     for (int c = 0; c < nchunks; ++c) {
         const int r0 = c * chunk, cnt = std::min(chunk, n_reads - r0);
         cudaStream_t st = m->streams[c & 1];
         int64_t* offs = J.h_offsets + r0 + c;   // cnt + 1 entries, relative to this chunk's samples
         int64_t total = 0;
+        bool whole = pinned_base != nullptr;    // every read of the chunk is used whole
+        const int16_t* first = nullptr;
         for (int i = 0; i < cnt; ++i) {
             const int16_t* p;
             int64_t len;
             get_read(r0 + i, &p, &len);
-            const int64_t r = std::min(len, region_max);
+            if (i == 0) first = p;
+            whole = whole && len <= region_max && p == first + total;
             offs[i] = total;
-            if (r > 0) std::memcpy(J.h_samples + base + total, p + (side == DBN_SIDE_START ? 0 : len - r), sizeof(int16_t) * r);
-            total += r;
+            total += std::min(len, region_max);
         }
         offs[cnt] = total;
+        const int16_t* h_src = J.h_samples + base;
+        auto copy_reads = [&](int part) {   // reads [lo, hi) of the chunk
+            const int parts = total >= (1 << 19) ? m->pool->parts() : 1;
+            if (part >= parts) return;
+            const int lo = static_cast<int>(static_cast<int64_t>(cnt) * part / parts);
+            const int hi = static_cast<int>(static_cast<int64_t>(cnt) * (part + 1) / parts);
+            for (int i = lo; i < hi; ++i) {
+                const int16_t* p;
+                int64_t len;
+                get_read(r0 + i, &p, &len);
+                const int64_t r = offs[i + 1] - offs[i];
+                if (r > 0)
+                    std::memcpy(J.h_samples + base + offs[i], p + (side == DBN_SIDE_START ? 0 : len - r), sizeof(int16_t) * r);
+            }
+        };
+        if (whole && total > 0) h_src = first;       // zero-copy: DMA straight from the caller's pinned buffer
+        else if (total >= (1 << 19)) m->pool->parallel(copy_reads);
+        else copy_reads(0);
         if (total > 0)
-            DBN_CUDA(cudaMemcpyAsync(J.d_samples + base, J.h_samples + base, sizeof(int16_t) * total,
-                                     cudaMemcpyHostToDevice, st));
+            DBN_CUDA(cudaMemcpyAsync(J.d_samples + base, h_src, sizeof(int16_t) * total, cudaMemcpyHostToDevice, st));
         DBN_CUDA(cudaMemcpyAsync(J.d_offsets + r0 + c, offs, sizeof(int64_t) * (cnt + 1), cudaMemcpyHostToDevice, st));
         rc = launch_call_batch(m, J.d_samples + base, J.d_offsets + r0 + c, cnt, side, steps, score_diff,
                                J.d_step + static_cast<size_t>(r0) * steps * nc, J.d_probs + r0 * nc, J.d_calls + r0, st);
@@ -354,9 +442,8 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
         DBN_CUDA(cudaMemcpyAsync(J.h_calls + r0, J.d_calls + r0, static_cast<size_t>(cnt), cudaMemcpyDeviceToHost, st));
         base += total;
     }
-    // completion: stream 0 joins stream 1, then records the job's stop event
+    // completion: one event per stream; wait() synchronises on both
     DBN_CUDA(cudaEventRecord(J.ev_join, m->streams[1]));
-    DBN_CUDA(cudaStreamWaitEvent(m->streams[0], J.ev_join, 0));
     DBN_CUDA(cudaEventRecord(J.ev_stop, m->streams[0]));
     J.busy = true;
     return DBN_OK;
@@ -406,6 +493,7 @@ void db_destroy(db_model* m) {
     }
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     if (m->ev_stop) cudaEventDestroy(m->ev_stop);
+    delete m->pool;
     delete m;
 }
 
@@ -461,6 +549,9 @@ int db_create(const void* weights_blob, size_t blob_bytes, int device, db_model*
             DBN_CUDA(cudaEventCreateWithFlags(&j.ev_join, cudaEventDisableTiming));
         }
         if (const char* v = getenv("DEEPBINNER_B200_CALL_CHUNK")) m->call_chunk_windows = std::max(1, atoi(v));
+        int gather_threads = 4;
+        if (const char* v = getenv("DEEPBINNER_B200_GATHER_THREADS")) gather_threads = std::max(1, std::min(64, atoi(v)));
+        m->pool = new GatherPool(gather_threads - 1);
         return 0;
     }();
     if (rc) {
@@ -597,8 +688,15 @@ int db_call_batch_submit(db_model* m, const int16_t* const* signals, const int64
 int db_call_batch_submit_packed(db_model* m, const int16_t* samples, const int64_t* offsets, int n_reads, int side,
                                 int scan_size, double score_diff, int* job) {
     if (n_reads > 0 && (!samples || !offsets)) return fail(DBN_EINVAL, "call_batch: NULL buffer");
+    // a page-locked caller buffer is read by the copy engine directly (see the header for the lifetime rule)
+    const int16_t* pinned = nullptr;
+    if (m && n_reads > 0) {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, samples) == cudaSuccess && attr.type == cudaMemoryTypeHost) pinned = samples;
+        cudaGetLastError();
+    }
     return submit_job(m, [&](int i, const int16_t** p, int64_t* len) { *p = samples + offsets[i]; *len = offsets[i + 1] - offsets[i]; },
-                      n_reads, side, scan_size, score_diff, job);
+                      n_reads, side, scan_size, score_diff, job, pinned);
 }
 
 int db_call_batch_wait(db_model* m, int job, float* probs, int8_t* calls) {
@@ -610,6 +708,7 @@ int db_call_batch_wait(db_model* m, int job, float* probs, int8_t* calls) {
     if (!probs || !calls) return fail(DBN_EINVAL, "call_batch: NULL buffer");
     DBN_CUDA(cudaSetDevice(m->device));
     DBN_CUDA(cudaEventSynchronize(J.ev_stop));
+    DBN_CUDA(cudaEventSynchronize(J.ev_join));
     std::memcpy(probs, J.h_probs, sizeof(float) * m->n_classes * J.n_reads);
     std::memcpy(calls, J.h_calls, static_cast<size_t>(J.n_reads));
     DBN_CUDA(cudaEventElapsedTime(&m->last_ms, J.ev_start, J.ev_stop));

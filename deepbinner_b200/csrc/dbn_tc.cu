@@ -87,7 +87,7 @@ constexpr int kSmemAct1 = kActBytes;
 constexpr int kSmemWbuf = 2 * kActBytes;
 constexpr int kSmemPrm = kSmemWbuf + kWbufBytes;
 constexpr int kSmemBar = kSmemPrm + kPrmFloats * 4;   // mbarriers, tmem pointer, reduction scratch
-constexpr int kTcSmemBytes = kSmemBar + 384;   // [0,72) mbarriers, 96 TMEM pointer, [128,320) reduction scratch, [320,384) joint rings
+constexpr int kTcSmemBytes = kSmemBar + 576;   // [0,72) mbarriers, 96 TMEM pointer, [128,512) reduction scratch, [512,576) joint rings
 static_assert(kTcSmemBytes <= 232448, "shared memory budget");
 constexpr int kTmemCols = 512;
 constexpr int kTmemWindowCols = 256;
@@ -876,7 +876,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t bar_epi[2] = {bar0 + 48, bar0 + 56};
     const uint32_t bar_final = bar0 + 64;
     // joint phase: rings of 4 (the MMA issuer runs at most 3 epilogues ahead, see TcJob::need)
-    const uint32_t bar_jmma = bar0 + 320, bar_jepi = bar0 + 352;   // + 8 * (eseq & 3)
+    const uint32_t bar_jmma = bar0 + 512, bar_jepi = bar0 + 544;   // + 8 * (eseq & 3)
     // joint phase weights: three whole-job slots (the normal weight buffer and two halves of the upper
     // part of window 1's ACT region, which is dead from conv1d_8 on), so that the loader runs two
     // jobs ahead of the MMA issuer and independent jobs follow each other without a weight bubble
@@ -903,6 +903,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     Conv1Params c1;
     WindowInput in[2] = {};
     float xv[2][3];
+    int raw[2][3];            // call mode: the thread's raw samples of both windows (0 outside the slice)
+    WindowGeom geom[2] = {};
     if (is_epi) {
         const int etid = static_cast<int>(threadIdx.x) - kEpiWarp0 * 32;
         load_conv1_params(P, etid, c1);
@@ -912,6 +914,27 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (x) in[w].x = x + static_cast<size_t>(win[w]) * kInputSize;
                 else in[w].xd = xd + static_cast<size_t>(win[w]) * kInputSize;
                 fetch_window_inputs(in[w], etid, xv[w]);
+            }
+        } else {
+            // fused call_batch (classify.py:342-357): the thread's samples of BOTH windows are requested
+            // here, so that the two dependent global latencies (offsets, samples) overlap the set-up
+            int64_t off[2], len[2];
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int read = win[w] % n_reads;
+                off[w] = __ldg(offsets + read);
+                len[w] = __ldg(offsets + read + 1) - off[w];
+            }
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                geom[w] = window_geometry(static_cast<int>(len[w]), win[w] / n_reads, side);
+                const int16_t* region = samples + off[w] + geom[w].a;
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = etid + k * kEpiThreads - geom[w].dst;   // index into the slice
+                    raw[w][k] = (etid + k * kEpiThreads < kInputSize && i >= 0 && i < geom[w].n)
+                                    ? static_cast<int>(__ldg(region + i)) : 0;
+                }
             }
         }
     }
@@ -951,34 +974,47 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         if (trace && blockIdx.x == 0 && tid == 0) trace[31 * 32 + 0] = clock64();
         for (int i = tid; i < P.prm_floats / 4; i += kEpiThreads)
             reinterpret_cast<float4*>(smem + kSmemPrm)[i] = __ldg(reinterpret_cast<const float4*>(P.prm) + i);
+        if (kCallMode) {
+            // z-score of both windows (trim_signal.py:61-69): exact integer sums over the slices, reduced
+            // over the 384 threads (samples outside a slice are 0 and do not count), mean / population
+            // stdev in double as numpy computes them
+            long long s[4] = {0, 0, 0, 0};
+#pragma unroll
+            for (int w = 0; w < 2; ++w)
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    s[2 * w] += raw[w][k];
+                    s[2 * w + 1] += static_cast<long long>(raw[w][k]) * raw[w][k];
+                }
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
+            long long* red = reinterpret_cast<long long*>(smem + kSmemBar + 128);   // [12 warps][4]: 384 B
+            if ((tid & 31) == 0) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) red[ewarp * 4 + q] = s[q];
+            }
+            epi_bar_sync();
+#pragma unroll
+            for (int q = 0; q < 4; ++q) s[q] = 0;
+            for (int i = 0; i < kEpiWarps; ++i)
+#pragma unroll
+                for (int q = 0; q < 4; ++q) s[q] += red[i * 4 + q];
+#pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                double mean = 0.0, stdev = 0.0;
+                if (geom[w].n > 0) zscore_params(s[2 * w], s[2 * w + 1], geom[w].n, &mean, &stdev);
+#pragma unroll
+                for (int k = 0; k < 3; ++k) {
+                    const int i = tid + k * kEpiThreads - geom[w].dst;
+                    const bool inside = tid + k * kEpiThreads < kInputSize && i >= 0 && i < geom[w].n;
+                    const double d = static_cast<double>(raw[w][k]) - mean;
+                    xv[w][k] = inside ? static_cast<float>(stdev > 0.0 ? d / stdev : d) : 0.f;
+                }
+            }
+        }
 #pragma unroll
         for (int w = 0; w < 2; ++w) {
-            if (kCallMode) {
-                const int step = win[w] / n_reads, read = win[w] % n_reads;
-                const int64_t off = offsets[read];
-                in[w].region = samples + off;
-                in[w].g = window_geometry(static_cast<int>(offsets[read + 1] - off), step, side);
-                // exact integer sums over the slice, reduced over the 384 threads
-                long long s1 = 0, s2 = 0;
-                for (int i = tid; i < in[w].g.n; i += kEpiThreads) {
-                    const long long v = in[w].region[in[w].g.a + i];
-                    s1 += v;
-                    s2 += v * v;
-                }
-                for (int o = 16; o > 0; o >>= 1) {
-                    s1 += __shfl_xor_sync(0xffffffffu, s1, o);
-                    s2 += __shfl_xor_sync(0xffffffffu, s2, o);
-                }
-                long long* red = reinterpret_cast<long long*>(smem + kSmemBar + 128);
-                epi_bar_sync();   // previous window's readers are done with the scratch
-                if ((tid & 31) == 0) { red[ewarp] = s1; red[12 + ewarp] = s2; }
-                epi_bar_sync();
-                s1 = 0; s2 = 0;
-                for (int i = 0; i < kEpiWarps; ++i) { s1 += red[i]; s2 += red[12 + i]; }
-                in[w].mean = 0.0; in[w].stdev = 0.0;
-                if (in[w].g.n > 0) zscore_params(s1, s2, in[w].g.n, &in[w].mean, &in[w].stdev);
-                fetch_window_inputs(in[w], tid, xv[w]);
-            }
             conv1_stage(c1, xv[w][0], xv[w][1], xv[w][2], sbase + (w ? kSmemAct1 : kSmemAct0),
                         smem + (w ? kSmemAct1 : kSmemAct0), tid);
             fence_proxy_async();

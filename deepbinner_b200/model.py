@@ -123,15 +123,13 @@ class B200Model:
             if len(rows) == n:
                 rows = None
         else:
-            n = len(signals)
-            arrays = [s if (type(s) is np.ndarray and s.dtype == np.int16 and s.flags.c_contiguous)
-                      else np.ascontiguousarray(s, dtype=np.int16) for s in signals]
-            ptrs = np.fromiter((a.ctypes.data for a in arrays), dtype=np.uint64, count=n)
-            lens = np.fromiter((a.size for a in arrays), dtype=np.int64, count=n)
-            rc = self._lib.db_call_batch_submit(self._handle, _native.as_ptr(ptrs), _native.as_ptr(lens), n,
-                                                side_code, int(scan_size), float(score_diff), ctypes.byref(job))
+            if not isinstance(signals, ReadPointers):
+                signals = ReadPointers(signals)
+            n = signals.n
+            rc = self._lib.db_call_batch_submit(self._handle, _native.as_ptr(signals.ptrs), _native.as_ptr(signals.lens),
+                                                n, side_code, int(scan_size), float(score_diff), ctypes.byref(job))
         _native.check(rc, 'db_call_batch_submit')
-        return PendingCalls(self, job.value, n, rows)
+        return PendingCalls(self, job.value, n, rows, keep=signals)
 
     # -- device-resident entry points (used by bench.py for kernel-only timing) --------------------
     def predict_device(self, d_x_ptr, n, d_probs_ptr, stream_ptr=0):
@@ -158,11 +156,28 @@ class B200Model:
         return int(self._lib.db_kernel_launches(self._handle))
 
 
+class ReadPointers:
+    """A list of 1-D integer signals as what db_call_batch_submit takes: an array of int16 pointers and
+    an array of lengths (built once per batch, shared by the start and the end model's jobs).  Keeps the
+    arrays alive."""
+
+    def __init__(self, signals):
+        self.arrays = [s if (type(s) is np.ndarray and s.dtype == np.int16 and s.flags.c_contiguous)
+                       else np.ascontiguousarray(s, dtype=np.int16) for s in signals]
+        self.n = len(self.arrays)
+        self.ptrs = np.fromiter((a.ctypes.data for a in self.arrays), dtype=np.uint64, count=self.n)
+        self.lens = np.fromiter((a.size for a in self.arrays), dtype=np.int64, count=self.n)
+
+    def __len__(self):
+        return self.n
+
+
 class PendingCalls:
     """An in-flight call_batch job of a B200Model (db_call_batch_submit .. db_call_batch_wait)."""
 
-    def __init__(self, model, job, n, rows):
+    def __init__(self, model, job, n, rows, keep=None):
         self._model, self._job, self._n, self._rows = model, job, n, rows
+        self._keep = keep      # page-locked inputs are read by the copy engine until the job completes
         self._out = None
 
     def result(self):
@@ -175,10 +190,13 @@ class PendingCalls:
             if self._rows is not None:
                 calls, probs = calls[self._rows], probs[self._rows]
             self._out = (calls, probs)
+            self._keep = None
         return self._out
 
 
 def signals_fit_int16(signals):
+    if isinstance(signals, ReadPointers):
+        return True
     if hasattr(signals, 'samples') and hasattr(signals, 'offsets'):   # packed by the native reader
         return signals.samples.dtype == np.int16
     for s in signals:

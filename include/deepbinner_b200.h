@@ -122,6 +122,9 @@ DBN_API int db_call_batch(db_model *model, const int16_t *samples, const int64_t
  * be waited for exactly once.  db_call_batch == submit_packed + wait.
  *   db_call_batch_submit:        read i = signals[i][0 .. lengths[i])   (ragged host arrays)
  *   db_call_batch_submit_packed: read i = samples[offsets[i] .. offsets[i+1])
+ * Exception to "no longer references the caller's buffers": if `samples` of the packed variant is
+ * page-locked memory (cudaHostAlloc / cudaHostRegister), reads that fit the scan region whole are copied
+ * to the device straight from it (no staging pass) - such a buffer must stay unchanged until wait().
  */
 DBN_API int db_call_batch_submit(db_model *model, const int16_t *const *signals, const int64_t *lengths,
                                  int n_reads, int side, int scan_size, double score_diff, int *job);
