@@ -457,6 +457,38 @@ def main():
     parallel.barrier()
     e2e_f32 = world_size * shard * e2e_steps / e2e_f32_s
 
+    # ---- BASELINE configs[4] stand-in on EVERY rank: `realtime` without the file system - a streaming source
+    #      of already-parsed reads, rounds of 20 480 reads per GPU in batches of 4 096 packed reads, start + end
+    #      models, scan 6144, through the product's batch pipeline; whole-job rate = reads of all ranks / slowest rank
+    stream_cfg = None
+    if not args.no_configs:
+        end_all = B200Model(str(ROOT / 'deepbinner_b200' / 'models' / 'EXP-NBD103_read_ends.dbnw'),
+                            device=local_rank, engine=args.engine)
+        ns5 = types.SimpleNamespace(scan_size=6144.0, batch_size=4096, score_diff=0.5, require_either=True,
+                                    require_start=False, require_both=False, verbose=False)
+        pool = torch.from_numpy(synthetic_reads(4096, seed=99 + rank, length=2 * (6144 + 512))).pin_memory().numpy()
+        pk = PackedReads(pool)
+        stream_batches = [(['s%d_%d' % (k, i) for i in range(4096)], pk) for k in range(5)]
+        pipeline_rate(cls, stream_batches, model, end_all, ns5, model.n_classes, reps=1)         # warm-up (all job slots)
+        torch.cuda.synchronize(dev)
+        parallel.barrier()
+        t0 = time.perf_counter()
+        rounds = 3
+        for _ in range(rounds):
+            cls.classify_read_batches(((i, sg, None) for i, sg in stream_batches), model, 1024, end_all, 1024,
+                                      model.n_classes, ns5)
+        stream_s = parallel.max_over_ranks(time.perf_counter() - t0)
+        parallel.barrier()
+        r5 = world_size * rounds * 5 * 4096 / stream_s
+        stream_cfg = {
+            'reads_per_s': r5, 'windows_per_s': 24 * r5, 'windows_per_read': 24, 'n_gpus': world_size,
+            'h2d_bytes_per_read': 2 * 2 * (6144 + 512), 'rounds': rounds, 'reads_per_round_per_gpu': 5 * 4096,
+            'what': 'BASELINE configs[4] stand-in: classify.classify_read_batches (the batch pipeline of `realtime`) over a '
+                    'streaming source of packed int16 reads (13 312 samples each, pinned host memory) on every GPU - reads '
+                    'are sharded, no collective; rounds of 20 480 reads per GPU in batches of 4 096, start + end models, '
+                    'scan 6144; whole-job rate = reads of all ranks / time of the slowest rank'}
+        end_all.close()
+
     configs, n256 = None, None
     if rank == 0 and not args.no_configs:
         # ---- the shape the reference's call_batch really produces at seam b1: predict() with n = 256
@@ -491,25 +523,9 @@ def main():
             configs['rapid_start_batch512'] = {
                 'reads_per_s': r, 'windows_per_s': 12 * r, 'windows_per_read': 12,
                 'what': 'BASELINE configs[2]: SQK-RBK004_read_starts, host lists of 512 ragged int16 reads, scan 6144'}
-            # configs[4] stand-in: a streaming source of already-parsed reads (the realtime loop minus the
-            # file system), rounds of 20 000 reads in batches of 4 096 packed reads, start + end models
-            pool = synthetic_reads(4096, seed=99, length=2 * (6144 + 512))
-            pk = PackedReads(pool)
-            rounds = [([None] * 4096, pk)] * 5                       # ~ one 20 000-read round
-            ns5 = types.SimpleNamespace(**dict(vars(ns), batch_size=4096))
-
-            class Ids(list):                                          # read ids are not needed for the rate
-                pass
-            stream_batches = [(['s%d_%d' % (k, i) for i in range(4096)], pk) for k in range(5)]
-            r = pipeline_rate(cls, stream_batches, model, end_model, ns5, model.n_classes, reps=2)
-            configs['realtime_stream_start_end'] = {
-                'reads_per_s_per_gpu': r, 'windows_per_s_per_gpu': 24 * r, 'windows_per_read': 24,
-                'what': 'BASELINE configs[4] stand-in on ONE GPU: classify.classify_read_batches over a streaming '
-                        'source of packed synthetic reads (13 312 samples each), rounds of 20 480 reads in batches of '
-                        '4 096, start + end models, scan 6144; multiply by the GPU count (reads are sharded, no '
-                        'collective) - the 8-GPU run is `deepbinner realtime --gpus 8`'}
             end_model.close()
             rapid.close()
+            configs['realtime_stream_start_end'] = stream_cfg
         except Exception as ex:  # noqa: BLE001
             configs = {'error': repr(ex)}
 
@@ -532,7 +548,7 @@ def main():
         if configs and 'error' not in configs:
             kernel_wps = value / world_size            # windows/s of the kernel on one GPU (1 window per read)
             for c in configs.values():
-                wps = c.get('windows_per_s', c.get('windows_per_s_per_gpu'))
+                wps = c['windows_per_s'] / c.get('n_gpus', 1)
                 c['fraction_of_kernel_rate'] = wps / kernel_wps
                 c['roofline_frac'] = wps * FLOP_PER_WINDOW / 1e12 / burst
                 if cpu is not None:

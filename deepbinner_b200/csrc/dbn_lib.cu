@@ -239,8 +239,12 @@ struct db_model {
         size_t d_probs_bytes = 0;
         int8_t* d_calls = nullptr;
         size_t d_calls_bytes = 0;
-        cudaEvent_t ev_start = nullptr, ev_stop = nullptr, ev_join = nullptr;
+        cudaEvent_t ev_start = nullptr, ev_stop = nullptr;
+        cudaEvent_t ev_done[3] = {nullptr, nullptr, nullptr};   // one per job stream
     } jobs[kJobSlots];
+    static constexpr int kJobStreams = 3;
+    cudaStream_t job_streams[kJobStreams] = {nullptr, nullptr, nullptr};   // chunks of call_batch jobs rotate over these
+    unsigned job_chunk_counter = 0;
     int call_chunk_windows = 2048;      // network windows per pipelined chunk of a job (DEEPBINNER_B200_CALL_CHUNK)
     GatherPool* pool = nullptr;         // host threads of the gather (DEEPBINNER_B200_GATHER_THREADS, default 4)
 };
@@ -335,7 +339,7 @@ using namespace dbn;
 // for every chunk the host gathers the scan regions (the only samples call_batch ever looks at: the
 // first / last scan_size + input_size/2 of each read, classify.py:337-349) into the job's pinned
 // staging and enqueues H2D copy -> network kernel -> merge/call kernel -> D2H of the results on one of
-// two streams (chunks alternate), so the gather and the copy of chunk i+1 run under the kernels of chunk
+// three streams (chunks rotate), so the gather and the copy of chunk i+1 run under the kernels of chunk
 // i.  submit() returns once everything is enqueued - the caller's buffers are no longer referenced - and
 // wait() blocks on the job's completion event and hands the results out.  Up to kJobSlots jobs per
 // handle may be in flight (next batch, or several jobs queued by a driver loop).
@@ -392,13 +396,15 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
     if ((rc = grow(&J.d_step, &J.d_step_bytes, sizeof(float) * nc * n_reads * steps))) return rc;
     if ((rc = grow(&J.d_probs, &J.d_probs_bytes, sizeof(float) * nc * n_reads))) return rc;
     if ((rc = grow(&J.d_calls, &J.d_calls_bytes, static_cast<size_t>(n_reads)))) return rc;
-    // (no cross-stream dependency: the chunks of consecutive jobs simply queue behind each other on the two
-    // streams, so the first copy of this job runs under the last kernel of the previous one)
-    DBN_CUDA(cudaEventRecord(J.ev_start, m->streams[0]));
+    // (no cross-stream dependency: the chunks of consecutive jobs simply queue behind each other on the job
+    // streams, so the first copy of this job runs under the last kernels of the previous one)
+    DBN_CUDA(cudaEventRecord(J.ev_start, m->job_streams[m->job_chunk_counter % db_model::kJobStreams]));
     int64_t base = 0;   // samples gathered so far
+    cudaStream_t last_stream = m->job_streams[0];
     for (int c = 0; c < nchunks; ++c) {
         const int r0 = c * chunk, cnt = std::min(chunk, n_reads - r0);
-        cudaStream_t st = m->streams[c & 1];
+        cudaStream_t st = m->job_streams[m->job_chunk_counter++ % db_model::kJobStreams];
+        last_stream = st;
         int64_t* offs = J.h_offsets + r0 + c;   // cnt + 1 entries, relative to this chunk's samples
         int64_t total = 0;
         bool whole = pinned_base != nullptr;    // every read of the chunk is used whole
@@ -442,9 +448,9 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
         DBN_CUDA(cudaMemcpyAsync(J.h_calls + r0, J.d_calls + r0, static_cast<size_t>(cnt), cudaMemcpyDeviceToHost, st));
         base += total;
     }
-    // completion: one event per stream; wait() synchronises on both
-    DBN_CUDA(cudaEventRecord(J.ev_join, m->streams[1]));
-    DBN_CUDA(cudaEventRecord(J.ev_stop, m->streams[0]));
+    // completion: one event per stream; wait() synchronises on all of them
+    for (int i = 0; i < db_model::kJobStreams; ++i) DBN_CUDA(cudaEventRecord(J.ev_done[i], m->job_streams[i]));
+    DBN_CUDA(cudaEventRecord(J.ev_stop, last_stream));
     J.busy = true;
     return DBN_OK;
 }
@@ -485,8 +491,11 @@ void db_destroy(db_model* m) {
         cudaFree(j.d_calls);
         if (j.ev_start) cudaEventDestroy(j.ev_start);
         if (j.ev_stop) cudaEventDestroy(j.ev_stop);
-        if (j.ev_join) cudaEventDestroy(j.ev_join);
+        for (cudaEvent_t e : j.ev_done)
+            if (e) cudaEventDestroy(e);
     }
+    for (cudaStream_t st : m->job_streams)
+        if (st) cudaStreamDestroy(st);
     for (int i = 0; i < 2; ++i) {
         if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
         if (m->h_out[i]) cudaFreeHost(m->h_out[i]);
@@ -546,8 +555,9 @@ int db_create(const void* weights_blob, size_t blob_bytes, int device, db_model*
         for (db_model::CallJob& j : m->jobs) {
             DBN_CUDA(cudaEventCreate(&j.ev_start));
             DBN_CUDA(cudaEventCreate(&j.ev_stop));
-            DBN_CUDA(cudaEventCreateWithFlags(&j.ev_join, cudaEventDisableTiming));
+            for (cudaEvent_t& e : j.ev_done) DBN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
+        for (cudaStream_t& st : m->job_streams) DBN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
         if (const char* v = getenv("DEEPBINNER_B200_CALL_CHUNK")) m->call_chunk_windows = std::max(1, atoi(v));
         int gather_threads = 4;
         if (const char* v = getenv("DEEPBINNER_B200_GATHER_THREADS")) gather_threads = std::max(1, std::min(64, atoi(v)));
@@ -707,8 +717,8 @@ int db_call_batch_wait(db_model* m, int job, float* probs, int8_t* calls) {
     if (J.n_reads == 0) return DBN_OK;
     if (!probs || !calls) return fail(DBN_EINVAL, "call_batch: NULL buffer");
     DBN_CUDA(cudaSetDevice(m->device));
+    for (cudaEvent_t e : J.ev_done) DBN_CUDA(cudaEventSynchronize(e));
     DBN_CUDA(cudaEventSynchronize(J.ev_stop));
-    DBN_CUDA(cudaEventSynchronize(J.ev_join));
     std::memcpy(probs, J.h_probs, sizeof(float) * m->n_classes * J.n_reads);
     std::memcpy(calls, J.h_calls, static_cast<size_t>(J.n_reads));
     DBN_CUDA(cudaEventElapsedTime(&m->last_ms, J.ev_start, J.ev_stop));

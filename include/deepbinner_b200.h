@@ -116,7 +116,7 @@ DBN_API int db_call_batch(db_model *model, const int16_t *samples, const int64_t
  * The same call split in two, so that the host can overlap its own work with the GPU's (prepare the
  * next batch, submit the other model's side of this batch, format results): submit() gathers the scan
  * regions chunk by chunk into pinned staging and enqueues copy -> kernels -> copy-back for every chunk
- * on two alternating streams; it returns as soon as everything is enqueued and no longer references the
+ * on three rotating streams; it returns as soon as everything is enqueued and no longer references the
  * caller's buffers.  wait() blocks until the job is complete and fills probs / calls as db_call_batch
  * does.  *job receives a small index; up to 4 jobs per handle may be in flight; every submitted job must
  * be waited for exactly once.  db_call_batch == submit_packed + wait.
