@@ -80,6 +80,8 @@ def load_library():
                                                 ctypes.c_int, ctypes.c_int, ctypes.c_int,
                                                 ctypes.c_double, ctypes.c_void_p, ctypes.c_void_p,
                                                 ctypes.c_void_p, ctypes.c_void_p]),
+        'db_zlib_inflate': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_int64, ctypes.c_void_p, ctypes.c_int64,
+                                           ctypes.POINTER(ctypes.c_int64), ctypes.c_int]),
         'db_fast5_read': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p,
                                          ctypes.c_int64, ctypes.POINTER(ctypes.c_int64)]),
         'db_fast5_list_root': (ctypes.c_int, [ctypes.c_char_p, ctypes.c_char_p, ctypes.c_int64,
@@ -89,6 +91,9 @@ def load_library():
                                                ctypes.POINTER(ctypes.c_void_p)]),
         'db_fast5_batch_read_reads': (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int,
                                                      ctypes.c_int, ctypes.c_int64,
+                                                     ctypes.POINTER(ctypes.c_void_p)]),
+        'db_fast5_batch_read_sides': (ctypes.c_int, [ctypes.POINTER(ctypes.c_char_p), ctypes.c_int,
+                                                     ctypes.c_int, ctypes.c_int64, ctypes.c_int,
                                                      ctypes.POINTER(ctypes.c_void_p)]),
         'db_fast5_batch_rows': (ctypes.c_int, [ctypes.c_void_p, ctypes.POINTER(ctypes.c_int64),
                                                ctypes.POINTER(ctypes.c_void_p)]),
@@ -122,8 +127,8 @@ EXPORTED_SYMBOLS = ['db_abi_version', 'db_last_error', 'db_create', 'db_destroy'
                     'db_predict_windows_f64', 'db_predict_windows_device', 'db_call_batch',
                     'db_call_batch_submit', 'db_call_batch_submit_packed', 'db_call_batch_wait',
                     'db_call_batch_device', 'db_last_gpu_ms', 'db_kernel_launches',
-                    'db_tc_num_jobs', 'db_tc_job_table', 'db_tc_packed', 'db_tc_debug_dump', 'db_tc_trace', 'db_fast5_read',
-                    'db_fast5_list_root', 'db_fast5_batch_read', 'db_fast5_batch_read_reads', 'db_fast5_batch_rows',
+                    'db_tc_num_jobs', 'db_tc_job_table', 'db_tc_packed', 'db_tc_debug_dump', 'db_tc_trace', 'db_zlib_inflate', 'db_fast5_read',
+                    'db_fast5_list_root', 'db_fast5_batch_read', 'db_fast5_batch_read_reads', 'db_fast5_batch_read_sides', 'db_fast5_batch_rows',
                     'db_fast5_batch_get',
                     'db_fast5_batch_free']
 

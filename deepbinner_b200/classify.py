@@ -228,12 +228,14 @@ def classify_fast5_files(fast5_files, start_model, start_input_size, end_model, 
     prefetcher = concurrent.futures.ThreadPoolExecutor(max_workers=1)
     files_done = [0]
 
+    sides = (1 if use_start else 0) | (2 if use_end else 0)   # which ends of the reads will be looked at
+
     def parsed_batches():
-        pending = prefetcher.submit(load_batch, batches[0], keep)
+        pending = prefetcher.submit(load_batch, batches[0], keep, sides)
         for index, batch in enumerate(batches):
             read_ids, signals, kept = pending.result()   # unreadable files are skipped (reference :135-136)
             if index + 1 < len(batches):
-                pending = prefetcher.submit(load_batch, batches[index + 1], keep)
+                pending = prefetcher.submit(load_batch, batches[index + 1], keep, sides)
             for read_id, file_index in zip(read_ids, kept):
                 read_id_to_fast5_file[read_id] = batch[file_index]
             yield read_ids, signals, len(batch)
@@ -312,11 +314,12 @@ def classify_read_batches(batches, start_model, start_input_size, end_model, end
     return classifications
 
 
-def load_batch(fast5_batch, keep):
+def load_batch(fast5_batch, keep, sides=3):
     """(read_ids, signals, kept file indices) of the readable files of a batch, parsed on native host
     threads (reference classify.py:133-139 calls get_read_id_and_signal per file).  `signals` is a
-    load_fast5s.PackedSignals: a list of int16 views plus the packed buffer behind them."""
-    return read_fast5_batch_packed(fast5_batch, keep=keep)
+    load_fast5s.PackedSignals: a list of int16 views plus the packed buffer behind them.  `sides`: which
+    ends of the reads the models will look at (1 start, 2 end, 3 both)."""
+    return read_fast5_batch_packed(fast5_batch, keep=keep, sides=sides)
 
 
 def classify_training_data(input_file, start_model, start_input_size, end_model, end_input_size,

@@ -6,12 +6,16 @@
 // direct blocks addressed through a single-leaf v2 B-tree name index), fixed-length string
 // attributes, int16 datasets with contiguous / compact / chunked (B-tree v1) layout and the deflate
 // (+ shuffle) filters.  A batch entry point parses many files on a thread pool.  Host-only code.
+#include <fcntl.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <zlib.h>
 
 #include <algorithm>
 #include <atomic>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <map>
 #include <string>
@@ -19,6 +23,7 @@
 #include <vector>
 
 #include "../../include/deepbinner_b200.h"
+#include "dbn_inflate.h"
 
 namespace dbn {
 int fail(int code, const char* fmt, ...);
@@ -62,11 +67,43 @@ struct Link {
     uint64_t addr;
 };
 
+// zlib inflate of one whole deflate stream into a caller buffer; returns the bytes produced (a stream
+// longer than the buffer is cut there: edge chunks are declared larger than the data set).  The z_stream
+// is kept per thread and reset between calls (inflateInit allocates and initialises ~40 KB every time).
+size_t zlib_inflate_into(const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len) {
+    struct Stream {
+        z_stream zs{};
+        bool ok = false;
+        Stream() { ok = inflateInit(&zs) == Z_OK; }
+        ~Stream() { if (ok) inflateEnd(&zs); }
+    };
+    thread_local Stream st;
+    if (!st.ok || inflateReset(&st.zs) != Z_OK) throw ParseError{"zlib init failed"};
+    st.zs.next_in = const_cast<Bytef*>(src);
+    st.zs.avail_in = static_cast<uInt>(src_len);
+    st.zs.next_out = dst;
+    st.zs.avail_out = static_cast<uInt>(dst_len);
+    const int rc = inflate(&st.zs, Z_FINISH);
+    if (rc != Z_STREAM_END && rc != Z_OK && rc != Z_BUF_ERROR) throw ParseError{"inflate failed"};
+    return st.zs.total_out;
+}
+
+// The signal chunk goes through the word-at-a-time decoder of dbn_inflate.h (2-3x zlib on this
+// literal-heavy data); a stream it rejects is handed to zlib, whose verdict stands.  `src` is readable
+// for kFilePadding bytes beyond its end (read_file pads the file buffer).
+constexpr size_t kFilePadding = 32;
+bool g_use_zlib_only = getenv("DEEPBINNER_B200_ZLIB") != nullptr;
+size_t inflate_into(const uint8_t* src, size_t src_len, uint8_t* dst, size_t dst_len) {
+    size_t got = 0;
+    if (!g_use_zlib_only && dbn_inflate::inflate_zlib(src, src_len, dst, dst_len, &got)) return got;
+    return zlib_inflate_into(src, src_len, dst, dst_len);
+}
+
 class File {
   public:
-    explicit File(const std::vector<uint8_t>& data) {
+    File(const std::vector<uint8_t>& data, size_t size) {
         b_.p = data.data();
-        b_.n = data.size();
+        b_.n = size;
         static const uint8_t sig[8] = {0x89, 'H', 'D', 'F', '\r', '\n', 0x1a, '\n'};
         if (b_.n < 96 || std::memcmp(b_.p, sig, 8) != 0) throw ParseError{"not an HDF5 file"};
         const int version = b_.u8(8);
@@ -191,7 +228,10 @@ class File {
     }
 
     // rank-1 int16 dataset -> out
-    void read_i16(uint64_t addr, std::vector<int16_t>* out) const {
+    // `head` > 0: only the first `head` samples are needed - chunks beyond them are skipped and the inflate of
+    // the chunk that holds them stops there (a start-model-only run never looks further into a read).
+    // Returns the full length of the data set.
+    uint64_t read_i16(uint64_t addr, std::vector<int16_t>* out, uint64_t head = 0) const {
         uint64_t len = 0;
         bool have_space = false, have_layout = false, is_i16 = false;
         Message layout{};
@@ -230,6 +270,8 @@ class File {
         }
         if (!have_space || !have_layout || !is_i16) throw ParseError{"Signal is not an int16 dataset"};
         if (len > (1ull << 32)) throw ParseError{"implausible Signal length"};
+        const uint64_t full_len = len;
+        if (head > 0 && head < len) len = head;
         out->assign(len, 0);
         if (b_.u8(layout.off) != 3) throw ParseError{"unsupported layout version"};
         const int cls = b_.u8(layout.off + 1);
@@ -252,6 +294,7 @@ class File {
         } else {
             throw ParseError{"unsupported layout class"};
         }
+        return full_len;
     }
 
   private:
@@ -405,22 +448,38 @@ class File {
                 walk_chunks(child, chunk_elems, filters, out, depth + 1);
                 continue;
             }
+            if (off >= out->size()) continue;   // beyond what is wanted of this data set
             b_.need(child, csize);
+            // Common case - deflate only (every fast5 of the reference's fixtures): inflate
+            // straight into the output signal, no intermediate copies (a chunk is declared as 201 536 elements
+            // in these files whatever the read length, so sizing a scratch buffer by it costs more than the
+            // inflate itself).
+            int active = 0, only = -1;
+            for (int f = 0; f < static_cast<int>(filters.size()); ++f)
+                if (!(mask & (1u << f))) {
+                    ++active;
+                    only = filters[f];
+                }
+            if (active == 0) {
+                if (off < out->size()) {
+                    const uint64_t cnt = std::min<uint64_t>({csize / 2, chunk_elems, out->size() - off});
+                    std::memcpy(out->data() + off, b_.p + child, cnt * 2);
+                }
+                continue;
+            }
+            if (active == 1 && only == 1) {
+                if (off < out->size()) {
+                    const uint64_t cnt = std::min<uint64_t>(chunk_elems, out->size() - off);
+                    inflate_into(b_.p + child, csize, reinterpret_cast<uint8_t*>(out->data() + off), cnt * 2);
+                }
+                continue;
+            }
             std::vector<uint8_t> raw(b_.p + child, b_.p + child + csize), tmp;
             for (int f = static_cast<int>(filters.size()) - 1; f >= 0; --f) {
                 if (mask & (1u << f)) continue;
                 if (filters[f] == 1) {
-                    tmp.assign(static_cast<size_t>(chunk_elems) * 2 + 64, 0);
-                    z_stream zs{};
-                    if (inflateInit(&zs) != Z_OK) throw ParseError{"zlib init failed"};
-                    zs.next_in = raw.data();
-                    zs.avail_in = static_cast<uInt>(raw.size());
-                    zs.next_out = tmp.data();
-                    zs.avail_out = static_cast<uInt>(tmp.size());
-                    const int rc = inflate(&zs, Z_FINISH);
-                    const size_t got = zs.total_out;
-                    inflateEnd(&zs);
-                    if (rc != Z_STREAM_END && rc != Z_OK && rc != Z_BUF_ERROR) throw ParseError{"inflate failed"};
+                    tmp.resize(static_cast<size_t>(chunk_elems) * 2 + 64);
+                    const size_t got = zlib_inflate_into(raw.data(), raw.size(), tmp.data(), tmp.size());
                     tmp.resize(got);
                     raw.swap(tmp);
                 } else if (filters[f] == 2) {
@@ -449,34 +508,41 @@ class File {
     uint64_t root_ = 0;
 };
 
-bool read_file(const char* path, std::vector<uint8_t>* data) {
-    FILE* f = std::fopen(path, "rb");
-    if (!f) return false;
-    std::fseek(f, 0, SEEK_END);
-    const long size = std::ftell(f);
-    std::fseek(f, 0, SEEK_SET);
-    if (size <= 0) {
-        std::fclose(f);
+// Whole file into `data` with plain open / fstat / read (no stdio buffering: one system call per 1 MB).
+bool read_file(const char* path, std::vector<uint8_t>* data, size_t* file_size) {
+    const int fd = ::open(path, O_RDONLY | O_CLOEXEC);
+    if (fd < 0) return false;
+    struct stat sb;
+    if (::fstat(fd, &sb) != 0 || sb.st_size <= 0) {
+        ::close(fd);
         return false;
     }
-    data->resize(static_cast<size_t>(size));
-    const size_t got = std::fread(data->data(), 1, data->size(), f);
-    std::fclose(f);
-    return got == data->size();
+    const size_t size = static_cast<size_t>(sb.st_size);
+    if (data->size() < size + kFilePadding) data->resize(size + kFilePadding);   // (the decoder may over-read a few bytes)
+    *file_size = size;
+    size_t got = 0;
+    while (got < size) {
+        const ssize_t r = ::read(fd, data->data() + got, size - got);
+        if (r <= 0) break;
+        got += static_cast<size_t>(r);
+    }
+    ::close(fd);
+    return got == size;
 }
 
 struct ReadRec {
     std::string id;
     std::vector<int16_t> signal;
+    uint64_t full_length = 0;
 };
 
 // One read group (`/Raw/Reads/Read_<n>` of the old layout, `/read_<uuid>/Raw` of the new one):
 // `read_id` attribute + `Signal` dataset (load_fast5s.py:33-44).
-bool read_group(const File& f, uint64_t group, ReadRec* r) {
+bool read_group(const File& f, uint64_t group, ReadRec* r, uint64_t head) {
     if (!f.string_attr(group, "read_id", &r->id)) return false;
     uint64_t sig;
     if (!f.find(group, "Signal", &sig)) return false;
-    f.read_i16(sig, &r->signal);
+    r->full_length = f.read_i16(sig, &r->signal, head);
     return true;
 }
 
@@ -486,12 +552,13 @@ bool read_group(const File& f, uint64_t group, ReadRec* r) {
 // `multi_to_single_fast5` first (realtime.py:183-196).  A read that cannot be parsed is skipped, as
 // an unreadable unpacked file would be (load_fast5s.py:48-49).
 // status: 0 ok, 1 unreadable / not HDF5 / no read.  *multi = the root holds more than one read group.
-int read_all(const char* path, std::vector<ReadRec>* reads, bool* multi, bool want_multi) {
+int read_all(const char* path, std::vector<ReadRec>* reads, bool* multi, bool want_multi, uint64_t head = 0) {
     *multi = false;
-    std::vector<uint8_t> data;
-    if (!read_file(path, &data)) return 1;
+    thread_local std::vector<uint8_t> data;   // reused: no allocation / zero fill per file once it has grown
+    size_t file_size = 0;
+    if (!read_file(path, &data, &file_size)) return 1;
     try {
-        File f(data);
+        File f(data, file_size);
         const std::vector<Link> root = f.links(f.root());
         for (const Link& l : root)
             if (l.name == "Raw") {   // old single-read layout: /Raw/Reads/<first child>
@@ -500,7 +567,7 @@ int read_all(const char* path, std::vector<ReadRec>* reads, bool* multi, bool wa
                 const std::vector<Link> kids = f.links(rg);
                 if (kids.empty()) return 1;
                 ReadRec r;
-                if (!read_group(f, kids[0].addr, &r)) return 1;
+                if (!read_group(f, kids[0].addr, &r, head)) return 1;
                 reads->push_back(std::move(r));
                 return 0;
             }
@@ -515,7 +582,7 @@ int read_all(const char* path, std::vector<ReadRec>* reads, bool* multi, bool wa
             ReadRec r;
             uint64_t raw;
             try {
-                if (f.find(l->addr, "Raw", &raw) && read_group(f, raw, &r)) reads->push_back(std::move(r));
+                if (f.find(l->addr, "Raw", &raw) && read_group(f, raw, &r, head)) reads->push_back(std::move(r));
             } catch (const ParseError&) {
                 if (!*multi) return 1;
             }
@@ -554,6 +621,21 @@ struct db_fast5_batch {
 #pragma GCC visibility push(default)
 extern "C" {
 
+int db_zlib_inflate(const uint8_t* src, int64_t src_len, uint8_t* dst, int64_t dst_capacity, int64_t* produced, int use_zlib) {
+    if (!src || !dst || !produced || src_len < 0 || dst_capacity < 0) return dbn::fail(DBN_EINVAL, "db_zlib_inflate: bad argument");
+    std::vector<uint8_t> padded(static_cast<size_t>(src_len) + kFilePadding, 0);
+    std::memcpy(padded.data(), src, static_cast<size_t>(src_len));
+    try {
+        size_t got = 0;
+        if (use_zlib) got = zlib_inflate_into(padded.data(), static_cast<size_t>(src_len), dst, static_cast<size_t>(dst_capacity));
+        else if (!dbn_inflate::inflate_zlib(padded.data(), static_cast<size_t>(src_len), dst, static_cast<size_t>(dst_capacity), &got)) return 1;
+        *produced = static_cast<int64_t>(got);
+        return 0;
+    } catch (const ParseError&) {
+        return 1;
+    }
+}
+
 int db_fast5_read(const char* path, char* read_id, int16_t* signal, int64_t capacity, int64_t* length) {
     if (!path || !read_id || !length) return dbn::fail(DBN_EINVAL, "db_fast5_read: NULL argument");
     std::string id;
@@ -571,9 +653,10 @@ int db_fast5_list_root(const char* path, char* names, int64_t capacity, int* cou
     if (!path || !names || !count) return dbn::fail(DBN_EINVAL, "db_fast5_list_root: NULL argument");
     *count = 0;
     std::vector<uint8_t> data;
-    if (!read_file(path, &data)) return 1;
+    size_t file_size = 0;
+    if (!read_file(path, &data, &file_size)) return 1;
     try {
-        File f(data);
+        File f(data, file_size);
         int64_t used = 0;
         for (const Link& l : f.links(f.root())) {
             const int64_t need = static_cast<int64_t>(l.name.size()) + 1;
@@ -593,7 +676,9 @@ int db_fast5_list_root(const char* path, char* names, int64_t capacity, int* cou
 // multi = 0: one row per file (a multi-read file is a row with status 2);
 // multi = 1: one row per READ - a multi-read file contributes all its reads, an unreadable file one
 // row with status 1.  Rows are in file order (reads of a file ordered by group name).
-static int batch_read(const char* const* paths, int n, int threads, int64_t keep, int multi, db_fast5_batch** out) {
+// sides: bit 0 = the start of the reads is needed, bit 1 = the end (start only: reads are cut after `keep`
+// samples and the inflate stops there).
+static int batch_read(const char* const* paths, int n, int threads, int64_t keep, int multi, int sides, db_fast5_batch** out) {
     if (!paths || n < 0 || !out) return dbn::fail(DBN_EINVAL, "db_fast5_batch_read: bad argument");
     db_fast5_batch* b = new db_fast5_batch();
     std::vector<std::vector<ReadRec>> per_file(n);
@@ -603,14 +688,15 @@ static int batch_read(const char* const* paths, int n, int threads, int64_t keep
     auto work = [&]() {
         for (int i = next.fetch_add(1); i < n; i = next.fetch_add(1)) {
             bool is_multi = false;
-            file_status[i] = read_all(paths[i], &per_file[i], &is_multi, multi != 0);
+            const uint64_t head = (keep > 0 && sides == 1) ? static_cast<uint64_t>(keep) : 0;
+            file_status[i] = read_all(paths[i], &per_file[i], &is_multi, multi != 0, head);
             if (file_status[i] == 0 && is_multi && !multi) file_status[i] = 2;
             if (file_status[i]) {
                 per_file[i].clear();
                 continue;
             }
             for (ReadRec& r : per_file[i]) {
-                full[i].push_back(static_cast<int64_t>(r.signal.size()));
+                full[i].push_back(static_cast<int64_t>(r.full_length));
                 // keep only what call_batch can ever look at: the first and last `keep` samples
                 if (keep > 0 && static_cast<int64_t>(r.signal.size()) > 2 * keep) {
                     r.signal.erase(r.signal.begin() + keep, r.signal.end() - keep);
@@ -660,11 +746,16 @@ static int batch_read(const char* const* paths, int n, int threads, int64_t keep
 }
 
 int db_fast5_batch_read(const char* const* paths, int n, int threads, int64_t keep, db_fast5_batch** out) {
-    return batch_read(paths, n, threads, keep, 0, out);
+    return batch_read(paths, n, threads, keep, 0, 3, out);
 }
 
 int db_fast5_batch_read_reads(const char* const* paths, int n, int threads, int64_t keep, db_fast5_batch** out) {
-    return batch_read(paths, n, threads, keep, 1, out);
+    return batch_read(paths, n, threads, keep, 1, 3, out);
+}
+
+int db_fast5_batch_read_sides(const char* const* paths, int n, int threads, int64_t keep, int sides, db_fast5_batch** out) {
+    if (sides < 1 || sides > 3) return dbn::fail(DBN_EINVAL, "db_fast5_batch_read_sides: sides must be 1 (start), 2 (end) or 3");
+    return batch_read(paths, n, threads, keep, 1, sides, out);
 }
 
 int db_fast5_batch_rows(const db_fast5_batch* b, int64_t* rows, const int32_t** row_file) {

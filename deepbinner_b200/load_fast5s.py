@@ -35,17 +35,20 @@ class PackedSignals(list):
         self.samples, self.offsets, self.rows = samples, offsets, rows
 
 
-def read_fast5_batch_packed(fast5_files, keep, threads=None):
+def read_fast5_batch_packed(fast5_files, keep, threads=None, sides=3):
     """Every read of every readable file, in input order (a multi-read fast5 contributes all its
     reads, ordered by group name): -> (read_ids, signals, kept) with `signals` a PackedSignals and
-    `kept[i]` the index of the file read i came from."""
+    `kept[i]` the index of the file read i came from.  `sides`: 1 = only the start of the reads will be
+    looked at (reads are cut after `keep` samples and decompression stops there), 2 = end, 3 = both."""
     lib = _native_lib()
     files = [str(f) for f in fast5_files]
     if lib is None:     # pure-Python reader: plain lists
         ids, sigs, kept = [], [], []
         for i, f in enumerate(files):
             for rid, sig in get_reads_python(f):
-                if keep > 0 and len(sig) > 2 * keep:
+                if keep > 0 and sides == 1:
+                    sig = sig[:keep]
+                elif keep > 0 and len(sig) > 2 * keep:
                     sig = np.concatenate([sig[:keep], sig[-keep:]])
                 ids.append(rid)
                 sigs.append(sig)
@@ -53,22 +56,26 @@ def read_fast5_batch_packed(fast5_files, keep, threads=None):
         return ids, sigs, kept
     if not files:
         return [], PackedSignals([], np.zeros(0, np.int16), np.zeros(1, np.int64), np.zeros(0, np.int64)), []
-    ids, samples, offsets, status, row_file = _native_batch(lib, files, keep, threads, reads=True)
+    ids, samples, offsets, status, row_file = _native_batch(lib, files, keep, threads, reads=True, sides=sides)
     ok = [r for r in range(len(ids)) if status[r] == 0]
     views = [samples[offsets[r]:offsets[r + 1]] for r in ok]
     return ([ids[r] for r in ok], PackedSignals(views, samples, offsets, np.asarray(ok, dtype=np.int64)),
             [int(row_file[r]) for r in ok])
 
 
-def _native_batch(lib, files, keep, threads, reads):
+def _native_batch(lib, files, keep, threads, reads, sides=3):
     """db_fast5_batch_read (one row per file) / db_fast5_batch_read_reads (one row per read) ->
     (read_ids, samples, offsets, status, row_file) with one entry per row."""
     n = len(files)
     arr = (ctypes.c_char_p * max(n, 1))(*[os.fsencode(f) for f in files])
     handle = ctypes.c_void_p()
     threads = threads or min(16, os.cpu_count() or 1)
-    entry = lib.db_fast5_batch_read_reads if reads else lib.db_fast5_batch_read
-    if entry(arr, n, int(threads), int(keep), ctypes.byref(handle)) != 0:
+    if reads and sides != 3:
+        rc = lib.db_fast5_batch_read_sides(arr, n, int(threads), int(keep), int(sides), ctypes.byref(handle))
+    else:
+        entry = lib.db_fast5_batch_read_reads if reads else lib.db_fast5_batch_read
+        rc = entry(arr, n, int(threads), int(keep), ctypes.byref(handle))
+    if rc != 0:
         raise RuntimeError('db_fast5_batch_read failed')
     try:
         rows, rf = ctypes.c_int64(), ctypes.c_void_p()

@@ -167,6 +167,12 @@ DBN_API int64_t db_kernel_launches(const db_model *model);
  *   offsets[n+1], full (untruncated) lengths[n], read ids [n][64], status[n]; the pointers stay
  *   valid until db_fast5_batch_free.
  */
+/* The decompressor the fast5 reader inflates signal chunks with (csrc/dbn_inflate.h; use_zlib = 1: the
+ * system zlib it is checked against).  src: a zlib stream; dst receives at most dst_capacity bytes (a
+ * longer stream is cut there, as for HDF5 edge chunks).  Returns 0, or 1 for a malformed stream.
+ * Exposed for tests/test_fast5_readers.py. */
+DBN_API int db_zlib_inflate(const uint8_t *src, int64_t src_len, uint8_t *dst, int64_t dst_capacity,
+                            int64_t *produced, int use_zlib);
 typedef struct db_fast5_batch db_fast5_batch;
 DBN_API int db_fast5_read(const char *path, char *read_id, int16_t *signal, int64_t capacity,
                           int64_t *length);
@@ -179,6 +185,11 @@ DBN_API int db_fast5_batch_read(const char *const *paths, int n, int threads, in
  * file is one row with status 1.  db_fast5_batch_rows gives the row count and, per row, the index of
  * the file it came from; db_fast5_batch_get's arrays are then per row. */
 DBN_API int db_fast5_batch_read_reads(const char *const *paths, int n, int threads, int64_t keep,
+                                      db_fast5_batch **out);
+/* db_fast5_batch_read_reads for a run that only looks at one side of the reads (sides: 1 = start, 2 = end,
+ * 3 = both).  Start only (e.g. the SQK-RBK004 preset): every read is cut after `keep` samples and the
+ * inflate of its signal chunk stops there instead of decoding the whole read. */
+DBN_API int db_fast5_batch_read_sides(const char *const *paths, int n, int threads, int64_t keep, int sides,
                                       db_fast5_batch **out);
 DBN_API int db_fast5_batch_rows(const db_fast5_batch *batch, int64_t *rows, const int32_t **row_file);
 DBN_API int db_fast5_batch_get(const db_fast5_batch *batch, const int16_t **samples,

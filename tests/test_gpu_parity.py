@@ -211,7 +211,7 @@ def test_classify_fast5_files_end_to_end(models, fixture_reads, reference_golden
     from deepbinner_b200 import classify as cls
     ids, sigs, names = fixture_reads
     table = {n: (i, s) for n, i, s in zip(names, ids, sigs)}
-    def load_batch(batch, keep):   # same contract as classify.load_batch: readable files only
+    def load_batch(batch, keep, sides=3):   # same contract as classify.load_batch: readable files only
         loaded = [table.get(str(f).split('/')[-1], (None, None)) for f in batch]
         kept = [i for i, (_, sig) in enumerate(loaded) if sig is not None]
         return [loaded[i][0] for i in kept], [loaded[i][1] for i in kept], kept
