@@ -166,7 +166,7 @@ __device__ __forceinline__ void prefetch_job(int j) {
 
 struct TcParams {
     int njobs;
-    const struct TcJob* jobs;   // global-memory copy of the job table (the MMA issuer prefetches from it)
+    const uint4* issue;       // global-memory table of IssueRec (what the MMA issuer needs of every job, 64 B each)
     const unsigned char* w;   // packed bf16 weights
     const float* prm;         // global copy of the smem parameter block + conv1 parameters
     int prm_floats;
@@ -822,37 +822,49 @@ __device__ __forceinline__ void issue_job_part(int ntaps, int ncb, uint32_t dwin
     }
 }
 
-// What the MMA issuer needs from a job descriptor, held in registers one job ahead.
+// What the MMA issuer needs from a job descriptor, held in registers one job ahead.  The issuer reads it
+// from a separate global table of 64-byte records in which EVERY word is used: a loaded-but-unused
+// component leaves a register that ptxas recycles as scratch at once, and the write-after-write
+// hazard on it makes the issuer sit out the full latency of the loads it has just issued - measured:
+// ~500 cycles at the top of every job with the 128-byte TcJob read by six 16-byte loads
+// (profiles/r02_issuer_waw.txt).
+struct alignas(16) IssueRec {
+    uint32_t n, idesc, ntiles, lp;                 // word 0
+    uint32_t tap16[3], lo16;                       // word 1
+    uint32_t shape, cb0, tcol, flags;              // word 2: shape = ncb | ntaps << 8; flags = first | last << 1 | joint << 2
+    uint32_t need, eseq, blk16, part1_16;          // word 3: blk16 = one K=16 block of B, part1_16 = offset of weight part 1 behind part 0 (joint jobs), 16-byte units
+};
+static_assert(sizeof(IssueRec) == 64, "IssueRec is read as four 16-byte words");
 struct IssueArgs {
-    uint32_t n, idesc, ntiles, lp, lo16, cb0, tcol, tap16[3];
+    uint32_t n, idesc, ntiles, lp, lo16, cb0, tcol, tap16[3], blk16, part1_16;
     int ntaps, ncb, first, last, joint, need, eseq;
 };
-// Issued as volatile loads: the instructions sit exactly where this is called (the top of the
-// previous job's iteration) and their results are first touched one job later, so the whole
-// latency is hidden.  (Plain loads of the __constant__ table were sunk by the compiler to their first
-// use, which put a constant-cache miss of several hundred cycles between every two jobs.)
+// The four raw words of a record.  They are fetched with volatile loads at the top of the PREVIOUS job's
+// iteration and not touched (not even unpacked) until the job starts, so the whole latency is hidden.
+// (Plain loads of the __constant__ table were sunk by the compiler to their first use, which put a
+// constant-cache miss of several hundred cycles between every two jobs.)
+struct IssueRaw {
+    uint4 w0, w1, w2, w3;
+};
 __device__ __forceinline__ uint4 ldg_volatile_v4(const void* p) {
     uint4 v;
     asm volatile("ld.global.nc.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p));
     return v;
 }
-__device__ __forceinline__ IssueArgs load_issue_args(const TcJob* J) {
-    const uint4* q = reinterpret_cast<const uint4*>(J);
-    const uint4 a0 = ldg_volatile_v4(q), a1 = ldg_volatile_v4(q + 1), a2 = ldg_volatile_v4(q + 2);
-    const uint4 a3 = ldg_volatile_v4(q + 3), a4 = ldg_volatile_v4(q + 4), a7 = ldg_volatile_v4(q + 7);
+__device__ __forceinline__ IssueRaw load_issue_raw(const uint4* q) {
+    IssueRaw r;
+    r.w0 = ldg_volatile_v4(q); r.w1 = ldg_volatile_v4(q + 1); r.w2 = ldg_volatile_v4(q + 2); r.w3 = ldg_volatile_v4(q + 3);
+    return r;
+}
+__device__ __forceinline__ IssueArgs unpack_issue(const IssueRaw& r) {
     IssueArgs a;
-    a.n = a0.x; a.idesc = a0.y; a.ntiles = a0.z;                       // n, idesc, ntiles, L
-    a.lp = a1.x; a.ntaps = a1.y; a.tap16[0] = a1.z; a.tap16[1] = a1.w;  // lp, ntaps, tap16[0], tap16[1]
-    a.tap16[2] = a2.x; a.lo16 = a2.y; a.ncb = a2.z; a.cb0 = a2.w;       // tap16[2], lo16, ncb, cb0
-    a.tcol = a3.y;                                                     // w_goff, tcol, w_part[2]
-    a.first = a4.x; a.last = a4.y;                                     // first, last, kind, bias_off
-    a.joint = a7.y; a.need = a7.z; a.eseq = a7.w;                      // zero_y, joint, need, eseq
+    a.n = r.w0.x; a.idesc = r.w0.y; a.ntiles = r.w0.z; a.lp = r.w0.w;
+    a.tap16[0] = r.w1.x; a.tap16[1] = r.w1.y; a.tap16[2] = r.w1.z; a.lo16 = r.w1.w;
+    a.ncb = static_cast<int>(r.w2.x & 0xFFu); a.ntaps = static_cast<int>(r.w2.x >> 8); a.cb0 = r.w2.y; a.tcol = r.w2.z;
+    a.first = static_cast<int>(r.w2.w & 1u); a.last = static_cast<int>((r.w2.w >> 1) & 1u); a.joint = static_cast<int>(r.w2.w >> 2);
+    a.need = static_cast<int>(r.w3.x); a.eseq = static_cast<int>(r.w3.y); a.blk16 = r.w3.z; a.part1_16 = r.w3.w;
     return a;
 }
-static_assert(offsetof(TcJob, lp) == 16 && offsetof(TcJob, tap16) == 24 && offsetof(TcJob, lo16) == 36 &&
-                  offsetof(TcJob, cb0) == 44 && offsetof(TcJob, tcol) == 52 && offsetof(TcJob, first) == 64 &&
-                  offsetof(TcJob, joint) == 116 && offsetof(TcJob, eseq) == 124,
-              "load_issue_args reads TcJob by 16-byte words");
 // ---------------------------------------------------------------------------------------------
 // the kernel
 // ---------------------------------------------------------------------------------------------
@@ -1080,11 +1092,11 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             // The issuer is ONE thread: a chain of dependent constant loads costs it ~40 cycles per
             // link, so the next job's descriptor is fetched (from the global copy of the table) while
             // this job's MMAs are issued.
-            IssueArgs nxt = load_issue_args(P.jobs);
+            IssueRaw nxt = load_issue_raw(P.issue);
             for (int j = 0; j < njobs; ++j) {
-                const IssueArgs J = nxt;
-                if (j + 1 < njobs) nxt = load_issue_args(P.jobs + j + 1);
-                const uint32_t blk16 = 2u * J.n;                 // one K=16 block of B, in 16-byte units
+                const IssueArgs J = unpack_issue(nxt);
+                if (j + 1 < njobs) nxt = load_issue_raw(P.issue + 4 * (j + 1));
+                const uint32_t blk16 = J.blk16;                  // one K=16 block of B, in 16-byte units
                 const uint32_t tap16[3] = {J.tap16[0], J.tap16[1], J.tap16[2]};
                 const bool first = J.first != 0, last = J.last != 0;
                 if (tracing) trace[(j * 2) * 16 + 11] = clock64();
@@ -1094,7 +1106,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     // overlaps the wait for the job's input instead of following it)
                     const int slot = jk % 3;
                     const uint32_t jw0_16 = (slot == 0 ? wbuf : slot == 1 ? jwslot1 : jwslot2) >> 4;
-                    const uint32_t jw1_16 = jw0_16 + (J.ntaps * J.ncb == 9 ? 10u : 4u) * blk16;   // behind part 0
+                    const uint32_t jw1_16 = jw0_16 + J.part1_16;   // behind part 0
                     mbar_wait(bar_jwfull0 + 8 * slot, (jk / 3) & 1);
                     if (tracing) trace[(j * 2) * 16 + 12] = clock64();
                     if (tracing) {   // in-situ cost of a poll of a barrier whose phase is known to be complete
@@ -1219,7 +1231,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 // ---------------------------------------------------------------------------------------------
 struct TcEngine {
     unsigned char* d_w = nullptr;
-    TcJob* d_jobs = nullptr;
+    uint4* d_issue = nullptr;
     float* d_prm = nullptr;
     TcParams params{};
     int njobs = 0;
@@ -1462,6 +1474,22 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     return true;
 }
 
+// The MMA issuer's view of a (finalized) job.
+static IssueRec issue_record(const TcJob& J) {
+    IssueRec r{};
+    r.n = static_cast<uint32_t>(J.n); r.idesc = static_cast<uint32_t>(J.idesc); r.ntiles = static_cast<uint32_t>(J.ntiles);
+    r.lp = static_cast<uint32_t>(J.lp);
+    for (int t = 0; t < 3; ++t) r.tap16[t] = static_cast<uint32_t>(J.tap16[t]);
+    r.lo16 = static_cast<uint32_t>(J.lo16);
+    r.shape = static_cast<uint32_t>(J.ncb | (J.ntaps << 8));
+    r.cb0 = static_cast<uint32_t>(J.cb0); r.tcol = static_cast<uint32_t>(J.tcol);
+    r.flags = static_cast<uint32_t>((J.first ? 1 : 0) | (J.last ? 2 : 0) | (J.joint << 2));
+    r.need = static_cast<uint32_t>(J.need); r.eseq = static_cast<uint32_t>(J.eseq);
+    r.blk16 = 2u * static_cast<uint32_t>(J.n);
+    r.part1_16 = (J.ntaps * J.ncb == 9 ? 10u : 4u) * r.blk16;
+    return r;
+}
+
 TcEngine* tc_create(const Blob& blob) {
     if (getenv("DBN_DISABLE_TC")) return nullptr;
     JobBuilder B(blob);
@@ -1469,12 +1497,14 @@ TcEngine* tc_create(const Blob& blob) {
     if (!build_jobs(blob, &B, &P)) return nullptr;
     TcEngine* e = new TcEngine();
     e->jobs = B.jobs;
+    std::vector<IssueRec> recs;
+    for (const TcJob& J : B.jobs) recs.push_back(issue_record(J));
     bool ok = cudaMalloc(&e->d_w, B.w.size()) == cudaSuccess &&
               cudaMalloc(&e->d_prm, B.prm.size() * sizeof(float)) == cudaSuccess &&
               cudaMemcpy(e->d_w, B.w.data(), B.w.size(), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaMemcpy(e->d_prm, B.prm.data(), B.prm.size() * sizeof(float), cudaMemcpyHostToDevice) == cudaSuccess &&
-              cudaMalloc(&e->d_jobs, B.jobs.size() * sizeof(TcJob)) == cudaSuccess &&
-              cudaMemcpy(e->d_jobs, B.jobs.data(), B.jobs.size() * sizeof(TcJob), cudaMemcpyHostToDevice) == cudaSuccess &&
+              cudaMalloc(&e->d_issue, recs.size() * sizeof(IssueRec)) == cudaSuccess &&
+              cudaMemcpy(e->d_issue, recs.data(), recs.size() * sizeof(IssueRec), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaFuncSetAttribute(k_tc_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
               cudaFuncSetAttribute(k_tc_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
               cudaFuncSetAttribute(k_tc_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess;
@@ -1486,7 +1516,7 @@ TcEngine* tc_create(const Blob& blob) {
     e->njobs = static_cast<int>(B.jobs.size());
     P.njobs = e->njobs;
     P.w = e->d_w;
-    P.jobs = e->d_jobs;
+    P.issue = e->d_issue;
     P.prm = e->d_prm;
     P.dbg_job = -1;
     P.dbg_out = nullptr;
@@ -1498,7 +1528,7 @@ TcEngine* tc_create(const Blob& blob) {
 void tc_destroy(TcEngine* e) {
     if (!e) return;
     cudaFree(e->d_w);
-    cudaFree(e->d_jobs);
+    cudaFree(e->d_issue);
     cudaFree(e->d_prm);
     delete e;
 }

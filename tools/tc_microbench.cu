@@ -250,6 +250,164 @@ __global__ void __launch_bounds__(128, 1) k_layout(int M, int N, int dlane, floa
     if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
 }
 
+
+// MODE 3 (separate kernel): how long does a cp.async.bulk of `bytes` (global -> shared, the engine's weight
+// load) take when the tensor pipe is idle / while warp 0 streams a 108-MMA burst (M=128, N=48) / behind
+// `chunks` separate copies on one barrier?  Every CTA of the grid does the same (L2 contention as in the engine).
+constexpr int kSmemLand = kSmemBar + 64;          // landing zone of the copy
+constexpr int kLandBytes = 27648;
+constexpr int kSmemCopyBytes = kSmemLand + kLandBytes;
+struct CopyResult { long long t_copy, t_burst, t_poll; };
+template <int BURST>
+__global__ void __launch_bounds__(160, 1) k_copy(const unsigned char* src, int bytes, int chunks, int reps, CopyResult* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_mma = sbase + kSmemBar, bar_w = sbase + kSmemBar + 8, bar_go = sbase + kSmemBar + 16;
+    volatile uint32_t* slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 32);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    for (int i = threadIdx.x; i < kSmemBar / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(smem)[i] = 0x3c003c00u;
+    if (threadIdx.x == 0) {
+        mbar_init(bar_mma, 1);
+        mbar_init(bar_w, 1);
+        mbar_init(bar_go, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 0) {
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(sbase + kSmemBar + 32), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *slot;
+    long long best_copy = 1ll << 60, best_burst = 1ll << 60, best_poll = 1ll << 60;
+    uint32_t ph = 0;
+    for (int rep = 0; rep < reps; ++rep) {
+        __syncthreads();
+        if (warp == 0) {
+            if (elect_one()) {
+                const long long t0 = clock64();
+                if (BURST) {
+                    issue_burst<128, 48, 9, 4, 1>(sbase);
+                    const long long ta = clock64();
+                    if (!mbar_try_wait(bar_go, 1)) __trap();   // a poll of an unrelated (passed) barrier phase right behind the burst, before the commit; the branch makes the clock read wait
+                    const long long tb = clock64();
+                    if (tb - ta < best_poll) best_poll = tb - ta;
+                    tc_commit(bar_mma);
+                    mbar_wait(bar_mma, ph);
+                    tc_fence_after();
+                }
+                const long long t1 = clock64();
+                if (t1 - t0 < best_burst) best_burst = t1 - t0;
+            }
+        } else if (warp == 1) {
+            if (elect_one()) {
+                const long long t0 = clock64();
+                asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar_w), "r"(bytes) : "memory");
+                const int cb = bytes / chunks;
+                for (int c = 0; c < chunks; ++c)
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(sbase + kSmemLand + c * cb),
+                                 "l"(src + (size_t)c * cb), "r"(cb), "r"(bar_w) : "memory");
+                mbar_wait(bar_w, ph);
+                const long long t1 = clock64();
+                if (t1 - t0 < best_copy) best_copy = t1 - t0;
+            }
+        }
+        ph ^= 1;
+    }
+    if (threadIdx.x == 0 && blockIdx.x == 0) { out->t_burst = 0; }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        if (warp == 0 && elect_one()) { out->t_burst = best_burst; out->t_poll = best_poll; }
+        if (warp == 1 && elect_one()) out->t_copy = best_copy;
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem), "r"(512) : "memory");
+}
+
+
+// MODE 4 (separate kernel): what does the MMA issuer (ONE elected lane) pay to learn that something is
+// ready while 12 "epilogue" warps hammer shared memory with 16-byte stores?
+//   (a) mbarrier.try_wait on a long-completed barrier, (b) mbarrier.test_wait, (c) a named barrier
+//   (barrier.sync id, 64 by the single lane; warp 1 arrived long before with barrier.arrive id, 64).
+struct PollResult { long long tw_idle, tw_busy, tt_idle, tt_busy, nb_idle, nb_busy, tw_max_busy, nb_max_busy; };
+__global__ void __launch_bounds__(448, 1) k_poll(int reps, PollResult* out) {
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const uint32_t sbase = smem_u32(smem);
+    const uint32_t bar_done = sbase + 200000;
+    volatile int* flag = reinterpret_cast<volatile int*>(smem + 200064);
+    volatile int* mail = reinterpret_cast<volatile int*>(smem + 200096);
+    const int warp = __shfl_sync(0xffffffffu, threadIdx.x >> 5, 0);
+    if (threadIdx.x == 0) {
+        mbar_init(bar_done, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        mbar_arrive(bar_done);
+        *flag = 0;
+    }
+    __syncthreads();
+    if (warp == 0) {
+        if (elect_one()) {
+            long long acc[6] = {0, 0, 0, 0, 0, 0}, mx[2] = {0, 0};
+            const long long kstart = clock64();
+            for (int busy = 0; busy < 2; ++busy) {
+                if (busy) {                      // the store warps start 100 000 cycles into the kernel
+                    while (clock64() - kstart < 103000) {}
+                }
+                for (int rep = 0; rep < reps; ++rep) {
+                    long long t0 = clock64();
+                    if (!mbar_try_wait(bar_done, 0)) __trap();   // the branch makes the clock read wait for the result
+                    long long t1 = clock64();
+                    uint32_t ok;
+                    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                                 : "=r"(ok) : "r"(bar_done), "r"(0) : "memory");
+                    if (!ok) __trap();
+                    long long t2 = clock64();
+                    // named barrier: warp 1 arrives on 2, we wait >= 400 cycles, then sync on it
+                    asm volatile("barrier.arrive 3, 64;" ::: "memory");     // go: warp 1 may arrive on barrier 2
+                    long long d = clock64();
+                    while (clock64() - d < 400) {}
+                    long long t3 = clock64();
+                    asm volatile("barrier.sync 2, 64;" ::: "memory");
+                    if (*mail != busy * reps + rep + 1) __trap();   // warp 1 wrote it before arriving
+                    long long t4 = clock64();
+                    acc[busy] += t1 - t0;
+                    acc[2 + busy] += t2 - t1;
+                    acc[4 + busy] += t4 - t3;
+                    if (busy && t1 - t0 > mx[0]) mx[0] = t1 - t0;
+                    if (busy && t4 - t3 > mx[1]) mx[1] = t4 - t3;
+                    if (ok == 12345) out->tw_idle = 1;
+                }
+            }
+            *flag = 2;
+            out->tw_idle = acc[0] / reps; out->tw_busy = acc[1] / reps;
+            out->tt_idle = acc[2] / reps; out->tt_busy = acc[3] / reps;
+            out->nb_idle = acc[4] / reps; out->nb_busy = acc[5] / reps;
+            out->tw_max_busy = mx[0]; out->nb_max_busy = mx[1];
+        }
+    } else if (warp == 1) {
+        for (int i = 0; i < 2 * reps; ++i) {
+            asm volatile("barrier.sync 3, 64;" ::: "memory");
+            if ((threadIdx.x & 31) == 0) *mail = i + 1;
+            __syncwarp();
+            asm volatile("barrier.arrive 2, 64;" ::: "memory");
+        }
+    } else {
+        // "epilogue" warps: once the flag is 1, stream 16-byte stores (each warp its own 16 KB) until it is 2
+        const uint32_t base = sbase + (warp - 2) * 16384 + (threadIdx.x & 31) * 16;
+        const long long kstart = clock64();
+        while (clock64() - kstart < 100000) {}
+        uint32_t k = 0;
+        while (*flag != 2) {
+#pragma unroll
+            for (int u = 0; u < 8; ++u)
+                asm volatile("st.shared.v4.b32 [%0], {%1,%1,%1,%1};" ::"r"(base + ((k + u) & 31) * 512), "r"(k) : "memory");
+            k += 8;
+        }
+    }
+}
+
 #define CK(x)                                                                              \
     do {                                                                                   \
         cudaError_t e_ = (x);                                                              \
@@ -289,6 +447,21 @@ static void run_shape() {
     if (M == 128 && N <= 128) run_burst<M, N, 9, 4, 0, 0>();
 }
 
+
+template <int BURST>
+static void run_copy(const unsigned char* d_src, int bytes, int chunks, int grid) {
+    static CopyResult* d_cr = nullptr;
+    if (!d_cr) CK(cudaMalloc(&d_cr, sizeof(CopyResult)));
+    CK(cudaMemset(d_cr, 0, sizeof(CopyResult)));
+    CK(cudaFuncSetAttribute(k_copy<BURST>, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemCopyBytes));
+    k_copy<BURST><<<grid, 160, kSmemCopyBytes>>>(d_src, bytes, chunks, 20, d_cr);
+    CK(cudaDeviceSynchronize());
+    CopyResult r;
+    CK(cudaMemcpy(&r, d_cr, sizeof(r), cudaMemcpyDeviceToHost));
+    std::printf("copy %5d B in %d chunk(s), grid %3d, %s | copy done after %6lld cycles (best of 20) | burst %6lld | poll behind the burst %lld\n",
+                bytes, chunks, grid, BURST ? "with a 108-MMA burst" : "tensor pipe idle     ", r.t_copy, r.t_burst, r.t_poll);
+}
+
 int main() {
     CK(cudaFuncSetAttribute(k_layout, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmemBytes));
     CK(cudaMalloc(&d_res, sizeof(Result)));
@@ -311,6 +484,36 @@ int main() {
     run_burst<128, 48, 1, 1, 1, 1>();
     run_burst<128, 48, 3, 1, 1, 1>();
     run_burst<128, 48, 9, 1, 1, 1>();
+
+
+    {
+        PollResult* d_pr;
+        CK(cudaMalloc(&d_pr, sizeof(PollResult)));
+        CK(cudaMemset(d_pr, 0, sizeof(PollResult)));
+        CK(cudaFuncSetAttribute(k_poll, cudaFuncAttributeMaxDynamicSharedMemorySize, 200128));
+        k_poll<<<1, 448, 200128>>>(50, d_pr);
+        cudaError_t e = cudaDeviceSynchronize();
+        if (e != cudaSuccess) { std::printf("poll test: CUDA error %s\n", cudaGetErrorString(e)); return 0; }
+        PollResult r;
+        CK(cudaMemcpy(&r, d_pr, sizeof(r), cudaMemcpyDeviceToHost));
+        std::printf("issuer-side cost of a readiness check (cycles, mean of 50): smem idle / 12 warps storing\n");
+        std::printf("  mbarrier.try_wait (completed)   %5lld / %5lld (max %lld)\n", r.tw_idle, r.tw_busy, r.tw_max_busy);
+        std::printf("  mbarrier.test_wait (completed)  %5lld / %5lld\n", r.tt_idle, r.tt_busy);
+        std::printf("  named barrier.sync (single lane, partner arrived 400 cycles earlier) %5lld / %5lld (max %lld)\n", r.nb_idle, r.nb_busy, r.nb_max_busy);
+    }
+    {
+        unsigned char* d_src;
+        CK(cudaMalloc(&d_src, 1 << 20));
+        CK(cudaMemset(d_src, 0, 1 << 20));
+        for (int grid : {1, 148}) {
+            for (int bytes : {3072, 9216, 27648}) {
+                run_copy<0>(d_src, bytes, 1, grid);
+                run_copy<1>(d_src, bytes, 1, grid);
+            }
+            run_copy<0>(d_src, 27648, 9, grid);
+            run_copy<1>(d_src, 27648, 9, grid);
+        }
+    }
     float* d_out;
     CK(cudaMalloc(&d_out, 128 * 8 * 4));
     for (int cfg = 0; cfg < 4; ++cfg) {
