@@ -60,23 +60,14 @@ namespace dbn {
 // ---------------------------------------------------------------------------------------------
 // geometry
 // ---------------------------------------------------------------------------------------------
-// The warp scheduler favours higher warp ids, so the two single-lane control warps get the LOWEST
-// ids: their issue / spin loops then only take slots the epilogue warps leave idle.
-#ifndef DBN_TC_CONTROL_HIGH
-#define DBN_TC_CONTROL_HIGH 1
-#endif
+// Warps 0-11: epilogue / CUDA-core stages; warp 12: weight loader; warps 13 and 14: the two MMA issuers.
 constexpr int kEpiWarps = 12;
-#if DBN_TC_CONTROL_HIGH
-constexpr int kEpiWarp0 = 0;                    // warps 0-11: epilogue / CUDA-core stages
-constexpr int kLoadWarp = 12;                   // warp 12: weight loader
-constexpr int kMmaWarp = 13;                    // warp 13: TMEM allocator + MMA issuer
-#else
-constexpr int kMmaWarp = 0;                     // warp 0: TMEM allocator + MMA issuer
-constexpr int kLoadWarp = 1;                    // warp 1: weight loader
-constexpr int kEpiWarp0 = 2;                    // warps 2-13: epilogue / CUDA-core stages
-#endif
+constexpr int kEpiWarp0 = 0;
+constexpr int kLoadWarp = 12;
+constexpr int kMmaWarp = 13;                    // issuer 0 (also allocates / frees tensor memory)
+constexpr int kMmaWarpB = 14;                   // issuer 1
 constexpr int kEpiThreads = kEpiWarps * 32;
-constexpr int kTcThreads = (2 + kEpiWarps) * 32;
+constexpr int kTcThreads = (3 + kEpiWarps) * 32;
 constexpr int kActBytes = 98688;                // 2 x [6][514][8] bf16
 constexpr int kWPart0 = 15360;                  // weight part 0: up to 5 K blocks x (hi + lo) x 1536 B
 constexpr int kWPart1 = 12288;                  // weight part 1: up to 4 K blocks
@@ -87,7 +78,9 @@ constexpr int kSmemAct1 = kActBytes;
 constexpr int kSmemWbuf = 2 * kActBytes;
 constexpr int kSmemPrm = kSmemWbuf + kWbufBytes;
 constexpr int kSmemBar = kSmemPrm + kPrmFloats * 4;   // mbarriers, tmem pointer, reduction scratch
-constexpr int kTcSmemBytes = kSmemBar + 576;   // [0,72) mbarriers, 96 TMEM pointer, [128,512) reduction scratch, [512,576) joint rings
+constexpr int kJointSlots = 7;                  // accumulator slots (64 TMEM columns each) the joint jobs rotate over
+constexpr int kJointRing = 16;                  // joint MMA-done / epilogue-done mbarriers: one per joint epilogue, never reused
+constexpr int kTcSmemBytes = kSmemBar + 512 + 2 * 8 * kJointRing;   // [0,72) mbarriers, 96 TMEM pointer, [128,384) joint weight barriers, 384 bar_x, [512,768) joint MMA / epilogue barriers
 static_assert(kTcSmemBytes <= 232448, "shared memory budget");
 constexpr int kTmemCols = 512;
 constexpr int kTmemWindowCols = 256;
@@ -831,13 +824,17 @@ __device__ __forceinline__ void issue_job_part(int ntaps, int ncb, uint32_t dwin
 struct alignas(16) IssueRec {
     uint32_t n, idesc, ntiles, lp;                 // word 0
     uint32_t tap16[3], lo16;                       // word 1
-    uint32_t shape, cb0, tcol, flags;              // word 2: shape = ncb | ntaps << 8; flags = first | last << 1 | joint << 2
+    uint32_t shape, cb0, tcol, flags;              // word 2: shape = ncb | ntaps << 8 | jk << 16 (jk = index among the joint jobs);
+                                                   // flags = first | last << 1 | joint << 2 | owner << 4 | both << 5
     uint32_t need, eseq, blk16, part1_16;          // word 3: blk16 = one K=16 block of B, part1_16 = offset of weight part 1 behind part 0 (joint jobs), 16-byte units
 };
 static_assert(sizeof(IssueRec) == 64, "IssueRec is read as four 16-byte words");
 struct IssueArgs {
     uint32_t n, idesc, ntiles, lp, lo16, cb0, tcol, tap16[3], blk16, part1_16;
     int ntaps, ncb, first, last, joint, need, eseq;
+    int jk;       // joint jobs: index among the joint jobs (weight slot (jk + 1) % 3)
+    int owner;    // joint jobs: the issuer (0 / 1) that issues the job
+    int both;     // single-window jobs: issuer 0 issues both windows (conv1d_2..4); otherwise issuer w issues window w
 };
 // The four raw words of a record.  They are fetched with volatile loads at the top of the PREVIOUS job's
 // iteration and not touched (not even unpacked) until the job starts, so the whole latency is hidden.
@@ -860,8 +857,10 @@ __device__ __forceinline__ IssueArgs unpack_issue(const IssueRaw& r) {
     IssueArgs a;
     a.n = r.w0.x; a.idesc = r.w0.y; a.ntiles = r.w0.z; a.lp = r.w0.w;
     a.tap16[0] = r.w1.x; a.tap16[1] = r.w1.y; a.tap16[2] = r.w1.z; a.lo16 = r.w1.w;
-    a.ncb = static_cast<int>(r.w2.x & 0xFFu); a.ntaps = static_cast<int>(r.w2.x >> 8); a.cb0 = r.w2.y; a.tcol = r.w2.z;
-    a.first = static_cast<int>(r.w2.w & 1u); a.last = static_cast<int>((r.w2.w >> 1) & 1u); a.joint = static_cast<int>(r.w2.w >> 2);
+    a.ncb = static_cast<int>(r.w2.x & 0xFFu); a.ntaps = static_cast<int>((r.w2.x >> 8) & 0xFFu); a.jk = static_cast<int>(r.w2.x >> 16);
+    a.cb0 = r.w2.y; a.tcol = r.w2.z;
+    a.first = static_cast<int>(r.w2.w & 1u); a.last = static_cast<int>((r.w2.w >> 1) & 1u); a.joint = static_cast<int>((r.w2.w >> 2) & 3u);
+    a.owner = static_cast<int>((r.w2.w >> 4) & 1u); a.both = static_cast<int>((r.w2.w >> 5) & 1u);
     a.need = static_cast<int>(r.w3.x); a.eseq = static_cast<int>(r.w3.y); a.blk16 = r.w3.z; a.part1_16 = r.w3.w;
     return a;
 }
@@ -887,12 +886,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const uint32_t bar_mma[2] = {bar0 + 32, bar0 + 40};
     const uint32_t bar_epi[2] = {bar0 + 48, bar0 + 56};
     const uint32_t bar_final = bar0 + 64;
-    // joint phase: rings of 4 (the MMA issuer runs at most 3 epilogues ahead, see TcJob::need)
-    const uint32_t bar_jmma = bar0 + 512, bar_jepi = bar0 + 544;   // + 8 * (eseq & 3)
+    // joint phase: one MMA-done and one epilogue-done barrier per joint epilogue (kJointRing >= their number)
+    const uint32_t bar_jmma = bar0 + 512, bar_jepi = bar0 + 512 + 8 * kJointRing;   // + 8 * eseq
     // joint phase weights: three whole-job slots (the normal weight buffer and two halves of the upper
     // part of window 1's ACT region, which is dead from conv1d_8 on), so that the loader runs two
     // jobs ahead of the MMA issuer and independent jobs follow each other without a weight bubble
-    const uint32_t bar_jwfull0 = bar0 + 72, bar_jwfree0 = bar0 + 104;   // + 8 * slot
+    // one weights-landed and one weights-free barrier PER JOINT JOB (never reused: the two issuers each see only
+    // their own jobs, and a parity wait is only safe for a waiter that has observed every earlier phase)
+    const uint32_t bar_jwfull0 = bar0 + 128, bar_jwfree0 = bar0 + 256;   // + 8 * jk
+    const uint32_t bar_x = bar0 + 384;   // both windows' epilogues of the last single-window job are done
     const uint32_t jwslot1 = sbase + kSmemAct1 + kYOff, jwslot2 = jwslot1 + kWbufBytes;
     volatile uint32_t* tmem_slot = reinterpret_cast<volatile uint32_t*>(smem + kSmemBar + 96);
     const int tid = threadIdx.x;
@@ -954,18 +956,19 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     if (threadIdx.x == kLoadWarp * 32) {
         mbar_init(bar_wfull[0], 1);
         mbar_init(bar_wfull[1], 1);
-        mbar_init(bar_wfree[0], 1);
-        mbar_init(bar_wfree[1], 1);
+        mbar_init(bar_wfree[0], 2);   // one commit per window pass (issuer 0 commits twice where it issues both windows)
+        mbar_init(bar_wfree[1], 2);
         mbar_init(bar_mma[0], 1);
         mbar_init(bar_mma[1], 1);
         mbar_init(bar_epi[0], kEpiArrivals);
         mbar_init(bar_epi[1], kEpiArrivals);
-        mbar_init(bar_final, 1);
-        for (int i = 0; i < 3; ++i) {
+        mbar_init(bar_final, 2);
+        for (int i = 0; i < kJointRing; ++i) {
             mbar_init(bar_jwfull0 + 8 * i, 1);
             mbar_init(bar_jwfree0 + 8 * i, 1);
         }
-        for (int i = 0; i < 4; ++i) {
+        mbar_init(bar_x, 2 * kEpiArrivals);
+        for (int i = 0; i < kJointRing; ++i) {
             mbar_init(bar_jmma + 8 * i, 1);
             mbar_init(bar_jepi + 8 * i, kEpiArrivals);
         }
@@ -1001,7 +1004,9 @@ __global__ void __launch_bounds__(kTcThreads, 1)
 #pragma unroll
             for (int q = 0; q < 4; ++q)
                 for (int o = 16; o > 0; o >>= 1) s[q] += __shfl_xor_sync(0xffffffffu, s[q], o);
-            long long* red = reinterpret_cast<long long*>(smem + kSmemBar + 128);   // [12 warps][4]: 384 B
+            // scratch [12 warps][4] (384 B) at the start of window 0's region: conv1_stage writes its first row there
+            // only after two more barriers of the epilogue threads
+            long long* red = reinterpret_cast<long long*>(smem + kSmemAct0);
             if ((tid & 31) == 0) {
 #pragma unroll
                 for (int q = 0; q < 4; ++q) red[ewarp * 4 + q] = s[q];
@@ -1045,12 +1050,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const int e = J.eseq;
                 long long* tr = (trace && blockIdx.x == 0 && tid == 0) ? trace + (j * 2) * 16 : nullptr;
                 run_epilogue(P, J, sbase + kSmemAct0, sbase + kSmemAct0, 0, prm, tmem_base + J.tcol, tid,
-                             bar_jmma + 8 * (e & 3), (e >> 2) & 1, p0, p1, tr);
+                             bar_jmma + 8 * e, 0, p0, p1, tr);
                 if (tr) tr[6] = clock64();
                 fence_proxy_async();
                 if (tr) tr[7] = clock64();
                 tc_fence_before();
-                epi_arrive(bar_jepi + 8 * (e & 3));
+                epi_arrive(bar_jepi + 8 * e);
                 if (tr) tr[3] = clock64();
                 continue;
             }
@@ -1065,6 +1070,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 if (tr) tr[7] = clock64();
                 tc_fence_before();
                 epi_arrive(bar_epi[w]);
+                if (j + 1 < njobs && c_jobs[j + 1].joint) epi_arrive(bar_x);
                 if (tr) tr[3] = clock64();
             }
         }
@@ -1075,23 +1081,31 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int i = tid; i < 2 * kActBytes / 16; i += kEpiThreads)
                     reinterpret_cast<uint4*>(P.dbg_out)[i] = reinterpret_cast<const uint4*>(smem)[i];
         }
-    } else if (warp == kMmaWarp) {
-        // ================= MMA issuer (one elected lane of a converged warp) =================
+    } else if (warp == kMmaWarp || warp == kMmaWarpB) {
+        // ================= the two MMA issuers (one elected lane of each warp) =================
+        // A single issuing thread is the bottleneck of everything behind conv1d_4: between two jobs it needs
+        // ~1 000 cycles (wait for the queue to drain before the commits may overwrite uniform registers the
+        // queued MMAs reference, barrier polls, descriptor set-up) against ~850 cycles of MMAs of a small job,
+        // and the tensor pipe only has the ~8 MMAs of its queue to bridge that.  So there are two issuers:
+        //   * conv1d_2..4 (`both`): issuer 0 alone, window 0 then window 1 - the tensor pipe is saturated
+        //     there, and strict alternation keeps one window's epilogue under the other window's MMAs;
+        //   * conv1d_5..9: issuer w issues window w, so the two windows form independent chains;
+        //   * joint jobs: issued by their `owner` (the jobs alternate; the K-slices of conv1d_17 stay with one
+        //     issuer so that the accumulation order is fixed).
+        // tcgen05.commit only tracks the MMAs of the committing thread, which is exactly what every barrier
+        // here wants.  All barrier parities follow from the job index (every single-window job completes one
+        // phase of bar_epi[w] / bar_wfull[p] / bar_wfree[p]), so the issuers share no state.
         // A full 512-column allocation by the only CTA on the SM starts at TMEM address 0; using
         // the literal keeps every MMA operand derived from uniform sources.
         if (tmem_base != 0) __trap();
+        const int me = warp == kMmaWarp ? 0 : 1;
         if (elect_one()) {
             constexpr uint32_t leader = 1;   // (a converged-warp variant with predicated tcgen05 ops was slower: R2UR.BROADCAST per operand)
             const bool tracing = trace && blockIdx.x == 0;
-            uint32_t wfull_phase = 0, epi_phase[2] = {0, 0};
-            int jepi_seen = 0;   // joint epilogues known to be complete
-            bool pre_epi[2] = {false, false}, pre_wfull0 = false;   // early probes that already succeeded
-            int jk = 0;          // joint jobs issued so far (weight slot = jk % 3)
             const uint32_t wp16[2] = {wbuf >> 4, (wbuf + kWPart0) >> 4};
             const uint32_t act16_0 = (sbase + kSmemAct0) >> 4, act16_1 = (sbase + kSmemAct1) >> 4;
-            // The issuer is ONE thread: a chain of dependent constant loads costs it ~40 cycles per
-            // link, so the next job's descriptor is fetched (from the global copy of the table) while
-            // this job's MMAs are issued.
+            // The next job's record is fetched (raw, see IssueRec) while this job's MMAs are issued.
+            bool in_joint = false;
             IssueRaw nxt = load_issue_raw(P.issue);
             for (int j = 0; j < njobs; ++j) {
                 const IssueArgs J = unpack_issue(nxt);
@@ -1099,31 +1113,22 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t blk16 = J.blk16;                  // one K=16 block of B, in 16-byte units
                 const uint32_t tap16[3] = {J.tap16[0], J.tap16[1], J.tap16[2]};
                 const bool first = J.first != 0, last = J.last != 0;
-                if (tracing) trace[(j * 2) * 16 + 11] = clock64();
+                const uint32_t par = static_cast<uint32_t>(j) & 1u;   // parity of the single-window barriers for job j
                 if (J.joint) {
+                    if (J.owner != me) continue;
                     // ---- both windows in one burst: [part 0: w0, w1] [part 1: w0, w1], one commit ----
-                    // weights first (whole job in slot jk % 3, normally landed long ago: the poll then
-                    // overlaps the wait for the job's input instead of following it)
-                    const int slot = jk % 3;
+                    // whole job's weights in slot (jk + 1) % 3 (slot 0 = the two-part buffer, which the last
+                    // single-window job still uses while the first two joint jobs are loaded)
+                    const int jk = J.jk, slot = (jk + 1) % 3;
                     const uint32_t jw0_16 = (slot == 0 ? wbuf : slot == 1 ? jwslot1 : jwslot2) >> 4;
                     const uint32_t jw1_16 = jw0_16 + J.part1_16;   // behind part 0
-                    mbar_wait(bar_jwfull0 + 8 * slot, (jk / 3) & 1);
+                    if (tracing) trace[(j * 2) * 16 + 11] = clock64();
+                    mbar_wait(bar_jwfull0 + 8 * jk, 0);
                     if (tracing) trace[(j * 2) * 16 + 12] = clock64();
-                    if (tracing) {   // in-situ cost of a poll of a barrier whose phase is known to be complete
-                        const long long t0 = clock64();
-                        mbar_wait(bar_jwfull0 + 8 * slot, (jk / 3) & 1);
-                        trace[(j * 2 + 1) * 16 + 14] = clock64() - t0;
-                        trace[(j * 2 + 1) * 16 + 13] = mbar_test(bar_jwfull0 + 8 * slot, (jk / 3) & 1) ? clock64() - t0 : -1;
-                    }
-                    if (first && J.eseq == 0) {   // first joint job: the per-window epilogues of the last
-#pragma unroll
-                        for (int w = 0; w < 2; ++w) {   // single-window job must be done
-                            if (!pre_epi[w]) mbar_wait(bar_epi[w], epi_phase[w]);
-                            epi_phase[w] ^= 1;
-                        }
-                    }
-                    for (const int need = J.need; jepi_seen < need; ++jepi_seen)
-                        mbar_wait(bar_jepi + 8 * (jepi_seen & 3), (jepi_seen >> 2) & 1);
+                    if (!in_joint) mbar_wait(bar_x, 0);   // this issuer's first joint job: both windows' epilogues of the last
+                    in_joint = true;                      // single-window job (X of both windows written, accumulators drained)
+                    // epilogues complete in order and `need` never decreases: the last needed one is enough
+                    if (J.need > 0) mbar_wait(bar_jepi + 8 * (J.need - 1), 0);
                     if (tracing) trace[(j * 2) * 16 + 13] = clock64();
                     tc_fence_after();
                     if (tracing) trace[(j * 2) * 16 + 0] = clock64();
@@ -1140,45 +1145,50 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         issue_job_part<1>(J.ntaps, J.ncb, dcol + (static_cast<uint32_t>(16 * w) << 16), 1,
                                           (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, jw1_16, blk16, J.n,
                                           J.idesc, false, leader);
-                    if (last) tc_commit(bar_jmma + 8 * (J.eseq & 3), leader);
-                    tc_commit(bar_jwfree0 + 8 * slot, leader);
+                    if (tracing) trace[(j * 2) * 16 + 14] = clock64();   // last MMA issued
+                    if (last) tc_commit(bar_jmma + 8 * J.eseq, leader);
+                    tc_commit(bar_jwfree0 + 8 * jk, leader);
                     if (tracing) trace[(j * 2) * 16 + 1] = clock64();
-                    ++jk;
                     continue;
                 }
-#pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                    if (first) {   // input written and previous accumulators drained
-                        if (!pre_epi[w]) mbar_wait(bar_epi[w], epi_phase[w]);
-                        pre_epi[w] = false;
-                        epi_phase[w] ^= 1;
-                    }
+                if (J.both && me != 0) {
+                    // issuer 1 only follows the barriers it will wait on later: a parity wait is only safe for a
+                    // waiter that has observed every earlier phase
+                    mbar_wait(bar_epi[1], par);
+                    mbar_wait(bar_wfull[0], par);
+                    mbar_wait(bar_wfull[1], par);
+                    continue;
+                }
+                const int w_first = J.both ? 0 : me, w_last = J.both ? 1 : me;
+                for (int w = w_first; w <= w_last; ++w) {
+                    // issuer 0 frees the weight parts for both windows when it issues both
+                    const bool free_now = w == w_last;
+                    const int nfree = J.both ? 2 : 1;
+                    if (tracing) trace[(j * 2 + w) * 16 + 11] = clock64();
+                    mbar_wait(bar_epi[w], par);   // input written and previous accumulators drained
                     if (tracing) trace[(j * 2 + w) * 16 + 12] = clock64();
                     tc_fence_after();
                     if (tracing) trace[(j * 2 + w) * 16 + 0] = clock64();
                     const uint32_t dwin = w * kTmemWindowCols;
                     // ---- weight part 0 (first K blocks); freed early so the loader can refill it ----
-                    if (w == 0 && !pre_wfull0) mbar_wait(bar_wfull[0], wfull_phase);
-                    if (w == 0) pre_wfull0 = false;
+                    if (w == w_first) mbar_wait(bar_wfull[0], par);
                     if (tracing) trace[(j * 2 + w) * 16 + 8] = clock64();
                     issue_job_part<0>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[0],
                                       blk16, J.n, J.idesc, first, leader);
-                    if (w == 1) tc_commit(bar_wfree[0], leader);
+                    if (free_now)
+                        for (int c = 0; c < nfree; ++c) tc_commit(bar_wfree[0], leader);
                     if (tracing) trace[(j * 2 + w) * 16 + 9] = clock64();
                     // ---- weight part 1 (remaining K blocks) ----
-                    if (w == 0) mbar_wait(bar_wfull[1], wfull_phase);
+                    if (w == w_first) mbar_wait(bar_wfull[1], par);
                     if (tracing) trace[(j * 2 + w) * 16 + 10] = clock64();
-                    // probe the barrier of the NEXT pass now; the answer arrives while part 1 is issued
-                    if (w == 0) pre_epi[1] = mbar_test(bar_epi[1], epi_phase[1]);
-                    else pre_epi[0] = mbar_test(bar_epi[0], epi_phase[0]);
                     issue_job_part<1>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[1],
                                       blk16, J.n, J.idesc, false, leader);
+                    if (tracing) trace[(j * 2 + w) * 16 + 14] = clock64();   // last MMA issued
                     if (last) tc_commit(bar_mma[w], leader);
-                    if (w == 1) tc_commit(bar_wfree[1], leader);
+                    if (free_now)
+                        for (int c = 0; c < nfree; ++c) tc_commit(bar_wfree[1], leader);
                     if (tracing) trace[(j * 2 + w) * 16 + 1] = clock64();
                 }
-                wfull_phase ^= 1;
-                if (j + 1 < njobs) pre_wfull0 = mbar_test(bar_wfull[0], wfull_phase);
             }
             tc_commit(bar_final, leader);
             mbar_wait(bar_final, 0);
@@ -1190,23 +1200,24 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         for (int j = 0; j < njobs; ++j) {
             const TcJob& J = c_jobs[j];
             const unsigned char* src = P.w + J.w_goff;
-            if (J.joint) {   // whole job ([part 0 | part 1] as packed) into slot jk % 3
-                const int slot = jk % 3;
-                if (jk == 0) {   // slot 0 is the normal weight buffer: the last two-part job must be done with it
-                    if (j > 0) {
+            if (J.joint) {   // whole job ([part 0 | part 1] as packed) into slot (jk + 1) % 3
+                const int slot = (jk + 1) % 3;
+                if (jk == 2) {   // first use of slot 0, the normal weight buffer: the last two-part job must be done with it
+                    if (j > 2) {
                         mbar_wait(bar_wfree[0], free_phase);
                         mbar_wait(bar_wfree[1], free_phase);
                     }
                 } else if (jk >= 3) {
-                    mbar_wait(bar_jwfree0 + 8 * slot, (jk / 3 - 1) & 1);
+                    mbar_wait(bar_jwfree0 + 8 * (jk - 3), 0);
                 }
-                // (slots 1 and 2 lie in window 1's region above everything conv1d_8.. keeps there; the
-                // loader gets here only after conv1d_9's weights were requested, i.e. after conv1d_8's
+                // (slots 1 and 2 - used by the first two joint jobs, whose weights are therefore requested while
+                // conv1d_9 is still running - lie in window 1's region above everything conv1d_8.. keeps there;
+                // the loader gets here only after conv1d_9's weights were requested, i.e. after conv1d_8's
                 // MMAs - and with them conv1d_7's epilogue, the last user of that space - completed)
                 const uint32_t bytes = J.w_part[0] + J.w_part[1];
                 if (trace && blockIdx.x == 0) trace[(j * 2 + 1) * 16 + 15] = clock64();   // when the load was issued
-                mbar_expect_tx(bar_jwfull0 + 8 * slot, bytes);
-                bulk_g2s(slot == 0 ? wbuf : slot == 1 ? jwslot1 : jwslot2, src, bytes, bar_jwfull0 + 8 * slot);
+                mbar_expect_tx(bar_jwfull0 + 8 * jk, bytes);
+                bulk_g2s(slot == 0 ? wbuf : slot == 1 ? jwslot1 : jwslot2, src, bytes, bar_jwfull0 + 8 * jk);
                 ++jk;
                 continue;
             }
@@ -1366,16 +1377,16 @@ struct JobBuilder {
         }
     }
 
-    // Mark the jobs from index `j0` on as the joint phase: accumulator slots rotate over three 64-column
+    // Mark the jobs from index `j0` on as the joint phase: accumulator slots rotate over kJointSlots 64-column
     // slots (K-slices of one conv share a slot) and `need` is derived from the data flow: `producer[j]`
     // = job whose epilogue writes this job's input (-1: available before the joint phase).
     void finish_joint(int j0, const std::vector<int>& producer, int slot_cols = kTmemTileCols) {
         std::vector<int> eseq_of(jobs.size(), -1), slot_of(jobs.size(), 0);
         int e = 0, slot = -1;
-        std::vector<int> last_user(3, -1);   // job with the epilogue that last drained the slot
+        std::vector<int> last_user(kJointSlots, -1);   // job with the epilogue that last drained the slot
         for (size_t j = j0; j < jobs.size(); ++j) {
             TcJob& J = jobs[j];
-            if (J.first) slot = (slot + 1) % 3;
+            if (J.first) slot = (slot + 1) % kJointSlots;
             slot_of[j] = slot;
             J.tcol = slot * slot_cols;
             int need = 0;
@@ -1410,9 +1421,11 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     // 32-channel tensor: both are 1x1 convs of X, so ONE job with N = 32 computes them); Y (parity
     // split, both windows) in window 0's region @43392.  The average pool in front of conv1d_10 is
     // folded into its weights (k=3, W/3).  Concat order [conv10, conv11, conv13, conv16]
-    // (network_architecture.py:68), BN5 per channel.  Job order: the long dependency chain
-    // conv1d_14 -> 15 -> 16 first, independent branches in between, so that the MMAs of one job run
-    // while the epilogue warps drain another.
+    // (network_architecture.py:68), BN5 per channel.  Job order: the dependency chain conv1d_14 -> 15 -> 16
+    // with the independent branches between its links (conv1d_10 behind conv1d_12+14, conv1d_11 and 13
+    // behind conv1d_15), each in its own accumulator slot, and the jobs alternate between the two MMA
+    // issuers, so that the tensor pipe always has a job whose input is ready while the epilogue warps
+    // drain the previous ones.
     const int j0 = static_cast<int>(B->jobs.size());
     std::vector<int> producer;
     auto joint = [&](TcJob& J, int kind, int prod) {
@@ -1422,15 +1435,18 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
         producer.push_back(prod);
     };
     joint(B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 25344, 0, 14), JOINT_PAIR, -1);              // j0: -> [4][66][8], lo +4224
-    joint(B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6), JOINT_PAIR, -1);                   // j0+1
+    joint(B->add(10, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 0, 0, true), JOINT_PAIR, -1);          // j0+1: avg pool folded
     B->jobs.back().zero_y = 1;
     joint(B->add(15, 64, 25344 + 2 * 66 * 16, 66, 4224, EPI_N48, 0, 12672, 0), JOINT_PAIR, j0);   // j0+2: groups 2-3 (conv1d_14)
-    joint(B->add(13, 64, 25344, 66, 4224, EPI_PARITY, 5, 0, 12), JOINT_PAIR, j0);              // j0+3: groups 0-1 (conv1d_12)
-    joint(B->add(10, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 0, 0, true), JOINT_PAIR, -1);          // j0+4: avg pool folded
+    joint(B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6), JOINT_PAIR, -1);                   // j0+3
+    joint(B->add(13, 64, 25344, 66, 4224, EPI_PARITY, 5, 0, 12), JOINT_PAIR, j0);              // j0+4: groups 0-1 (conv1d_12)
     joint(B->add(16, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 18), JOINT_PAIR, j0 + 2);          // j0+5
     // conv1d_17 .. conv1d_20, JOINT_STACK: both windows stacked in one tile (row = 18 w + position).
     // conv1d_17: stride 2 on the parity-split Y (tap0 = Ye[i], tap1 = Yo[i], tap2 = Ye[i+1]),
-    // K = 3 x 192 split in 4 jobs of 3 channel blocks so each weight chunk fits the buffer
+    // K = 3 x 192 split in 4 jobs of 3 channel blocks so each weight chunk fits the buffer; slice s reads
+    // the 48 channels written by one inception branch (concat order conv1d_10, 11, 13, 16), so the first
+    // three slices are issued while conv1d_16 is still in flight
+    const int y_writer[4] = {j0 + 1, j0 + 3, j0 + 4, j0 + 5};
     for (int s = 0; s < 4; ++s) {
         TcJob J{};
         J.n = 48; J.idesc = 64; J.ntiles = 1; J.L = 34; J.lp = kYRows; J.ntaps = 3;
@@ -1444,7 +1460,7 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
         B->pack_weights(17, 48, 3 * s, 3, &J);
         if (J.last) B->pack_params(17, 48, 6, 0, &J);
         B->jobs.push_back(J);
-        producer.push_back(s == 0 ? j0 + 5 : -1);   // every Y writer precedes conv1d_16's epilogue
+        producer.push_back(y_writer[s]);
     }
     joint(B->add(18, 34, 0, 36, 3456, EPI_N48, 0, 0, 0), JOINT_STACK, j0 + 9);
     joint(B->add(19, 34, 0, 36, 3456, EPI_N48_POOL_BN, 7, 0, 0), JOINT_STACK, j0 + 10);   // -> [6][19][8], lo +1824
@@ -1475,15 +1491,15 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
 }
 
 // The MMA issuer's view of a (finalized) job.
-static IssueRec issue_record(const TcJob& J) {
+static IssueRec issue_record(const TcJob& J, int jk, int owner, bool both) {
     IssueRec r{};
     r.n = static_cast<uint32_t>(J.n); r.idesc = static_cast<uint32_t>(J.idesc); r.ntiles = static_cast<uint32_t>(J.ntiles);
     r.lp = static_cast<uint32_t>(J.lp);
     for (int t = 0; t < 3; ++t) r.tap16[t] = static_cast<uint32_t>(J.tap16[t]);
     r.lo16 = static_cast<uint32_t>(J.lo16);
-    r.shape = static_cast<uint32_t>(J.ncb | (J.ntaps << 8));
+    r.shape = static_cast<uint32_t>(J.ncb | (J.ntaps << 8) | (jk << 16));
     r.cb0 = static_cast<uint32_t>(J.cb0); r.tcol = static_cast<uint32_t>(J.tcol);
-    r.flags = static_cast<uint32_t>((J.first ? 1 : 0) | (J.last ? 2 : 0) | (J.joint << 2));
+    r.flags = static_cast<uint32_t>((J.first ? 1 : 0) | (J.last ? 2 : 0) | (J.joint << 2) | (owner << 4) | (both ? 32 : 0));
     r.need = static_cast<uint32_t>(J.need); r.eseq = static_cast<uint32_t>(J.eseq);
     r.blk16 = 2u * static_cast<uint32_t>(J.n);
     r.part1_16 = (J.ntaps * J.ncb == 9 ? 10u : 4u) * r.blk16;
@@ -1497,8 +1513,17 @@ TcEngine* tc_create(const Blob& blob) {
     if (!build_jobs(blob, &B, &P)) return nullptr;
     TcEngine* e = new TcEngine();
     e->jobs = B.jobs;
+    // issuer assignment: conv1d_2..4 (L = 512) by issuer 0 for both windows, conv1d_5..9 one window per issuer;
+    // the joint jobs alternate between the issuers, the K-slices of one conv staying together
     std::vector<IssueRec> recs;
-    for (const TcJob& J : B.jobs) recs.push_back(issue_record(J));
+    int jk = 0, owner = 1, nepi = 0;
+    for (const TcJob& J : B.jobs) {
+        if (J.joint && J.first) owner ^= 1;
+        recs.push_back(issue_record(J, J.joint ? jk : 0, J.joint ? owner : 0, !J.joint && J.L >= 512));
+        if (J.joint) ++jk;
+        if (J.joint && J.last) ++nepi;
+    }
+    if (nepi > kJointRing) return nullptr;
     bool ok = cudaMalloc(&e->d_w, B.w.size()) == cudaSuccess &&
               cudaMalloc(&e->d_prm, B.prm.size() * sizeof(float)) == cudaSuccess &&
               cudaMemcpy(e->d_w, B.w.data(), B.w.size(), cudaMemcpyHostToDevice) == cudaSuccess &&

@@ -63,10 +63,10 @@ JOBS = [
     (6, 'conv8', lambda d, w: decode(d[w], 0, 6, 130, 128, 12480)),
     (7, 'bn4', lambda d, w: decode(d[w], 0, 6, 66, 64, 6336)),
     (8, 'conv12+14', lambda d, w: decode(d[w], 25344, 4, 66, 64, 4224)),
-    (9, 'bn5:48', lambda d, w: decode_parity(d[0], w, 6, 6)),
+    (9, 'bn5:0', lambda d, w: decode_parity(d[0], w, 0, 6)),      # average pool folded into conv1d_10
     (10, 'conv15', lambda d, w: decode(d[w], 12672, 6, 66, 64, 6336)),
-    (11, 'bn5:96', lambda d, w: decode_parity(d[0], w, 12, 6)),
-    (12, 'bn5:0', lambda d, w: decode_parity(d[0], w, 0, 6)),     # average pool folded into conv1d_10
+    (11, 'bn5:48', lambda d, w: decode_parity(d[0], w, 6, 6)),
+    (12, 'bn5:96', lambda d, w: decode_parity(d[0], w, 12, 6)),
     (13, 'bn5:144', lambda d, w: decode_parity(d[0], w, 18, 6)),
     (17, 'bn6', lambda d, w: decode_stacked(d[0], w, 36, 16, 18, 3456)),
     (18, 'conv18', lambda d, w: decode_stacked(d[0], w, 36, 16, 18, 3456)),

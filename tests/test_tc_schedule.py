@@ -4,7 +4,7 @@ the C ABI without a GPU (db_tc_job_table).
 The joint phase lets the MMA issuer run ahead of the epilogue warps: every joint job carries `need`,
 the number of joint epilogues that must have completed before its MMAs may be issued.  These tests
 re-derive the hazards from the table itself - shared-memory tensors (who wrote what a job reads),
-accumulator slots (who drained the slot a job overwrites), the 4-deep mbarrier rings - so that an edit
+accumulator slots (who drained the slot a job overwrites), the one-barrier-per-epilogue arrays - so that an edit
 of the job order or of the buffer layout that forgets a dependency fails here, on the CPU."""
 import numpy as np
 import pytest
@@ -16,7 +16,7 @@ FIELDS = ('n idesc ntiles L lp ntaps tap0 tap1 tap2 lo16 ncb cb0 w_goff tcol wp0
 EPI_N48, EPI_N48_POOL_BN, EPI_N48_BN, EPI_N16, EPI_PARITY, EPI_HEAD = range(6)
 JOINT_NONE, JOINT_PAIR, JOINT_STACK = range(3)
 W_PART0, W_PART1 = 15360, 12288
-RING = 4
+RING = 16     # kJointRing: one MMA-done / epilogue-done / weights barrier per joint epilogue resp. joint job, never reused
 
 
 def job_table(name, which):
@@ -74,16 +74,20 @@ def test_joint_schedule_is_hazard_free(name, which, njobs):
         assert all(j['tcol'] + 64 <= 256 for j in jobs) and all(j['ntiles'] <= 4 for j in jobs)
 
     slot_drained_by = {}     # accumulator slot -> eseq of the epilogue that last read it
-    writer_of = []           # (extent, eseq, is_parity) of tensors written by epilogues of the sequence
+    writer_of = []           # (extent, eseq, channel groups of the concat tensor or None) written by epilogues of the sequence
     done_epilogues = e0
     for k, j in enumerate(seq):
         # (a) the tensor the job reads was written by an epilogue that `need` covers
         if j['joint'] == JOINT_STACK and j['kind'] == EPI_N48_BN and j['ntaps'] == 3 and j['ncb'] == 3 and \
                 j['lo16'] * 16 > 8192:
-            producers = [e for (_, e, parity) in writer_of if parity]          # conv1d_17 reads the concat tensor
+            # a K-slice of conv1d_17 reads channel groups [2 cb0, 2 cb0 + 2 ncb) of the concat tensor: the branch
+            # whose epilogue wrote exactly those groups must be complete
+            g0, g1 = 2 * j['cb0'], 2 * j['cb0'] + 2 * j['ncb']
+            producers = [e for (_, e, parity) in writer_of if parity is not None and parity[0] < g1 and g0 < parity[1]]
+            assert producers, (k, j)
         else:
             lo, hi = in_extent(j)
-            producers = [e for ((a, b), e, parity) in writer_of if not parity and a < hi and lo < b]
+            producers = [e for ((a, b), e, parity) in writer_of if parity is None and a < hi and lo < b]
         if producers:
             assert j['need'] >= max(producers) + 1, (k, j, producers)
         # (b) the accumulator slot(s) were drained
@@ -91,15 +95,16 @@ def test_joint_schedule_is_hazard_free(name, which, njobs):
         for c in cols:
             if j['first'] and c in slot_drained_by:
                 assert j['need'] >= slot_drained_by[c] + 1, (k, j)
-        # (c) the 4-deep mbarrier rings never hold more than three unconsumed phases
+        # (c) every joint job / joint epilogue has its own barrier
         if j['last']:
             done_epilogues += 1
-        assert done_epilogues - j['need'] <= RING - 1, (k, j)
+        assert done_epilogues <= RING and k < RING, (k, j)
         if j['last']:
             for c in cols:
                 slot_drained_by[c] = j['eseq']
             if j['kind'] != EPI_HEAD:
-                writer_of.append((out_extent(j), j['eseq'], j['kind'] == EPI_PARITY))
+                groups = (j['out_cg'], j['out_cg'] + j['out_ncg']) if j['kind'] == EPI_PARITY else None
+                writer_of.append((out_extent(j), j['eseq'], groups))
     # the head is the last epilogue and waits for everything before it
     assert joint[-1]['kind'] == EPI_HEAD and joint[-1]['need'] == eseq[-1]
 
@@ -117,7 +122,7 @@ def test_parameter_blocks_fit(name):
 # ---------------------------------------------------------------------------------------------
 # job -> (conv layers computed by it (second = appended along N), BatchNorm applied in its epilogue)
 FUSED_LAYERS = [((2,), 0), ((3,), 0), ((4,), 2), ((5,), 0), ((6,), 0), ((7,), 3), ((8,), 0), ((9,), 4),
-                ((12, 14), 0), ((11,), 5), ((15,), 0), ((13,), 5), ((10,), 5), ((16,), 5),
+                ((12, 14), 0), ((10,), 5), ((15,), 0), ((11,), 5), ((13,), 5), ((16,), 5),
                 ((17,), 0), ((17,), 0), ((17,), 0), ((17,), 6), ((18,), 0), ((19,), 7), ((20,), 0)]
 
 

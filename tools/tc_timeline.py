@@ -12,8 +12,8 @@ sys.path.insert(0, str(ROOT))
 from deepbinner_b200.model import B200Model, tc_num_jobs  # noqa: E402
 from deepbinner_b200 import _native  # noqa: E402
 
-NAMES = ['conv2', 'conv3', 'conv4', 'conv5', 'conv6', 'conv7', 'conv8', 'conv9', 'c12+14', 'conv11',
-         'conv15', 'conv13', 'conv10f', 'conv16', 'c17a', 'c17b', 'c17c', 'c17d', 'conv18',
+NAMES = ['conv2', 'conv3', 'conv4', 'conv5', 'conv6', 'conv7', 'conv8', 'conv9', 'c12+14', 'conv10f',
+         'conv15', 'conv11', 'conv13', 'conv16', 'c17a', 'c17b', 'c17c', 'c17d', 'conv18',
          'conv19', 'conv20']
 
 
@@ -40,12 +40,11 @@ def main():
             print('{:8s} {}  | {:8d} {:8d} | {:8d} {:8d} | {:6d} {:6d} | {:5d} {:5d} {:5d} {:5d} {:5d} | {:5d} {:5d} {:5d} {:5d} | top {:6d} waited {:6d} need {:6d}'.format(
                 NAMES[j], w, a, b, c, d, b - a, (d - c) if c >= 0 else -1,
                 e4 - c, e5 - e4, e6 - e5, e7 - e6, d - e7, x8 - a, x9 - x8, x10 - x9, b - x10, x11, x12, x13))
-    print('joint-phase weight loads: job | load issued by the loader | issuer reached the job | weights seen (latency if the issuer waited)')
+    print('issuer turn-around (joint jobs): job | weights requested by the loader | top | weights ok | inputs ok | first MMA | last MMA issued | commits done')
     for j in range(8, nj):
-        ld, top, seen = int(trace[j, 1, 15] - t0), int(trace[j, 0, 11] - t0), int(trace[j, 0, 12] - t0)
-        print('  {:8s} | {:7d} | {:7d} | {:7d}  ({}) | repeat poll {} cycles, + test_wait {}'.format(NAMES[j], ld, top, seen,
-              'load -> seen {} cycles'.format(seen - ld) if seen - top > 150 else 'ready',
-              int(trace[j, 1, 14]), int(trace[j, 1, 13])))
+        ld = int(trace[j, 1, 15] - t0)
+        v = [int(trace[j, 0, k] - t0) if trace[j, 0, k] > 0 else -1 for k in (11, 12, 13, 0, 14, 1)]
+        print('  {:8s} | {:7d} | {:7d} | {:7d} | {:7d} | {:7d} | {:7d} | {:7d}'.format(NAMES[j], ld, *v))
     print('total', int(trace[:nj, :, :14].max() - t0))
 
 
