@@ -109,6 +109,8 @@ def load_library():
                                             ctypes.c_void_p]),
         'db_tc_trace': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p,
                                        ctypes.c_void_p]),
+        'db_tc_trace_call': (ctypes.c_int, [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int,
+                                            ctypes.c_void_p, ctypes.c_void_p]),
         'db_last_gpu_ms': (ctypes.c_float, [ctypes.c_void_p]),
         'db_kernel_launches': (ctypes.c_int64, [ctypes.c_void_p]),
     }
@@ -127,7 +129,7 @@ EXPORTED_SYMBOLS = ['db_abi_version', 'db_last_error', 'db_create', 'db_destroy'
                     'db_predict_windows_f64', 'db_predict_windows_device', 'db_call_batch',
                     'db_call_batch_submit', 'db_call_batch_submit_packed', 'db_call_batch_wait',
                     'db_call_batch_device', 'db_last_gpu_ms', 'db_kernel_launches',
-                    'db_tc_num_jobs', 'db_tc_job_table', 'db_tc_packed', 'db_tc_debug_dump', 'db_tc_trace', 'db_zlib_inflate', 'db_fast5_read',
+                    'db_tc_num_jobs', 'db_tc_job_table', 'db_tc_packed', 'db_tc_debug_dump', 'db_tc_trace', 'db_tc_trace_call', 'db_zlib_inflate', 'db_fast5_read',
                     'db_fast5_list_root', 'db_fast5_batch_read', 'db_fast5_batch_read_reads', 'db_fast5_batch_read_sides', 'db_fast5_batch_rows',
                     'db_fast5_batch_get',
                     'db_fast5_batch_free']

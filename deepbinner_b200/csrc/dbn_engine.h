@@ -27,6 +27,8 @@ int tc_job_table(const Blob& blob, int which, int32_t* out, int max_jobs);
 int tc_packed(const Blob& blob, int which, unsigned char* w_out, int64_t w_cap, float* prm_out, int64_t prm_cap,
               int64_t* w_bytes, int64_t* prm_floats);
 int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_trace, cudaStream_t st);
+int tc_trace_call(TcEngine* e, const int16_t* d_samples, const int64_t* d_offsets, int n_reads, float* d_probs,
+                  long long* d_trace, cudaStream_t st);
 // Debug: run windows d_x[0..1] through jobs 0..job and dump both activation regions.
 int tc_debug_dump(TcEngine* e, const float* d_x, int job, unsigned char* d_out, cudaStream_t st);
 

@@ -816,6 +816,22 @@ int db_tc_trace(db_model* m, const float* d_x, int n, float* d_probs, int64_t* t
     return DBN_OK;
 }
 
+int db_tc_trace_call(db_model* m, const int16_t* d_samples, const int64_t* d_offsets, int n_reads, float* d_probs,
+                     int64_t* trace) {
+    if (!m || !m->tc) return fail(DBN_EINVAL, "tcgen05 engine not available");
+    DBN_CUDA(cudaSetDevice(m->device));
+    const size_t bytes = 32 * 2 * 16 * sizeof(long long);
+    int rc = grow(&m->d_step, &m->d_step_bytes, bytes);
+    if (rc) return rc;
+    cudaStream_t st = m->streams[0];
+    DBN_CUDA(cudaMemsetAsync(m->d_step, 0, bytes, st));
+    rc = tc_trace_call(m->tc, d_samples, d_offsets, n_reads, d_probs, reinterpret_cast<long long*>(m->d_step), st);
+    if (rc) return rc;
+    DBN_CUDA(cudaMemcpyAsync(trace, m->d_step, bytes, cudaMemcpyDeviceToHost, st));
+    DBN_CUDA(cudaStreamSynchronize(st));
+    return DBN_OK;
+}
+
 float db_last_gpu_ms(const db_model* m) { return m ? m->last_ms : 0.f; }
 
 int64_t db_kernel_launches(const db_model* m) { return m ? m->launches : 0; }

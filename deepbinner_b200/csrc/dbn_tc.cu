@@ -1532,7 +1532,8 @@ TcEngine* tc_create(const Blob& blob) {
               cudaMemcpy(e->d_issue, recs.data(), recs.size() * sizeof(IssueRec), cudaMemcpyHostToDevice) == cudaSuccess &&
               cudaFuncSetAttribute(k_tc_forward<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
               cudaFuncSetAttribute(k_tc_forward<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
-              cudaFuncSetAttribute(k_tc_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess;
+              cudaFuncSetAttribute(k_tc_forward<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess &&
+              cudaFuncSetAttribute(k_tc_forward<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, kTcSmemBytes) == cudaSuccess;
     if (!ok) {
         cudaGetLastError();
         tc_destroy(e);
@@ -1644,6 +1645,17 @@ int tc_trace(TcEngine* e, const float* d_x, int n, float* d_probs, long long* d_
     k_tc_forward<false, true><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(P, d_x, nullptr, nullptr, nullptr, 0, 0,
                                                                       n, d_probs);
     return launch_check("tcgen05 trace");
+}
+
+// The same for the fused call_batch form of the kernel (int16 scan regions, z-score in the prologue; one window per read).
+int tc_trace_call(TcEngine* e, const int16_t* d_samples, const int64_t* d_offsets, int n_reads, float* d_probs,
+                  long long* d_trace, cudaStream_t st) {
+    if (int rc = sync_table(e->jobs)) return rc;
+    TcParams P = e->params;
+    P.trace = d_trace;
+    k_tc_forward<true, true><<<(n_reads + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(P, nullptr, nullptr, d_samples, d_offsets,
+                                                                           n_reads, 0, n_reads, d_probs);
+    return launch_check("tcgen05 trace (call mode)");
 }
 
 // Debug: run windows d_x[0..1] up to and including job `job`, dump both ACT regions (2*98688 B).

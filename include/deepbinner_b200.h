@@ -218,6 +218,10 @@ DBN_API int db_tc_debug_dump(db_model *model, const float *x, int job, unsigned 
 /* Timeline of CTA 0 for n device-resident windows: trace[job][window][8] SM-clock stamps (MMA issue
  * start/end, epilogue start/end, then epilogue internals); host buffer of 32*2*8 int64. */
 DBN_API int db_tc_trace(db_model *model, const float *d_x, int n, float *d_probs, int64_t *trace);
+/* The same for the fused call_batch form of the kernel: n_reads device-resident int16 scan regions
+ * (offsets[n_reads + 1]), side 'start', one window per read. */
+DBN_API int db_tc_trace_call(db_model *model, const int16_t *d_samples, const int64_t *d_offsets, int n_reads,
+                             float *d_probs, int64_t *trace);
 
 #ifdef __cplusplus
 }

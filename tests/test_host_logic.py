@@ -210,7 +210,7 @@ def test_c_abi_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(lib_path)
     header = (ROOT / 'include' / 'deepbinner_b200.h').read_text()
     declared = re.findall(r'DBN_API\s+[\w\s\*]+?\b(db_\w+)\s*\(', header)
-    assert sorted(declared) == sorted(_native.EXPORTED_SYMBOLS) and len(declared) == 31
+    assert sorted(declared) == sorted(_native.EXPORTED_SYMBOLS) and len(declared) == 32
     for sym in declared:
         assert hasattr(lib, sym), sym
     lib.db_abi_version.restype = ctypes.c_int

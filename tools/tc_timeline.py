@@ -19,18 +19,26 @@ NAMES = ['conv2', 'conv3', 'conv4', 'conv5', 'conv6', 'conv7', 'conv8', 'conv9',
 
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 296
+    call_mode = len(sys.argv) > 2 and sys.argv[2] == 'call'   # fused call_batch form: int16 scan regions, z-score in the prologue
     m = B200Model(str(ROOT / 'deepbinner_b200/models/EXP-NBD103_read_starts.dbnw'))
     m.set_engine('tcgen05')
     x = torch.randn(n, 1024, device='cuda')
     p = torch.zeros(n, 13, device='cuda')
     trace = np.zeros((32, 2, 16), dtype=np.int64)
+    samples = (torch.randn(n * 1024, device='cuda') * 80 + 500).to(torch.int16)
+    offsets = torch.arange(n + 1, device='cuda', dtype=torch.int64) * 1024
     for _ in range(3):
-        rc = m._lib.db_tc_trace(m._handle, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(p.data_ptr()),
-                                _native.as_ptr(trace))
+        if call_mode:
+            rc = m._lib.db_tc_trace_call(m._handle, ctypes.c_void_p(samples.data_ptr()), ctypes.c_void_p(offsets.data_ptr()),
+                                         n, ctypes.c_void_p(p.data_ptr()), _native.as_ptr(trace))
+        else:
+            rc = m._lib.db_tc_trace(m._handle, ctypes.c_void_p(x.data_ptr()), n, ctypes.c_void_p(p.data_ptr()),
+                                    _native.as_ptr(trace))
         _native.check(rc, 'db_tc_trace')
     nj = tc_num_jobs(m)
     misc = trace[31].reshape(-1)
     t0 = misc[0] if misc[0] > 0 else trace[:nj][trace[:nj] > 0].min()
+    print('call mode (int16 scan regions, z-score in the prologue)' if call_mode else 'predict mode (fp32 windows)')
     print('kernel start 0 | conv1 w0 done {} | conv1 w1 done {}'.format(int(misc[1] - t0), int(misc[2] - t0)))
     print('job      win | mma_issue_start issue_end | epi_start epi_end | issue_dur epi_dur | epi: params tmem compute fence | mma: wfull0 part0 wfull1 part1')
     for j in range(nj):
