@@ -220,8 +220,17 @@ __device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
 }
 // Bounded wait: a protocol bug must become a trap (reported as a CUDA error), never a hang.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+#ifdef DBN_TC_DEBUG_WAIT   // debugging aid (-DDBN_TC_DEBUG_WAIT): report a wait that does not end and carry on (results are then wrong)
+    for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
+        if (spin > (1u << 12)) {
+            printf("mbarrier wait timed out: block %d thread %d barrier offset %d parity %u clock %lld\n", blockIdx.x, threadIdx.x,
+                   static_cast<int>(bar & 0x3FFFF) - 1024 - kSmemBar, parity, clock64());
+            return;
+        }
+#else
     for (uint32_t spin = 0; !mbar_try_wait(bar, parity); ++spin)
         if (spin > (1u << 26)) __trap();
+#endif
 }
 // Non-blocking probe of a phase.  The MMA issuer uses it to look at the barrier of its NEXT wait
 // early: a poll queues behind the epilogue warps' shared-memory traffic (hundreds of cycles when
@@ -953,6 +962,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         }
     }
 
+    // barrier set-up, shared by two otherwise idle threads (one thread needs ~10 cycles per mbarrier.init, and
+    // there is one barrier per joint job / joint epilogue)
     if (threadIdx.x == kLoadWarp * 32) {
         mbar_init(bar_wfull[0], 1);
         mbar_init(bar_wfull[1], 1);
@@ -967,6 +978,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_init(bar_jwfull0 + 8 * i, 1);
             mbar_init(bar_jwfree0 + 8 * i, 1);
         }
+        fence_barrier_init();
+    } else if (threadIdx.x == kMmaWarpB * 32) {
         mbar_init(bar_x, 2 * kEpiArrivals);
         for (int i = 0; i < kJointRing; ++i) {
             mbar_init(bar_jmma + 8 * i, 1);
