@@ -245,6 +245,13 @@ struct db_model {
     static constexpr int kJobStreams = 3;
     cudaStream_t job_streams[kJobStreams] = {nullptr, nullptr, nullptr};   // chunks of call_batch jobs rotate over these
     unsigned job_chunk_counter = 0;
+    // Host -> device copies of the chunks go through their own stream and the chunk's compute stream waits for
+    // the chunk's copy event: in stream order behind the previous chunk of the same compute stream, the three
+    // streams fell into lockstep - all kernels end together and nobody's next input is on the device yet
+    // (a ~100 us hole in front of every third kernel, profiles/r02_e2e_pipeline.txt).
+    cudaStream_t copy_stream = nullptr;
+    static constexpr int kCopyEvents = 16;
+    cudaEvent_t ev_copy[kCopyEvents] = {};
     int call_chunk_windows = 2048;      // network windows per pipelined chunk of a job (DEEPBINNER_B200_CALL_CHUNK)
     GatherPool* pool = nullptr;         // host threads of the gather (DEEPBINNER_B200_GATHER_THREADS, default 4)
 };
@@ -438,8 +445,11 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
         else if (total >= (1 << 19)) m->pool->parallel(copy_reads);
         else copy_reads(0);
         if (total > 0)
-            DBN_CUDA(cudaMemcpyAsync(J.d_samples + base, h_src, sizeof(int16_t) * total, cudaMemcpyHostToDevice, st));
-        DBN_CUDA(cudaMemcpyAsync(J.d_offsets + r0 + c, offs, sizeof(int64_t) * (cnt + 1), cudaMemcpyHostToDevice, st));
+            DBN_CUDA(cudaMemcpyAsync(J.d_samples + base, h_src, sizeof(int16_t) * total, cudaMemcpyHostToDevice, m->copy_stream));
+        DBN_CUDA(cudaMemcpyAsync(J.d_offsets + r0 + c, offs, sizeof(int64_t) * (cnt + 1), cudaMemcpyHostToDevice, m->copy_stream));
+        cudaEvent_t copied = m->ev_copy[m->job_chunk_counter % db_model::kCopyEvents];   // (a wait refers to the record it follows)
+        DBN_CUDA(cudaEventRecord(copied, m->copy_stream));
+        DBN_CUDA(cudaStreamWaitEvent(st, copied, 0));
         rc = launch_call_batch(m, J.d_samples + base, J.d_offsets + r0 + c, cnt, side, steps, score_diff,
                                J.d_step + static_cast<size_t>(r0) * steps * nc, J.d_probs + r0 * nc, J.d_calls + r0, st);
         if (rc) return rc;
@@ -494,6 +504,9 @@ void db_destroy(db_model* m) {
         for (cudaEvent_t e : j.ev_done)
             if (e) cudaEventDestroy(e);
     }
+    if (m->copy_stream) cudaStreamDestroy(m->copy_stream);
+    for (cudaEvent_t e : m->ev_copy)
+        if (e) cudaEventDestroy(e);
     for (cudaStream_t st : m->job_streams)
         if (st) cudaStreamDestroy(st);
     for (int i = 0; i < 2; ++i) {
@@ -558,6 +571,8 @@ int db_create(const void* weights_blob, size_t blob_bytes, int device, db_model*
             for (cudaEvent_t& e : j.ev_done) DBN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         }
         for (cudaStream_t& st : m->job_streams) DBN_CUDA(cudaStreamCreateWithFlags(&st, cudaStreamNonBlocking));
+        DBN_CUDA(cudaStreamCreateWithFlags(&m->copy_stream, cudaStreamNonBlocking));
+        for (cudaEvent_t& e : m->ev_copy) DBN_CUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
         if (const char* v = getenv("DEEPBINNER_B200_CALL_CHUNK")) m->call_chunk_windows = std::max(1, atoi(v));
         int gather_threads = 4;
         if (const char* v = getenv("DEEPBINNER_B200_GATHER_THREADS")) gather_threads = std::max(1, std::min(64, atoi(v)));
