@@ -543,7 +543,7 @@ def main():
         avg_launch_ms = ms / max(launches, 1)      # one network pass over a batch = one kernel
         achieved = FLOP_PER_WINDOW * BATCH / (avg_launch_ms * 1e-3) / 1e12
         traffic = None
-        tfile = ROOT / 'profiles' / 'traffic_r01.json'
+        tfile = ROOT / 'profiles' / 'traffic_r02.json'
         if tfile.exists():
             traffic = json.loads(tfile.read_text()).get(model.engine)
         terms = 1 if model.engine == 'fp32' else 3

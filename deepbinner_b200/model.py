@@ -156,6 +156,15 @@ class B200Model:
         return int(self._lib.db_kernel_launches(self._handle))
 
 
+def _data_pointer(a):
+    """Address of an array's first element.  ctypes' from_buffer / addressof is ~2.5x cheaper than
+    ndarray.ctypes.data (0.8 vs 2 us per read: this is the per-read host cost of the list-of-arrays API),
+    but needs a writable, non-empty buffer."""
+    if a.size and a.flags.writeable:
+        return ctypes.addressof(ctypes.c_char.from_buffer(a))
+    return a.ctypes.data
+
+
 class ReadPointers:
     """A list of 1-D integer signals as what db_call_batch_submit takes: an array of int16 pointers and
     an array of lengths (built once per batch, shared by the start and the end model's jobs).  Keeps the
@@ -165,7 +174,7 @@ class ReadPointers:
         self.arrays = [s if (type(s) is np.ndarray and s.dtype == np.int16 and s.flags.c_contiguous)
                        else np.ascontiguousarray(s, dtype=np.int16) for s in signals]
         self.n = len(self.arrays)
-        self.ptrs = np.fromiter((a.ctypes.data for a in self.arrays), dtype=np.uint64, count=self.n)
+        self.ptrs = np.fromiter(map(_data_pointer, self.arrays), dtype=np.uint64, count=self.n)
         self.lens = np.fromiter((a.size for a in self.arrays), dtype=np.int64, count=self.n)
 
     def __len__(self):
