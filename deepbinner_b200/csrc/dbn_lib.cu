@@ -415,13 +415,20 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
         int64_t* offs = J.h_offsets + r0 + c;   // cnt + 1 entries, relative to this chunk's samples
         int64_t total = 0;
         bool whole = pinned_base != nullptr;    // every read of the chunk is used whole
+        bool uniform = pinned_base != nullptr;  // ... or the reads are consecutive and equally long (rows of a packed reader batch)
         const int16_t* first = nullptr;
+        int64_t len0 = 0, consumed = 0;
         for (int i = 0; i < cnt; ++i) {
             const int16_t* p;
             int64_t len;
             get_read(r0 + i, &p, &len);
-            if (i == 0) first = p;
+            if (i == 0) {
+                first = p;
+                len0 = len;
+            }
             whole = whole && len <= region_max && p == first + total;
+            uniform = uniform && len == len0 && p == first + consumed;
+            consumed += len;
             offs[i] = total;
             total += std::min(len, region_max);
         }
@@ -441,11 +448,23 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
                     std::memcpy(J.h_samples + base + offs[i], p + (side == DBN_SIDE_START ? 0 : len - r), sizeof(int16_t) * r);
             }
         };
-        if (whole && total > 0) h_src = first;       // zero-copy: DMA straight from the caller's pinned buffer
-        else if (total >= (1 << 19)) m->pool->parallel(copy_reads);
-        else copy_reads(0);
-        if (total > 0)
-            DBN_CUDA(cudaMemcpyAsync(J.d_samples + base, h_src, sizeof(int16_t) * total, cudaMemcpyHostToDevice, m->copy_stream));
+        if (whole && total > 0) {
+            // zero-copy: DMA straight from the caller's pinned buffer
+            DBN_CUDA(cudaMemcpyAsync(J.d_samples + base, first, sizeof(int16_t) * total, cudaMemcpyHostToDevice, m->copy_stream));
+        } else if (uniform && total > 0 && len0 > region_max) {
+            // zero-copy, strided: equally long rows (e.g. [first keep | last keep] samples of every read, as the
+            // native fast5 reader packs both ends) - one 2-D DMA takes this side's region out of every row, no
+            // staging pass through host memory (which is what bounded 8 ranks on one host)
+            const int16_t* src = first + (side == DBN_SIDE_START ? 0 : len0 - region_max);
+            DBN_CUDA(cudaMemcpy2DAsync(J.d_samples + base, sizeof(int16_t) * region_max, src, sizeof(int16_t) * len0,
+                                       sizeof(int16_t) * region_max, static_cast<size_t>(cnt), cudaMemcpyHostToDevice,
+                                       m->copy_stream));
+        } else {
+            if (total >= (1 << 19)) m->pool->parallel(copy_reads);
+            else copy_reads(0);
+            if (total > 0)
+                DBN_CUDA(cudaMemcpyAsync(J.d_samples + base, h_src, sizeof(int16_t) * total, cudaMemcpyHostToDevice, m->copy_stream));
+        }
         DBN_CUDA(cudaMemcpyAsync(J.d_offsets + r0 + c, offs, sizeof(int64_t) * (cnt + 1), cudaMemcpyHostToDevice, m->copy_stream));
         cudaEvent_t copied = m->ev_copy[m->job_chunk_counter % db_model::kCopyEvents];   // (a wait refers to the record it follows)
         DBN_CUDA(cudaEventRecord(copied, m->copy_stream));

@@ -334,6 +334,30 @@ def test_packed_signals_take_the_same_fused_path(models, fast5_dir, fixture_read
         assert np.array_equal(np.array(a[1]), np.array(b[1]))
 
 
+def test_equally_long_packed_rows_in_pinned_memory_are_copied_strided(models, fixture_reads, multi_reads):
+    """Rows of equal length longer than the scan region, consecutive in ONE page-locked buffer (what a reader
+    that keeps [first keep | last keep] samples of every read hands over): db_call_batch_submit_packed takes each
+    side's region out of every row with one strided DMA (no staging gather) - results identical to the list path,
+    for both sides, also with pageable memory (staging path) and over several chunks."""
+    import torch
+    import types
+    from deepbinner_b200 import classify as cls
+    _, sigs, _ = fixture_reads
+    _, msigs = multi_reads
+    long_reads = [s for s in list(sigs) + list(msigs) if len(s) >= 13312]
+    rows = np.stack([np.concatenate([s[:6656], s[-6656:]]) for s in long_reads] * 100).astype(np.int16)   # > one chunk
+    ids = ['r%d' % i for i in range(len(rows))]
+    pinned = torch.from_numpy(rows.copy()).pin_memory().numpy()
+    for buf in (pinned, rows):
+        packed = types.SimpleNamespace(samples=buf.reshape(-1), offsets=np.arange(len(rows) + 1, dtype=np.int64) * rows.shape[1],
+                                       rows=np.arange(len(rows), dtype=np.int64))
+        for side, name in (('start', 'EXP-NBD103_read_starts'), ('end', 'EXP-NBD103_read_ends')):
+            a = cls.call_batch(1024, 13, ids, packed, models[name], make_args(), side)
+            b = cls.call_batch(1024, 13, ids, [r for r in rows], models[name], make_args(), side)
+            assert a[0] == b[0] and len(a[0]) == len(rows)
+            assert np.array_equal(np.array(a[1]), np.array(b[1]))
+
+
 def test_realtime_on_real_fast5_files(fast5_dir, tmp_path, capsys):
     """`deepbinner realtime --stop`: files are classified on the GPU and moved into barcodeNN/."""
     import shutil
