@@ -55,8 +55,24 @@ def build_library(force=False, verbose=False, defines=(), out=None):
     return str(out)
 
 
+def build_fastptr(force=False):
+    """The optional CPython helper csrc/dbn_fastptr.c -> deepbinner_b200/_fastptr.<abi>.so (gcc; host only)."""
+    import sysconfig
+    out = PKG / ('_fastptr' + sysconfig.get_config_var('EXT_SUFFIX'))
+    src = CSRC / 'dbn_fastptr.c'
+    if not force and out.exists() and out.stat().st_mtime >= src.stat().st_mtime:
+        return str(out)
+    cmd = ['gcc', '-O2', '-shared', '-fPIC', '-I' + sysconfig.get_paths()['include'], str(src), '-o', str(out)]
+    proc = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.STDOUT, text=True)
+    if proc.returncode != 0:
+        raise RuntimeError('gcc failed:\n' + ' '.join(cmd) + '\n' + proc.stdout)
+    return str(out)
+
+
 if __name__ == '__main__':
     defs = [a[2:] for a in sys.argv[1:] if a.startswith('-D')]
     outs = [a[6:] for a in sys.argv[1:] if a.startswith('--out=')]
     print(build_library(force='--force' in sys.argv or bool(defs), verbose='-v' in sys.argv, defines=defs,
                         out=outs[0] if outs else None))
+    if not outs:
+        print(build_fastptr(force='--force' in sys.argv))

@@ -156,6 +156,12 @@ class B200Model:
         return int(self._lib.db_kernel_launches(self._handle))
 
 
+try:
+    from . import _fastptr          # optional CPython helper (csrc/dbn_fastptr.c, built by build.py)
+except ImportError:                 # pure-Python pointer extraction below
+    _fastptr = None
+
+
 def _data_pointer(a):
     """Address of an array's first element.  ctypes' from_buffer / addressof is ~2.5x cheaper than
     ndarray.ctypes.data (0.8 vs 2 us per read: this is the per-read host cost of the list-of-arrays API),
@@ -171,6 +177,15 @@ class ReadPointers:
     arrays alive."""
 
     def __init__(self, signals):
+        if _fastptr is not None:
+            # C helper (buffer protocol): handles the leading run of C-contiguous int16 arrays - normally all
+            arrays = signals if type(signals) is list else list(signals)
+            n = len(arrays)
+            ptrs, lens = np.empty(n, dtype=np.uint64), np.empty(n, dtype=np.int64)
+            done = _fastptr.fill(arrays, ptrs.ctypes.data, lens.ctypes.data) if n else 0
+            if done == n:
+                self.arrays, self.n, self.ptrs, self.lens = arrays, n, ptrs, lens
+                return
         self.arrays = [s if (type(s) is np.ndarray and s.dtype == np.int16 and s.flags.c_contiguous)
                        else np.ascontiguousarray(s, dtype=np.int16) for s in signals]
         self.n = len(self.arrays)

@@ -243,3 +243,30 @@ def test_crafted_weight_blobs_are_rejected_not_read_out_of_bounds():
         entry.pack_into(blob, 24, *bad)
         rc = lib.db_tc_job_table(bytes(blob), len(blob), 0, _native.as_ptr(out), 32)
         assert rc == -2, (bad[1:], rc, lib.db_last_error())
+
+
+def test_read_pointers_with_and_without_the_c_helper(monkeypatch):
+    """model.ReadPointers (pointer / length arrays of the list-of-arrays call_batch API): the CPython helper
+    (csrc/dbn_fastptr.c, buffer protocol) and the pure-Python fallback give the same arrays; anything that is not
+    a C-contiguous int16 array is converted."""
+    from deepbinner_b200 import build, model
+    build.build_fastptr()
+    import importlib
+    fast = importlib.import_module('deepbinner_b200._fastptr')
+    ro = np.arange(7, dtype=np.int16)
+    ro.flags.writeable = False
+    signals = [np.arange(100, dtype=np.int16), ro, np.zeros(0, np.int16), np.arange(6, dtype=np.int32), [3, 2, 1],
+               np.arange(20, dtype=np.int16)[::2]]
+    outs = []
+    for helper in (fast, None):
+        monkeypatch.setattr(model, '_fastptr', helper)
+        r = model.ReadPointers(signals)
+        assert r.n == len(signals) and r.lens.tolist() == [100, 7, 0, 6, 3, 10]
+        assert all(a.dtype == np.int16 and a.flags.c_contiguous for a in r.arrays)
+        assert all(int(p) == a.ctypes.data for p, a in zip(r.ptrs, r.arrays) if a.size)
+        outs.append([a.tolist() for a in r.arrays])
+        # the fast path keeps the caller's arrays (no copies) when every item qualifies
+        plain = [np.arange(5, dtype=np.int16), np.arange(9, dtype=np.int16)]
+        r2 = model.ReadPointers(plain)
+        assert all(x is y for x, y in zip(r2.arrays, plain)) and r2.lens.tolist() == [5, 9]
+    assert outs[0] == outs[1]
