@@ -565,3 +565,27 @@ def test_multi_read_fast5_classifies_like_its_reads(models, oracle_weights, fast
     oc_e, _ = orc.call_batch(oracle_weights['EXP-NBD103_read_ends'], reads, 'end', 6144, 0.5)
     assert list(got.values()) == [orc.combine_calls(a, b, require_either=True) for a, b in zip(oc_s, oc_e)]
     capsys.readouterr()
+
+
+def test_two_devices_in_one_process(fixture_reads):
+    """Handles on two devices in ONE process (db_create takes a device ordinal): the job table lives in
+    per-device constant memory, so each device needs its own upload (the cache of what was uploaded is keyed by
+    device).  Needs two visible GPUs; `gpurun --gpus 2 -- python -m pytest tests -m gpu -k two_devices`."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip('needs two visible GPUs')
+    from deepbinner_b200.model import B200Model
+    _, sigs, _ = fixture_reads
+    x = orc.make_windows(sigs, 1024, 0, 'start').astype(np.float32)
+    name = 'EXP-NBD103_read_starts'
+    a, b = B200Model(model_path(name), device=0), B200Model(model_path(name), device=1)
+    pa, pb = a.predict(x[:, :, None]), b.predict(x[:, :, None])
+    ca, cb = a.call_batch(sigs, 'start', 6144, 0.5), b.call_batch(sigs, 'start', 6144, 0.5)
+    assert np.array_equal(pa, pb) and np.array_equal(ca[0], cb[0]) and np.array_equal(ca[1], cb[1])
+    ref = orc.forward(orc.load_weights(model_path(name)), x)
+    assert np.abs(pb - ref).max() <= TOL
+    for eng in ('fp32', 'tcgen05'):      # and again after switching engines on the second device only
+        b.set_engine(eng)
+        assert np.abs(b.predict(x[:, :, None]) - ref).max() <= TOL
+    a.close()
+    b.close()
