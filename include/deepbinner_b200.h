@@ -115,16 +115,18 @@ DBN_API int db_call_batch(db_model *model, const int16_t *samples, const int64_t
 /*
  * The same call split in two, so that the host can overlap its own work with the GPU's (prepare the
  * next batch, submit the other model's side of this batch, format results): submit() gathers the scan
- * regions chunk by chunk into pinned staging and enqueues copy -> kernels -> copy-back for every chunk
- * on three rotating streams; it returns as soon as everything is enqueued and no longer references the
- * caller's buffers.  wait() blocks until the job is complete and fills probs / calls as db_call_batch
+ * regions chunk by chunk into pinned staging and enqueues copy (on a dedicated copy stream) -> kernels ->
+ * copy-back for every chunk (on three rotating compute streams that wait for the chunk's copy event); it
+ * returns as soon as everything is enqueued and no longer references the caller's buffers.  wait() blocks until the job is complete and fills probs / calls as db_call_batch
  * does.  *job receives a small index; up to 4 jobs per handle may be in flight; every submitted job must
  * be waited for exactly once.  db_call_batch == submit_packed + wait.
  *   db_call_batch_submit:        read i = signals[i][0 .. lengths[i])   (ragged host arrays)
  *   db_call_batch_submit_packed: read i = samples[offsets[i] .. offsets[i+1])
  * Exception to "no longer references the caller's buffers": if `samples` of the packed variant is
- * page-locked memory (cudaHostAlloc / cudaHostRegister), reads that fit the scan region whole are copied
- * to the device straight from it (no staging pass) - such a buffer must stay unchanged until wait().
+ * page-locked memory (cudaHostAlloc / cudaHostRegister), chunks whose reads all fit the scan region whole,
+ * and chunks of equally long reads (rows that hold the first and the last `keep` samples of every read,
+ * as the fast5 batch reader packs them: one strided 2-D copy takes this side's region out of every row),
+ * are copied to the device straight from it (no staging pass) - such a buffer must stay unchanged until wait().
  */
 DBN_API int db_call_batch_submit(db_model *model, const int16_t *const *signals, const int64_t *lengths,
                                  int n_reads, int side, int scan_size, double score_diff, int *job);
