@@ -885,7 +885,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                  int side, int n_windows, float* __restrict__ probs) {
     extern __shared__ __align__(1024) unsigned char smem[];
     const uint32_t sbase = smem_u32(smem);
-    long long* const trace = kDiag ? P.trace : nullptr;
+    long long* const trace0 = kDiag ? P.trace : nullptr;
     const int dbg_job = kDiag ? P.dbg_job : -1;
     const uint32_t wbuf = sbase + kSmemWbuf;
     const uint32_t prm = sbase + kSmemPrm;
@@ -911,57 +911,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     // convergent regions and the MMA issuer's address arithmetic can use the uniform datapath
     const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0);
 
-    // Epilogue threads issue every global load of the prologue BEFORE the set-up barrier (conv1
-    // parameters, in predict mode the samples of BOTH windows): their latency overlaps the barrier
-    // initialisation and the TMEM allocation, which the otherwise idle loader warp / MMA warp do.
     const bool is_epi = warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps;
-    int win[2];
-    bool valid[2];
-#pragma unroll
-    for (int w = 0; w < 2; ++w) {
-        const int idx = 2 * blockIdx.x + w;
-        valid[w] = idx < n_windows;
-        win[w] = valid[w] ? idx : n_windows - 1;
-    }
-    Conv1Params c1;
-    WindowInput in[2] = {};
-    float xv[2][3];
-    int raw[2][3];            // call mode: the thread's raw samples of both windows (0 outside the slice)
-    WindowGeom geom[2] = {};
-    if (is_epi) {
-        const int etid = static_cast<int>(threadIdx.x) - kEpiWarp0 * 32;
-        load_conv1_params(P, etid, c1);
-        if (!kCallMode) {
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                if (x) in[w].x = x + static_cast<size_t>(win[w]) * kInputSize;
-                else in[w].xd = xd + static_cast<size_t>(win[w]) * kInputSize;
-                fetch_window_inputs(in[w], etid, xv[w]);
-            }
-        } else {
-            // fused call_batch (classify.py:342-357): the thread's samples of BOTH windows are requested
-            // here, so that the two dependent global latencies (offsets, samples) overlap the set-up
-            int64_t off[2], len[2];
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                const int read = win[w] % n_reads;
-                off[w] = __ldg(offsets + read);
-                len[w] = __ldg(offsets + read + 1) - off[w];
-            }
-#pragma unroll
-            for (int w = 0; w < 2; ++w) {
-                geom[w] = window_geometry(static_cast<int>(len[w]), win[w] / n_reads, side);
-                const int16_t* region = samples + off[w] + geom[w].a;
-#pragma unroll
-                for (int k = 0; k < 3; ++k) {
-                    const int i = etid + k * kEpiThreads - geom[w].dst;   // index into the slice
-                    raw[w][k] = (etid + k * kEpiThreads < kInputSize && i >= 0 && i < geom[w].n)
-                                    ? static_cast<int>(__ldg(region + i)) : 0;
-                }
-            }
-        }
-    }
-
+    // PERSISTENT over the window pairs of the launch (grid = min(pairs, SMs)); every role loops over the pairs on
+    // its own, there is no CTA-wide barrier between two pairs: the barriers are not re-initialised, a barrier that
+    // completes once per pair is waited for with parity `it & 1`, bar_epi[w] completes nine times per pair (its
+    // parity for job j is (j + it) & 1), the weight / MMA barriers of the single-window jobs eight times (their
+    // parities restart with every pair).
+    const int npairs = (n_windows + 1) / 2;
     // barrier set-up, shared by two otherwise idle threads (one thread needs ~10 cycles per mbarrier.init, and
     // there is one barrier per joint job / joint epilogue)
     if (threadIdx.x == kLoadWarp * 32) {
@@ -999,9 +955,63 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         // ================= epilogue / CUDA-core warps =================
         const int tid = static_cast<int>(threadIdx.x) - kEpiWarp0 * 32;   // epilogue-relative thread id
         const int ewarp = tid >> 5;
+        for (int pair = blockIdx.x, it = 0; pair < npairs; pair += gridDim.x, ++it) {
+        const uint32_t ph = static_cast<uint32_t>(it) & 1u;
+        long long* const trace = it == 0 ? trace0 : nullptr;   // the timeline is that of the CTA's first pair
+            // Epilogue threads issue every global load of the prologue BEFORE the set-up barrier (conv1
+            // parameters, in predict mode the samples of BOTH windows): their latency overlaps the barrier
+            // initialisation and the TMEM allocation, which the otherwise idle loader warp / MMA warp do.
+            int win[2];
+            bool valid[2];
+        #pragma unroll
+            for (int w = 0; w < 2; ++w) {
+                const int idx = 2 * pair + w;
+                valid[w] = idx < n_windows;
+                win[w] = valid[w] ? idx : n_windows - 1;
+            }
+            Conv1Params c1;
+            WindowInput in[2] = {};
+            float xv[2][3];
+            int raw[2][3];            // call mode: the thread's raw samples of both windows (0 outside the slice)
+            WindowGeom geom[2] = {};
+            {
+                const int etid = tid;
+                load_conv1_params(P, etid, c1);
+                if (!kCallMode) {
+        #pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        if (x) in[w].x = x + static_cast<size_t>(win[w]) * kInputSize;
+                        else in[w].xd = xd + static_cast<size_t>(win[w]) * kInputSize;
+                        fetch_window_inputs(in[w], etid, xv[w]);
+                    }
+                } else {
+                    // fused call_batch (classify.py:342-357): the thread's samples of BOTH windows are requested
+                    // here, so that the two dependent global latencies (offsets, samples) overlap the set-up
+                    int64_t off[2], len[2];
+        #pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        const int read = win[w] % n_reads;
+                        off[w] = __ldg(offsets + read);
+                        len[w] = __ldg(offsets + read + 1) - off[w];
+                    }
+        #pragma unroll
+                    for (int w = 0; w < 2; ++w) {
+                        geom[w] = window_geometry(static_cast<int>(len[w]), win[w] / n_reads, side);
+                        const int16_t* region = samples + off[w] + geom[w].a;
+        #pragma unroll
+                        for (int k = 0; k < 3; ++k) {
+                            const int i = etid + k * kEpiThreads - geom[w].dst;   // index into the slice
+                            raw[w][k] = (etid + k * kEpiThreads < kInputSize && i >= 0 && i < geom[w].n)
+                                            ? static_cast<int>(__ldg(region + i)) : 0;
+                        }
+                    }
+                }
+            }
+
         if (trace && blockIdx.x == 0 && tid == 0) trace[31 * 32 + 0] = clock64();
-        for (int i = tid; i < P.prm_floats / 4; i += kEpiThreads)
-            reinterpret_cast<float4*>(smem + kSmemPrm)[i] = __ldg(reinterpret_cast<const float4*>(P.prm) + i);
+        if (it == 0)
+            for (int i = tid; i < P.prm_floats / 4; i += kEpiThreads)
+                reinterpret_cast<float4*>(smem + kSmemPrm)[i] = __ldg(reinterpret_cast<const float4*>(P.prm) + i);
         if (kCallMode) {
             // z-score of both windows (trim_signal.py:61-69): exact integer sums over the slices, reduced
             // over the 384 threads (samples outside a slice are 0 and do not count), mean / population
@@ -1063,7 +1073,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const int e = J.eseq;
                 long long* tr = (trace && blockIdx.x == 0 && tid == 0) ? trace + (j * 2) * 16 : nullptr;
                 run_epilogue(P, J, sbase + kSmemAct0, sbase + kSmemAct0, 0, prm, tmem_base + J.tcol, tid,
-                             bar_jmma + 8 * e, 0, p0, p1, tr);
+                             bar_jmma + 8 * e, ph, p0, p1, tr);
                 if (tr) tr[6] = clock64();
                 fence_proxy_async();
                 if (tr) tr[7] = clock64();
@@ -1094,6 +1104,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 for (int i = tid; i < 2 * kActBytes / 16; i += kEpiThreads)
                     reinterpret_cast<uint4*>(P.dbg_out)[i] = reinterpret_cast<const uint4*>(smem)[i];
         }
+        }   // pairs
     } else if (warp == kMmaWarp || warp == kMmaWarpB) {
         // ================= the two MMA issuers (one elected lane of each warp) =================
         // A single issuing thread is the bottleneck of everything behind conv1d_4: between two jobs it needs
@@ -1114,10 +1125,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
         const int me = warp == kMmaWarp ? 0 : 1;
         if (elect_one()) {
             constexpr uint32_t leader = 1;   // (a converged-warp variant with predicated tcgen05 ops was slower: R2UR.BROADCAST per operand)
-            const bool tracing = trace && blockIdx.x == 0;
             const uint32_t wp16[2] = {wbuf >> 4, (wbuf + kWPart0) >> 4};
             const uint32_t act16_0 = (sbase + kSmemAct0) >> 4, act16_1 = (sbase + kSmemAct1) >> 4;
             // The next job's record is fetched (raw, see IssueRec) while this job's MMAs are issued.
+            for (int pair = blockIdx.x, it = 0; pair < npairs; pair += gridDim.x, ++it) {
+            const uint32_t ph = static_cast<uint32_t>(it) & 1u;
+            long long* const trace = it == 0 ? trace0 : nullptr;
+            const bool tracing = trace && blockIdx.x == 0;
             bool in_joint = false;
             IssueRaw nxt = load_issue_raw(P.issue);
             for (int j = 0; j < njobs; ++j) {
@@ -1126,7 +1140,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t blk16 = J.blk16;                  // one K=16 block of B, in 16-byte units
                 const uint32_t tap16[3] = {J.tap16[0], J.tap16[1], J.tap16[2]};
                 const bool first = J.first != 0, last = J.last != 0;
-                const uint32_t par = static_cast<uint32_t>(j) & 1u;   // parity of the single-window barriers for job j
+                const uint32_t parw = static_cast<uint32_t>(j) & 1u;           // parity of the weight barriers for job j
+                const uint32_t par = static_cast<uint32_t>(j + it) & 1u;      // parity of bar_epi[w] for job j of this pair
                 if (J.joint) {
                     if (J.owner != me) continue;
                     // ---- both windows in one burst: [part 0: w0, w1] [part 1: w0, w1], one commit ----
@@ -1136,12 +1151,12 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     const uint32_t jw0_16 = (slot == 0 ? wbuf : slot == 1 ? jwslot1 : jwslot2) >> 4;
                     const uint32_t jw1_16 = jw0_16 + J.part1_16;   // behind part 0
                     if (tracing) trace[(j * 2) * 16 + 11] = clock64();
-                    mbar_wait(bar_jwfull0 + 8 * jk, 0);
+                    mbar_wait(bar_jwfull0 + 8 * jk, ph);
                     if (tracing) trace[(j * 2) * 16 + 12] = clock64();
-                    if (!in_joint) mbar_wait(bar_x, 0);   // this issuer's first joint job: both windows' epilogues of the last
+                    if (!in_joint) mbar_wait(bar_x, ph);   // this issuer's first joint job: both windows' epilogues of the last
                     in_joint = true;                      // single-window job (X of both windows written, accumulators drained)
                     // epilogues complete in order and `need` never decreases: the last needed one is enough
-                    if (J.need > 0) mbar_wait(bar_jepi + 8 * (J.need - 1), 0);
+                    if (J.need > 0) mbar_wait(bar_jepi + 8 * (J.need - 1), ph);
                     if (tracing) trace[(j * 2) * 16 + 13] = clock64();
                     tc_fence_after();
                     if (tracing) trace[(j * 2) * 16 + 0] = clock64();
@@ -1168,8 +1183,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     // issuer 1 only follows the barriers it will wait on later: a parity wait is only safe for a
                     // waiter that has observed every earlier phase
                     mbar_wait(bar_epi[1], par);
-                    mbar_wait(bar_wfull[0], par);
-                    mbar_wait(bar_wfull[1], par);
+                    mbar_wait(bar_wfull[0], parw);
+                    mbar_wait(bar_wfull[1], parw);
                     continue;
                 }
                 const int w_first = J.both ? 0 : me, w_last = J.both ? 1 : me;
@@ -1184,7 +1199,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     if (tracing) trace[(j * 2 + w) * 16 + 0] = clock64();
                     const uint32_t dwin = w * kTmemWindowCols;
                     // ---- weight part 0 (first K blocks); freed early so the loader can refill it ----
-                    if (w == w_first) mbar_wait(bar_wfull[0], par);
+                    if (w == w_first) mbar_wait(bar_wfull[0], parw);
                     if (tracing) trace[(j * 2 + w) * 16 + 8] = clock64();
                     issue_job_part<0>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[0],
                                       blk16, J.n, J.idesc, first, leader);
@@ -1192,7 +1207,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         for (int c = 0; c < nfree; ++c) tc_commit(bar_wfree[0], leader);
                     if (tracing) trace[(j * 2 + w) * 16 + 9] = clock64();
                     // ---- weight part 1 (remaining K blocks) ----
-                    if (w == w_first) mbar_wait(bar_wfull[1], par);
+                    if (w == w_first) mbar_wait(bar_wfull[1], parw);
                     if (tracing) trace[(j * 2 + w) * 16 + 10] = clock64();
                     issue_job_part<1>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[1],
                                       blk16, J.n, J.idesc, false, leader);
@@ -1203,11 +1218,15 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     if (tracing) trace[(j * 2 + w) * 16 + 1] = clock64();
                 }
             }
+            }   // pairs
             tc_commit(bar_final, leader);
             mbar_wait(bar_final, 0);
         }
     } else if (warp == kLoadWarp && elect_one()) {
         // ================= weight loader (one elected lane) =================
+        for (int pair = blockIdx.x, it = 0; pair < npairs; pair += gridDim.x, ++it) {
+        const uint32_t ph = static_cast<uint32_t>(it) & 1u;
+        long long* const trace = it == 0 ? trace0 : nullptr;
         uint32_t free_phase = 0;
         int jk = 0;
         for (int j = 0; j < njobs; ++j) {
@@ -1221,7 +1240,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                         mbar_wait(bar_wfree[1], free_phase);
                     }
                 } else if (jk >= 3) {
-                    mbar_wait(bar_jwfree0 + 8 * (jk - 3), 0);
+                    mbar_wait(bar_jwfree0 + 8 * (jk - 3), ph);
                 }
                 // (slots 1 and 2 - used by the first two joint jobs, whose weights are therefore requested while
                 // conv1d_9 is still running - lie in window 1's region above everything conv1d_8.. keeps there;
@@ -1244,7 +1263,13 @@ __global__ void __launch_bounds__(kTcThreads, 1)
             mbar_expect_tx(bar_wfull[1], J.w_part[1]);
             bulk_g2s(wbuf + kWPart0, src + J.w_part[0], J.w_part[1], bar_wfull[1]);
         }
+        // the weight slots are reused by the next pair: the MMAs of the last three joint jobs must be done with them
+        for (int k = jk > 3 ? jk - 3 : 0; k < jk; ++k) mbar_wait(bar_jwfree0 + 8 * k, ph);
+        }   // pairs
     }
+    // (the control warps work on one elected lane; a CTA-wide barrier counts a warp as arrived as soon as any of
+    // its lanes executes it, so every warp reconverges first)
+    __syncwarp();
     tc_fence_before();
     __syncthreads();
     if (warp == kMmaWarp) tmem_dealloc(tmem_base, kTmemCols);
@@ -1259,6 +1284,7 @@ struct TcEngine {
     float* d_prm = nullptr;
     TcParams params{};
     int njobs = 0;
+    int sm_count = 148;        // grid of the persistent kernel = min(window pairs, SMs)
     std::vector<TcJob> jobs;   // uploaded to constant memory (identical for every model of this topology)
 };
 
@@ -1553,6 +1579,12 @@ TcEngine* tc_create(const Blob& blob) {
         return nullptr;
     }
     e->njobs = static_cast<int>(B.jobs.size());
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess ||
+        cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || e->sm_count <= 0) {
+        cudaGetLastError();
+        e->sm_count = 148;
+    }
     P.njobs = e->njobs;
     P.w = e->d_w;
     P.issue = e->d_issue;
@@ -1602,7 +1634,7 @@ static int launch_check(const char* what) {
 int tc_predict(TcEngine* e, const float* d_x, const double* d_xd, int64_t n, float* d_probs,
                cudaStream_t st) {
     if (int rc = sync_table(e->jobs)) return rc;
-    const int grid = static_cast<int>((n + 1) / 2);
+    const int grid = static_cast<int>(std::min<int64_t>((n + 1) / 2, e->sm_count));
     k_tc_forward<false, false><<<grid, kTcThreads, kTcSmemBytes, st>>>(e->params, d_x, d_xd, nullptr, nullptr,
                                                                0, 0, static_cast<int>(n), d_probs);
     return launch_check("tcgen05 kernel");
@@ -1612,7 +1644,7 @@ int tc_call_windows(TcEngine* e, const int16_t* d_samples, const int64_t* d_offs
                     int side, int steps, float* d_step_probs, cudaStream_t st) {
     const int n = n_reads * steps;
     if (int rc = sync_table(e->jobs)) return rc;
-    k_tc_forward<true, false><<<(n + 1) / 2, kTcThreads, kTcSmemBytes, st>>>(e->params, nullptr, nullptr, d_samples,
+    k_tc_forward<true, false><<<std::min((n + 1) / 2, e->sm_count), kTcThreads, kTcSmemBytes, st>>>(e->params, nullptr, nullptr, d_samples,
                                                                       d_offsets, n_reads, side, n,
                                                                       d_step_probs);
     return launch_check("tcgen05 kernel");

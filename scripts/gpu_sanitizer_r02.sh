@@ -13,6 +13,8 @@ for eng in ('tcgen05', 'fp32'):
     calls, probs = m.call_batch(sigs[:3], 'end', 1024, 0.5)
     calls2, probs2 = m.call_batch(sigs, 'start', 6144, 0.5)
     p = m.predict(np.random.RandomState(0).randn(5, 1024).astype(np.float32))
+    big = m.predict(np.random.RandomState(1).randn(420, 1024).astype(np.float32))   # 210 window pairs: some CTAs of the persistent kernel run two
+    calls3, probs3 = m.call_batch(sigs * 6, 'start', 6144, 0.5)                       # 252 window pairs through the fused form
     print(eng, calls.tolist(), float(p.sum()))
 PY
 for tool in memcheck racecheck synccheck; do
