@@ -134,7 +134,7 @@ struct alignas(128) TcJob {
     int w_goff;       // byte offset of this job's packed weights in global memory ([part 0 | part 1])
     int tcol;         // joint jobs: first accumulator column (slot * 64)
     int w_part[2];    // bytes of each part; a part is [hi blocks | lo blocks] of its K-block range
-    int first, last;  // first: zero the accumulators; last: run the epilogue
+    int first, last;  // first: zero the accumulators; last: bit 0 = run the epilogue, bit 1 (joint jobs) = an issuer waits on exactly this epilogue's barrier
     // epilogue
     int kind, bias_off, bn_off;  // float offsets into the smem parameter block
     int out_off, out_lp, out_lo_delta, out_cg_base, out_ncg, out_L;
@@ -914,9 +914,8 @@ __global__ void __launch_bounds__(kTcThreads, 1)
     const bool is_epi = warp >= kEpiWarp0 && warp < kEpiWarp0 + kEpiWarps;
     // PERSISTENT over the window pairs of the launch (grid = min(pairs, SMs)); every role loops over the pairs on
     // its own, there is no CTA-wide barrier between two pairs: the barriers are not re-initialised, a barrier that
-    // completes once per pair is waited for with parity `it & 1`, bar_epi[w] completes nine times per pair (its
-    // parity for job j is (j + it) & 1), the weight / MMA barriers of the single-window jobs eight times (their
-    // parities restart with every pair).
+    // completes once per pair is waited for with parity `it & 1`, the barriers of the single-window jobs (weights,
+    // MMA-done, bar_epi[w]) complete eight times per pair, so their parities restart with every pair.
     const int npairs = (n_windows + 1) / 2;
     // barrier set-up, shared by two otherwise idle threads (one thread needs ~10 cycles per mbarrier.init, and
     // there is one barrier per joint job / joint epilogue)
@@ -1078,7 +1077,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 fence_proxy_async();
                 if (tr) tr[7] = clock64();
                 tc_fence_before();
-                epi_arrive(bar_jepi + 8 * e);
+                if (J.last & 2) epi_arrive(bar_jepi + 8 * e);   // only where an issuer waits on exactly this epilogue (TcJob::last)
                 if (tr) tr[3] = clock64();
                 continue;
             }
@@ -1092,8 +1091,10 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 fence_proxy_async();
                 if (tr) tr[7] = clock64();
                 tc_fence_before();
-                epi_arrive(bar_epi[w]);
+                // (the last single-window job is followed by the joint jobs, which wait for BOTH windows on bar_x: bar_epi[w]
+                // then completes eight times per pair and every one of its phases has a waiter)
                 if (j + 1 < njobs && c_jobs[j + 1].joint) epi_arrive(bar_x);
+                else epi_arrive(bar_epi[w]);
                 if (tr) tr[3] = clock64();
             }
         }
@@ -1141,7 +1142,7 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                 const uint32_t tap16[3] = {J.tap16[0], J.tap16[1], J.tap16[2]};
                 const bool first = J.first != 0, last = J.last != 0;
                 const uint32_t parw = static_cast<uint32_t>(j) & 1u;           // parity of the weight barriers for job j
-                const uint32_t par = static_cast<uint32_t>(j + it) & 1u;      // parity of bar_epi[w] for job j of this pair
+                const uint32_t par = parw;                                     // ... and of bar_epi[w] (eight completions per pair, too)
                 if (J.joint) {
                     if (J.owner != me) continue;
                     // ---- both windows in one burst: [part 0: w0, w1] [part 1: w0, w1], one commit ----
@@ -1441,6 +1442,11 @@ struct JobBuilder {
                 last_user[slot] = static_cast<int>(j);
             }
         }
+        // the issuers wait for epilogue need - 1 only (epilogues complete in order): mark those epilogues
+        for (size_t j = j0; j < jobs.size(); ++j)
+            if (jobs[j].last)
+                for (size_t k = j0; k < jobs.size(); ++k)
+                    if (jobs[k].need - 1 == jobs[j].eseq) jobs[j].last |= 2;
     }
 };
 
