@@ -1194,13 +1194,14 @@ __global__ void __launch_bounds__(kTcThreads, 1)
                     const bool free_now = w == w_last;
                     const int nfree = J.both ? 2 : 1;
                     if (tracing) trace[(j * 2 + w) * 16 + 11] = clock64();
+                    // weight part 0 first (normally landed long ago): its poll then overlaps the wait for the input
+                    if (w == w_first) mbar_wait(bar_wfull[0], parw);
                     mbar_wait(bar_epi[w], par);   // input written and previous accumulators drained
                     if (tracing) trace[(j * 2 + w) * 16 + 12] = clock64();
                     tc_fence_after();
                     if (tracing) trace[(j * 2 + w) * 16 + 0] = clock64();
                     const uint32_t dwin = w * kTmemWindowCols;
                     // ---- weight part 0 (first K blocks); freed early so the loader can refill it ----
-                    if (w == w_first) mbar_wait(bar_wfull[0], parw);
                     if (tracing) trace[(j * 2 + w) * 16 + 8] = clock64();
                     issue_job_part<0>(J.ntaps, J.ncb, dwin, J.ntiles, (w ? act16_1 : act16_0), tap16, J.cb0, J.lp, J.lo16, wp16[0],
                                       blk16, J.n, J.idesc, first, leader);
