@@ -379,6 +379,48 @@ __device__ __forceinline__ uint32_t pack_bf16x2(float lo_elem, float hi_elem) {
     asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi_elem), "f"(lo_elem));
     return r;
 }
+// Packed fp32 pairs (Blackwell FFMA2: one instruction, two IEEE fp32 FMAs - bit-identical to two FFMAs).  The epilogues
+// and conv1d_1 are instruction-issue bound, and most of their arithmetic is independent per channel.
+#ifndef DBN_TC_F32X2
+#define DBN_TC_F32X2 1
+#endif
+__device__ __forceinline__ uint64_t pack2(float lo, float hi) {
+    uint64_t r;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+    return r;
+}
+__device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi) {
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+}
+__device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c) {
+    uint64_t r;
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(r) : "l"(a), "l"(b), "l"(c));
+    return r;
+}
+// a * b + c on 8 values, pairwise packed
+__device__ __forceinline__ void fma8(const float* a, const float* b, const float* c, float* out) {
+#if DBN_TC_F32X2
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        unpack2(fma2(pack2(a[2 * i], a[2 * i + 1]), pack2(b[2 * i], b[2 * i + 1]), pack2(c[2 * i], c[2 * i + 1])),
+                out[2 * i], out[2 * i + 1]);
+#else
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = fmaf(a[i], b[i], c[i]);
+#endif
+}
+// a * s + c with one scalar s
+__device__ __forceinline__ void fma8s(const float* a, float s, const float* c, float* out) {
+#if DBN_TC_F32X2
+    const uint64_t s2 = pack2(s, s);
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        unpack2(fma2(pack2(a[2 * i], a[2 * i + 1]), s2, pack2(c[2 * i], c[2 * i + 1])), out[2 * i], out[2 * i + 1]);
+#else
+#pragma unroll
+    for (int i = 0; i < 8; ++i) out[i] = fmaf(a[i], s, c[i]);
+#endif
+}
 // hi is rounded to nearest (one F2FP per pair on the XU pipe); lo is the TRUNCATED upper half of
 // the exact remainder x - hi (one PRMT per pair).  The remainder's sign is symmetric around zero,
 // so truncating it toward zero is unbiased with respect to x; |x - hi - lo| <= 2^-16 |x|.
@@ -387,8 +429,14 @@ __device__ __forceinline__ void split8(const float (&v)[8], uint4* hi, uint4* lo
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
         h[i] = pack_bf16x2(v[2 * i], v[2 * i + 1]);
+#if DBN_TC_F32X2
+        float r0, r1;   // both remainders with one FFMA2: v - hi = hi * (-1) + v (exact, as the two subtractions)
+        unpack2(fma2(pack2(__uint_as_float(h[i] << 16), __uint_as_float(h[i] & 0xFFFF0000u)), pack2(-1.f, -1.f),
+                     pack2(v[2 * i], v[2 * i + 1])), r0, r1);
+#else
         const float r0 = v[2 * i] - __uint_as_float(h[i] << 16);
         const float r1 = v[2 * i + 1] - __uint_as_float(h[i] & 0xFFFF0000u);
+#endif
         l[i] = __byte_perm(__float_as_uint(r0), __float_as_uint(r1), 0x7632);
     }
     *hi = make_uint4(h[0], h[1], h[2], h[3]);
@@ -483,14 +531,12 @@ __device__ __forceinline__ void conv1_stage(const Conv1Params& c, float x0, floa
     for (int k = 0; k < 8; ++k) {
         const int p = p0 + 64 * k;
         float v[8];
+        fma8s(c.w0, xs[k][0], c.b, v);
+        fma8s(c.w1, xs[k][1], v, v);
+        fma8s(c.w2, xs[k][2], v, v);
 #pragma unroll
-        for (int e = 0; e < 8; ++e) {
-            float a = c.b[e];
-            a = fmaf(c.w0[e], xs[k][0], a);
-            a = fmaf(c.w1[e], xs[k][1], a);
-            a = fmaf(c.w2[e], xs[k][2], a);
-            v[e] = fmaf(c.sc[e], fmaxf(a, 0.f), c.sh[e]);
-        }
+        for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+        fma8(c.sc, v, c.sh, v);
         uint4 hi, lo;
         split8(v, &hi, &lo);
         const uint32_t a0 = act + (cg * 514 + p + 1) * 16;
@@ -656,12 +702,10 @@ __device__ __forceinline__ void epilogue_tiles(const EpiArgs& A, uint32_t act, u
                 const float send = odd ? acc[e] : acc[8 + e];
                 v[e] = fmaxf(keep, __shfl_xor_sync(0xffffffffu, send, 1));
             }
+            fma8s(v, 1.0f, bias, v);   // v + bias (exact)
 #pragma unroll
-            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e] + bias[e], 0.f);
-            if (BN) {
-#pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[e], v[e], sh[e]);
-            }
+            for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+            if (BN) fma8(sc, v, sh, v);
             uint4 hi, lo;
             split8(v, &hi, &lo);
             if (valid) {   // both lanes of a pair write: channel group cg0 (even lane) / cg0 + 1 (odd lane)
@@ -681,12 +725,10 @@ __device__ __forceinline__ void epilogue_tiles(const EpiArgs& A, uint32_t act, u
 #pragma unroll
             for (int g = 0; g < NC / 8; ++g) {
                 float v[8];
+                fma8s(&acc[g * 8], es, &bias[g * 8], v);
 #pragma unroll
-                for (int e = 0; e < 8; ++e) v[e] = fmaxf(fmaf(acc[g * 8 + e], es, bias[g * 8 + e]), 0.f);
-                if (BN) {
-#pragma unroll
-                    for (int e = 0; e < 8; ++e) v[e] = fmaf(sc[g * 8 + e], v[e], sh[g * 8 + e]);
-                }
+                for (int e = 0; e < 8; ++e) v[e] = fmaxf(v[e], 0.f);
+                if (BN) fma8(&sc[g * 8], v, &sh[g * 8], v);
                 uint4 hi, lo;
                 split8(v, &hi, &lo);
                 if (stack && !valid) {   // separator rows of a stacked tensor are zero padding
