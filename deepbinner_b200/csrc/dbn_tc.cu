@@ -94,7 +94,7 @@ constexpr int kStackPitch = 18;
 constexpr int kYRows = 2 * kStackPitch;    // 36
 constexpr int kYArray = 24 * kYRows * 16;  // 13824
 constexpr int kYOff = kActBytes - 4 * kYArray;   // 43392
-static_assert(kYOff >= 33792, "Y buffer overlaps the inception scratch tensors");
+static_assert(kYOff >= 34176, "Y buffer overlaps the inception scratch tensors");
 static_assert(kYOff + 2 * kWbufBytes <= kActBytes, "joint weight slots must fit behind window 1's inception tensors");
 constexpr int kMaxJobs = 32;
 
@@ -1441,7 +1441,10 @@ struct JobBuilder {
         J.edge15 = fold_avg3 ? 1 : 0;
         J.out_L = pool ? L / 2 : L;
         J.out_off = out_off;
-        J.out_lp = J.out_L + 2;
+        // pooled outputs get two spare rows per channel group: the two lanes of a pool pair store to channel groups
+        // g and g + 1, and with a group pitch of 64 (mod 128) bytes their 16-byte rows fall on disjoint banks
+        // ((L/2 + 2) * 16 is 32 mod 128 for L/2 = 256, 128, 64: a 2-way bank conflict on every pooled store)
+        J.out_lp = J.out_L + (pool && kind != EPI_PARITY ? 4 : 2);
         J.out_ncg = cout / 8;
         J.out_lo_delta = J.out_ncg * J.out_lp * 16;
         J.out_cg_base = out_cg_base;
@@ -1498,14 +1501,14 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
     // T1 (BN1 output) is written by conv1_stage: [6][514][8], lo at +49344
     B->add(2, 512, 0, 514, 49344, EPI_N48, 0, 0, 0);
     B->add(3, 512, 0, 514, 49344, EPI_N48, 0, 0, 0);
-    B->add(4, 512, 0, 514, 49344, EPI_N48_POOL_BN, 2, 0, 0);      // -> [6][258][8], lo +24768
-    B->add(5, 256, 0, 258, 24768, EPI_N16, 0, 0, 0);              // -> [2][258][8], lo +8256
-    B->add(6, 256, 0, 258, 8256, EPI_N48, 0, 0, 0);               // -> [6][258][8]
-    B->add(7, 256, 0, 258, 24768, EPI_N48_POOL_BN, 3, 0, 0);      // -> [6][130][8], lo +12480
-    B->add(8, 128, 0, 130, 12480, EPI_N48, 0, 0, 0);
-    B->add(9, 128, 0, 130, 12480, EPI_N48_POOL_BN, 4, 0, 0);      // X [6][66][8], lo +6336
+    B->add(4, 512, 0, 514, 49344, EPI_N48_POOL_BN, 2, 0, 0);      // -> [6][260][8], lo +24960 (pooled: pitch L/2 + 4)
+    B->add(5, 256, 0, 260, 24960, EPI_N16, 0, 0, 0);              // -> [2][258][8], lo +8256
+    B->add(6, 256, 0, 258, 8256, EPI_N48, 0, 0, 0);               // -> [6][258][8], lo +24768
+    B->add(7, 256, 0, 258, 24768, EPI_N48_POOL_BN, 3, 0, 0);      // -> [6][132][8], lo +12672
+    B->add(8, 128, 0, 132, 12672, EPI_N48, 0, 0, 0);              // -> [6][130][8], lo +12480
+    B->add(9, 128, 0, 130, 12480, EPI_N48_POOL_BN, 4, 0, 0);      // X [6][68][8], lo +6528
     // ---- joint phase (both windows per job) ----
-    // Inception block, JOINT_PAIR: X @0, T15 @12672, T1214 @25344 (conv1d_12 | conv1d_14 outputs as one
+    // Inception block, JOINT_PAIR: X @0 (pitch 68), T15 @13056, T1214 @25728 (conv1d_12 | conv1d_14 outputs as one
     // 32-channel tensor: both are 1x1 convs of X, so ONE job with N = 32 computes them); Y (parity
     // split, both windows) in window 0's region @43392.  The average pool in front of conv1d_10 is
     // folded into its weights (k=3, W/3).  Concat order [conv10, conv11, conv13, conv16]
@@ -1522,13 +1525,13 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
         J.ntiles = 1;
         producer.push_back(prod);
     };
-    joint(B->add(12, 64, 0, 66, 6336, EPI_N16, 0, 25344, 0, 14), JOINT_PAIR, -1);              // j0: -> [4][66][8], lo +4224
-    joint(B->add(10, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 0, 0, true), JOINT_PAIR, -1);          // j0+1: avg pool folded
+    joint(B->add(12, 64, 0, 68, 6528, EPI_N16, 0, 25728, 0, 14), JOINT_PAIR, -1);              // j0: -> [4][66][8], lo +4224
+    joint(B->add(10, 64, 0, 68, 6528, EPI_PARITY, 5, 0, 0, 0, true), JOINT_PAIR, -1);          // j0+1: avg pool folded
     B->jobs.back().zero_y = 1;
-    joint(B->add(15, 64, 25344 + 2 * 66 * 16, 66, 4224, EPI_N48, 0, 12672, 0), JOINT_PAIR, j0);   // j0+2: groups 2-3 (conv1d_14)
-    joint(B->add(11, 64, 0, 66, 6336, EPI_PARITY, 5, 0, 6), JOINT_PAIR, -1);                   // j0+3
-    joint(B->add(13, 64, 25344, 66, 4224, EPI_PARITY, 5, 0, 12), JOINT_PAIR, j0);              // j0+4: groups 0-1 (conv1d_12)
-    joint(B->add(16, 64, 12672, 66, 6336, EPI_PARITY, 5, 0, 18), JOINT_PAIR, j0 + 2);          // j0+5
+    joint(B->add(15, 64, 25728 + 2 * 66 * 16, 66, 4224, EPI_N48, 0, 13056, 0), JOINT_PAIR, j0);   // j0+2: groups 2-3 (conv1d_14)
+    joint(B->add(11, 64, 0, 68, 6528, EPI_PARITY, 5, 0, 6), JOINT_PAIR, -1);                   // j0+3
+    joint(B->add(13, 64, 25728, 66, 4224, EPI_PARITY, 5, 0, 12), JOINT_PAIR, j0);              // j0+4: groups 0-1 (conv1d_12)
+    joint(B->add(16, 64, 13056, 66, 6336, EPI_PARITY, 5, 0, 18), JOINT_PAIR, j0 + 2);          // j0+5
     // conv1d_17 .. conv1d_20, JOINT_STACK: both windows stacked in one tile (row = 18 w + position).
     // conv1d_17: stride 2 on the parity-split Y (tap0 = Ye[i], tap1 = Yo[i], tap2 = Ye[i+1]),
     // K = 3 x 192 split in 4 jobs of 3 channel blocks so each weight chunk fits the buffer; slice s reads
@@ -1551,8 +1554,8 @@ static bool build_jobs(const Blob& blob, JobBuilder* B, TcParams* P) {
         producer.push_back(y_writer[s]);
     }
     joint(B->add(18, 34, 0, 36, 3456, EPI_N48, 0, 0, 0), JOINT_STACK, j0 + 9);
-    joint(B->add(19, 34, 0, 36, 3456, EPI_N48_POOL_BN, 7, 0, 0), JOINT_STACK, j0 + 10);   // -> [6][19][8], lo +1824
-    joint(B->add(20, 17, 0, 19, 1824, EPI_HEAD, 0, 0, 0), JOINT_STACK, j0 + 11);
+    joint(B->add(19, 34, 0, 36, 3456, EPI_N48_POOL_BN, 7, 0, 0), JOINT_STACK, j0 + 10);   // -> [6][21][8], lo +2016
+    joint(B->add(20, 17, 0, 21, 2016, EPI_HEAD, 0, 0, 0), JOINT_STACK, j0 + 11);
     B->jobs.back().idesc = 128;   // the head epilogue reads all 17 rows from TMEM lane quadrant 0
     B->finish_joint(j0, producer);
     B->finalize_jobs();

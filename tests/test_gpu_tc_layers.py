@@ -39,7 +39,7 @@ def decode_parity(act0, w, cg0, ncg):
     return y, ye[:, r0 + 16:r0 + 18, :], None
 
 
-def decode_stacked(act0, w, lp, length, pitch, lo_delta):
+def decode_stacked(act0, w, lp, length, pitch, lo_delta, halo_row=None):
     """Stacked tail tensors (both windows in window 0's region): [6][lp][8] hi/lo, window w at rows
     1 + pitch*w + i; returns (tensor, halo rows, separator rows)."""
     def arr(o):
@@ -47,7 +47,7 @@ def decode_stacked(act0, w, lp, length, pitch, lo_delta):
     full = arr(0) + arr(lo_delta)
     r0 = 1 + pitch * w
     t = full[:, r0:r0 + length, :].transpose(1, 0, 2).reshape(length, 48)
-    halos = np.stack([full[:, 0, :], full[:, lp - 1, :]])
+    halos = np.stack([full[:, 0, :], full[:, lp - 1 if halo_row is None else halo_row, :]])
     sep = full[:, 1 + length:1 + pitch, :] if (pitch > length and length == 16) else None
     return t, halos, sep
 
@@ -56,21 +56,21 @@ def decode_stacked(act0, w, lp, length, pitch, lo_delta):
 JOBS = [
     (0, 'conv2', lambda d, w: decode(d[w], 0, 6, 514, 512, 49344)),
     (1, 'conv3', lambda d, w: decode(d[w], 0, 6, 514, 512, 49344)),
-    (2, 'bn2', lambda d, w: decode(d[w], 0, 6, 258, 256, 24768)),
+    (2, 'bn2', lambda d, w: decode(d[w], 0, 6, 260, 256, 24960)),      # pooled outputs: pitch L/2 + 4
     (3, 'conv5', lambda d, w: decode(d[w], 0, 2, 258, 256, 8256)),
     (4, 'conv6', lambda d, w: decode(d[w], 0, 6, 258, 256, 24768)),
-    (5, 'bn3', lambda d, w: decode(d[w], 0, 6, 130, 128, 12480)),
+    (5, 'bn3', lambda d, w: decode(d[w], 0, 6, 132, 128, 12672)),
     (6, 'conv8', lambda d, w: decode(d[w], 0, 6, 130, 128, 12480)),
-    (7, 'bn4', lambda d, w: decode(d[w], 0, 6, 66, 64, 6336)),
-    (8, 'conv12+14', lambda d, w: decode(d[w], 25344, 4, 66, 64, 4224)),
+    (7, 'bn4', lambda d, w: decode(d[w], 0, 6, 68, 64, 6528)),
+    (8, 'conv12+14', lambda d, w: decode(d[w], 25728, 4, 66, 64, 4224)),
     (9, 'bn5:0', lambda d, w: decode_parity(d[0], w, 0, 6)),      # average pool folded into conv1d_10
-    (10, 'conv15', lambda d, w: decode(d[w], 12672, 6, 66, 64, 6336)),
+    (10, 'conv15', lambda d, w: decode(d[w], 13056, 6, 66, 64, 6336)),
     (11, 'bn5:48', lambda d, w: decode_parity(d[0], w, 6, 6)),
     (12, 'bn5:96', lambda d, w: decode_parity(d[0], w, 12, 6)),
     (13, 'bn5:144', lambda d, w: decode_parity(d[0], w, 18, 6)),
     (17, 'bn6', lambda d, w: decode_stacked(d[0], w, 36, 16, 18, 3456)),
     (18, 'conv18', lambda d, w: decode_stacked(d[0], w, 36, 16, 18, 3456)),
-    (19, 'bn7', lambda d, w: decode_stacked(d[0], w, 19, 8, 9, 1824)),
+    (19, 'bn7', lambda d, w: decode_stacked(d[0], w, 21, 8, 9, 2016, halo_row=18)),   # pooled output: two spare rows
 ]
 
 
