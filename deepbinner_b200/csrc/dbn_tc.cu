@@ -1,7 +1,8 @@
 // tcgen05 / TMEM tensor-core engine for the Deepbinner network (reference
 // network_architecture.py:18-95; executed by model.predict at classify.py:361).
 //
-// One CTA processes TWO windows.  All activations stay in shared memory as split-bf16 pairs
+// One CTA processes TWO windows at a time and is persistent over the window pairs of a launch (grid =
+// min(pairs, SMs)).  All activations stay in shared memory as split-bf16 pairs
 // (hi = bf16_rn(x), lo = upper half of the exact remainder x - hi); every Conv1D from conv1d_2 to
 // conv1d_20 is a sequence of tcgen05.mma (kind::f16, M=128 positions x N=Cout x K=16) instructions
 // accumulating in fp32 in tensor memory.  A k=3 'same' convolution is three accumulating MMAs per
@@ -11,12 +12,13 @@
 // im2col is ever materialised.  Precision: three MMA terms per K block (A_hi*W_hi, A_hi*W_lo with
 // A_hi reused from the tensor core's collector buffer, A_lo*W_hi) give ~16 mantissa bits on both
 // operands, which SURVEY Appendix C shows is needed for the 1e-3 probability bar (single bf16
-// fails, fp16 overflows).
+// fails, fp16 overflows; dropping either cross term of any single layer fails too,
+// profiles/r02_precision_probe_*.txt).
 //
 // A whole layer's output for one window (up to 4 tiles x 48 fp32 columns) lives in TMEM, so the
 // epilogue (bias, ReLU, [MaxPool2], [BatchNorm affine], hi/lo split) can overwrite the layer's
 // input in place once its MMAs have completed.  The network is a table of 21 MMA jobs in constant
-// memory, in two phases:
+// memory (the issuers read a compact copy, IssueRec, from global memory), in two phases:
 //   * conv1d_2 .. conv1d_9 (L = 512 .. 128): one pass per window, M=128 tiles; the two windows of
 //     the CTA alternate so that the tensor pipe works on one while the epilogue warps drain the other;
 //   * "joint" jobs from the inception block on (L <= 64): ONE MMA burst and ONE epilogue pass serve
@@ -25,19 +27,23 @@
 //     quadrant, so all 32 lanes of every epilogue warp carry rows.  conv1d_12 + conv1d_14 share one
 //     job (N = 32); the AveragePooling1D in front of conv1d_10 is folded into its weights (k=3, W/3,
 //     end rows rescaled by 1.5 in the epilogue).  conv1d_17 .. 20: both windows stacked in one tensor
-//     (row = 18 w + position), conv1d_17 as four K-slices.  Joint jobs rotate over three accumulator
+//     (row = 18 w + position), conv1d_17 as four K-slices.  Joint jobs rotate over kJointSlots accumulator
 //     slots and are ordered so that independent branches sit between dependent ones; each carries
 //     the number of joint epilogues that must be complete before it may issue (`need`), which lets
-//     the tensor pipe run up to two jobs ahead of the epilogue warps.
+//     the tensor pipe run ahead of the epilogue warps.
 //
-// Warp roles (448 threads): warps 0-11 = epilogue (TMEM lane quadrant = warp % 4, 16 accumulator
+// Warp roles (480 threads): warps 0-11 = epilogue (TMEM lane quadrant = warp % 4, 16 accumulator
 // columns per warp) and the CUDA-core stages (z-score + conv1d_1, softmax head); warp 12 = weight
-// loader (cp.async.bulk + mbarrier; each job's weights come in two K-block parts so the next job's
-// first part streams in while the second is still in use); warp 13 = TMEM allocator + MMA issuer (one
-// elected lane).  The issuer is a single thread (one dependent instruction every ~4 cycles, slower
-// when the epilogue warps of its scheduler are busy), so everything it does between two MMAs
-// matters: job descriptors are fetched one job ahead, tcgen05 descriptors are built from
-// pre-shifted fields, and all diagnostics live in a separate kernel instantiation.
+// loader (cp.async.bulk + mbarrier; each single-window job's weights come in two K-block parts so the next
+// job's first part streams in while the second is still in use; joint jobs get whole-job slots); warps 13
+// and 14 = the two MMA issuers (one elected lane each; warp 13 also allocates / frees tensor memory).  An
+// issuer is a single thread (one dependent instruction every ~4 cycles, slower when the epilogue warps of
+// its scheduler are busy) and needs ~1 000 cycles between two jobs (queue drain before the commits,
+// barrier polls, descriptor set-up), so everything it does between two MMAs matters: issue records are
+// fetched one job ahead, tcgen05 descriptors are built from pre-shifted fields, all diagnostics live in a
+// separate kernel instantiation - and there are two of them, so that the turn-around of one overlaps the
+// burst of the other (conv1d_5..9: one window each; joint jobs: alternating).  Every role loops over the
+// CTA's window pairs on its own; there is no CTA-wide barrier between two pairs (see the kernel).
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
 
@@ -114,9 +120,9 @@ enum EpiKind {
 //               tools/tc_microbench.cu), so each epilogue warp drains 16 rows of either window;
 //   JOINT_STACK (conv1d_17 onwards): both windows stacked in one tensor (row = 18 w + position) in
 //               window 0's region, one M=64 MMA set (conv1d_20: M=128, head epilogue).
-// Joint jobs rotate over three accumulator slots and carry `need` = number of joint epilogues that
+// Joint jobs rotate over kJointSlots accumulator slots and carry `need` = number of joint epilogues that
 // must have completed before their MMAs may be issued (input produced / slot drained), so the
-// tensor pipe runs up to two jobs ahead of the epilogue warps where the graph allows it.
+// tensor pipe runs ahead of the epilogue warps where the graph allows it.
 enum JointKind { JOINT_NONE = 0, JOINT_PAIR = 1, JOINT_STACK = 2 };
 
 struct alignas(128) TcJob {
@@ -453,7 +459,7 @@ __device__ __forceinline__ void unpack8(uint4 hi, uint4 lo, float (&v)[8]) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// CUDA-core stages (epilogue warps, 256 threads)
+// CUDA-core stages (epilogue warps, 384 threads)
 // ---------------------------------------------------------------------------------------------
 
 // Input of one window: either normalised values (predict seam) or an int16 scan region that is
