@@ -268,6 +268,28 @@ def test_full_batch_properties(models):
         assert np.allclose(big.sum(axis=1), 1.0, atol=1e-5)
 
 
+def test_odd_window_counts_across_persistent_pairs(models):
+    """The tensor-core kernel works on window PAIRS and is persistent (grid = min(pairs, SMs)): odd counts leave a
+    half-filled last pair, counts above 2 x SMs make some CTAs run several pairs.  Every row must be bit-identical
+    to the same window predicted in another batch composition, in both input forms."""
+    model = models['EXP-NBD103_read_ends']
+    x = np.random.RandomState(9).randn(901, 1024).astype(np.float32) * 1.5
+    reads = synthetic_signals(75, seed=12, length=np.random.RandomState(13).randint(200, 7000, 75))
+    for eng in engines(model):
+        model.set_engine(eng)
+        ref = model.predict(x)
+        for n in (1, 2, 3, 295, 297, 299, 593, 901):
+            assert np.array_equal(model.predict(x[:n]), ref[:n]), n
+            assert np.array_equal(model.predict(x[901 - n:]), ref[901 - n:]), n
+        calls, probs = model.call_batch(reads, 'end', 6144, 0.5)          # 75 reads x 12 steps = 900 windows
+        for n in (1, 25, 49, 74):                                          # 12 n windows: odd pair counts, 1 .. 3 pairs per CTA
+            c, p = model.call_batch(reads[:n], 'end', 6144, 0.5)
+            assert np.array_equal(p, probs[:n]) and np.array_equal(c, calls[:n]), n
+        c, p = model.call_batch(reads[:37], 'end', 512, 0.5)              # one step: 37 windows, last pair half-filled
+        c2, p2 = model.call_batch(reads[:36], 'end', 512, 0.5)
+        assert np.array_equal(p[:36], p2) and np.array_equal(c[:36], c2)
+
+
 def test_synthetic_parity_sample(models, oracle_weights):
     """The benchmark's synthetic gaussian reads: calls identical and probabilities within 1e-3 of
     the oracle on a sample the oracle finishes in seconds."""
