@@ -287,10 +287,13 @@ def pipeline_rate(cls, batches, start, end, args_ns, n_classes, reps):
     for _ in range(2):                                                            # warm-up passes (buffers of all job slots)
         cls.classify_read_batches(((i, s, None) for i, s in batches), start, 1024 if start else None, end,
                                   1024 if end else None, n_classes, args_ns)
-    t0 = time.perf_counter()
-    cls.classify_read_batches(source(), start, 1024 if start else None, end, 1024 if end else None,
-                              n_classes, args_ns)
-    return reps * sum(len(i) for i, _ in batches) / (time.perf_counter() - t0)
+    rates = []
+    for _ in range(3):                                                            # median of three timed runs (each ~0.1 s)
+        t0 = time.perf_counter()
+        cls.classify_read_batches(source(), start, 1024 if start else None, end, 1024 if end else None,
+                                  n_classes, args_ns)
+        rates.append(reps * sum(len(i) for i, _ in batches) / (time.perf_counter() - t0))
+    return sorted(rates)[1]
 
 
 def main():
@@ -513,7 +516,7 @@ def main():
                                        require_start=False, require_both=False, verbose=False)
             ids256 = ['r%d' % i for i in range(256)]
             b256 = [(ids256, ragged_reads(256, 7 + k)) for k in range(4)]
-            r = pipeline_rate(cls, b256, model, end_model, ns, model.n_classes, reps=10)
+            r = pipeline_rate(cls, b256, model, end_model, ns, model.n_classes, reps=30)
             configs['native_start_end_batch256'] = {
                 'reads_per_s': r, 'windows_per_s': 24 * r, 'windows_per_read': 24,
                 'what': 'BASELINE configs[1]: classify.classify_read_batches (both sides submitted per batch, '
@@ -521,7 +524,7 @@ def main():
             ids512 = ['r%d' % i for i in range(512)]
             b512 = [(ids512, ragged_reads(512, 11 + k)) for k in range(4)]
             ns3 = types.SimpleNamespace(**dict(vars(ns), batch_size=512))
-            r = pipeline_rate(cls, b512, rapid, None, ns3, rapid.n_classes, reps=10)
+            r = pipeline_rate(cls, b512, rapid, None, ns3, rapid.n_classes, reps=30)
             configs['rapid_start_batch512'] = {
                 'reads_per_s': r, 'windows_per_s': 12 * r, 'windows_per_read': 12,
                 'what': 'BASELINE configs[2]: SQK-RBK004_read_starts, host lists of 512 ragged int16 reads, scan 6144'}

@@ -252,7 +252,7 @@ struct db_model {
     cudaStream_t copy_stream = nullptr;
     static constexpr int kCopyEvents = 16;
     cudaEvent_t ev_copy[kCopyEvents] = {};
-    int call_chunk_windows = 2048;      // network windows per pipelined chunk of a job (DEEPBINNER_B200_CALL_CHUNK)
+    int call_chunk_windows = 0;         // network windows per pipelined chunk of a job; 0 = chosen per job (DEEPBINNER_B200_CALL_CHUNK fixes it)
     GatherPool* pool = nullptr;         // host threads of the gather (DEEPBINNER_B200_GATHER_THREADS, default 4)
 };
 
@@ -379,7 +379,18 @@ static int submit_job(db_model* m, GetRead get_read, int n_reads, int side, int 
     }
     DBN_CUDA(cudaSetDevice(m->device));
     const int64_t region_max = static_cast<int64_t>(scan_size) + m->input_size / 2;
-    const int chunk_max = std::max(1, m->call_chunk_windows / steps);   // reads per chunk, at most
+    // Windows per chunk.  A launch of the persistent network kernel is the more efficient the more window pairs each
+    // of its CTAs gets, a pipeline needs several chunks in flight: with other jobs of this handle already queued the
+    // job is cut in two (3072 .. 16384 windows per chunk), a lone job - a synchronous caller - in chunks of 2048 so
+    // that its own copies overlap its own kernels (measured: profiles/r02_chunk_sweep.txt).
+    int chunk_windows = m->call_chunk_windows;
+    if (chunk_windows <= 0) {
+        int queued = 0;
+        for (int i = 0; i < db_model::kJobSlots; ++i) queued += m->jobs[i].busy ? 1 : 0;
+        const int64_t job_windows = static_cast<int64_t>(n_reads) * steps;
+        chunk_windows = queued > 0 ? static_cast<int>(std::min<int64_t>(std::max<int64_t>(job_windows / 2, 3072), 16384)) : 2048;
+    }
+    const int chunk_max = std::max(1, chunk_windows / steps);   // reads per chunk, at most
     const int nchunks = (n_reads + chunk_max - 1) / chunk_max;
     const int chunk = (n_reads + nchunks - 1) / std::max(nchunks, 1);   // balanced chunks
     const size_t nc = m->n_classes;

@@ -117,7 +117,10 @@ DBN_API int db_call_batch(db_model *model, const int16_t *samples, const int64_t
  * next batch, submit the other model's side of this batch, format results): submit() gathers the scan
  * regions chunk by chunk into pinned staging and enqueues copy (on a dedicated copy stream) -> kernels ->
  * copy-back for every chunk (on three rotating compute streams that wait for the chunk's copy event); it
- * returns as soon as everything is enqueued and no longer references the caller's buffers.  wait() blocks until the job is complete and fills probs / calls as db_call_batch
+ * returns as soon as everything is enqueued and no longer references the caller's buffers.  Chunk size: 2048 network
+ * windows for a lone job, half the job (3072 .. 16384 windows) when other jobs of the handle are already queued - larger
+ * launches of the persistent kernel are more efficient, a lone job needs its own copies under its own kernels
+ * (profiles/r02_chunk_sweep.txt; DEEPBINNER_B200_CALL_CHUNK fixes the size).  wait() blocks until the job is complete and fills probs / calls as db_call_batch
  * does.  *job receives a small index; up to 4 jobs per handle may be in flight; every submitted job must
  * be waited for exactly once.  db_call_batch == submit_packed + wait.
  *   db_call_batch_submit:        read i = signals[i][0 .. lengths[i])   (ragged host arrays)
