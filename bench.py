@@ -49,7 +49,7 @@ FLOP_PER_WINDOW = 33629952          # 2 x 16,814,976 MACs
 BATCH = 256                          # launch batch of the metric
 SHARD = 65536                        # reads resident per GPU and processed per step
 MODEL = 'EXP-NBD103_read_starts'
-N_STREAMS = 4
+N_STREAMS = int(os.environ.get('DBN_BENCH_STREAMS', '4'))   # launches of the headline loop rotate over this many streams
 
 
 def model_path():
