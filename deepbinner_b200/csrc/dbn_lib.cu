@@ -3,6 +3,9 @@
 // classify.py:361 model.predict / network_architecture.py:18-95).  No CPU fallback.
 #include <cuda_runtime.h>
 
+#include <atomic>
+#include <chrono>
+
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
@@ -132,6 +135,7 @@ class GatherPool {
         {
             std::lock_guard<std::mutex> lock(m_);
             stop_ = true;
+            stop_flag_.store(true, std::memory_order_release);
         }
         cv_.notify_all();
         for (std::thread& t : threads_) t.join();
@@ -157,6 +161,15 @@ class GatherPool {
         int seen = 0;
         for (;;) {
             const std::function<void(int)>* fn;
+            // A caller that comes back every 100 - 200 us (predict with 256 windows per call, the chunks of a job) should
+            // not pay a futex wake-up (20 - 100 us) each time: poll for a short while before going to sleep.
+            for (const auto t0 = std::chrono::steady_clock::now();
+                 generation_.load(std::memory_order_acquire) == seen && !stop_flag_.load(std::memory_order_acquire) &&
+                 std::chrono::steady_clock::now() - t0 < std::chrono::microseconds(150);) {
+#if defined(__x86_64__)
+                __builtin_ia32_pause();
+#endif
+            }
             {
                 std::unique_lock<std::mutex> lock(m_);
                 cv_.wait(lock, [&] { return stop_ || generation_ != seen; });
@@ -175,7 +188,9 @@ class GatherPool {
     std::mutex m_;
     std::condition_variable cv_, done_;
     const std::function<void(int)>* fn_ = nullptr;
-    int pending_ = 0, generation_ = 0;
+    int pending_ = 0;
+    std::atomic<int> generation_{0};
+    std::atomic<bool> stop_flag_{false};
     bool stop_ = false;
 };
 
@@ -201,6 +216,8 @@ struct db_model {
     cudaEvent_t ev_slot[2] = {nullptr, nullptr};
     float* h_out[2] = {nullptr, nullptr};   // pinned result staging of the pipelined host predict
     size_t h_out_bytes[2] = {0, 0};
+    float* h_in[2] = {nullptr, nullptr};    // pinned fp32 input staging of the host predict for PAGEABLE caller arrays
+    size_t h_in_bytes[2] = {0, 0};
     float last_ms = 0.f;
     int64_t launches = 0;
     // device scratch (grown on demand)
@@ -542,6 +559,7 @@ void db_destroy(db_model* m) {
     for (int i = 0; i < 2; ++i) {
         if (m->ev_slot[i]) cudaEventDestroy(m->ev_slot[i]);
         if (m->h_out[i]) cudaFreeHost(m->h_out[i]);
+        if (m->h_in[i]) cudaFreeHost(m->h_in[i]);
     }
     if (m->ev_start) cudaEventDestroy(m->ev_start);
     if (m->ev_stop) cudaEventDestroy(m->ev_stop);
@@ -653,6 +671,10 @@ int db_get_engine(const db_model* m) { return m ? m->engine : DBN_EINVAL; }
 // chunk i+1 overlaps the kernel of chunk i.  Results go D2H into pinned staging (a copy into the
 // caller's pageable array would block the host and serialise the pipeline) and are copied out when
 // the slot is reused / at the end.
+// A PAGEABLE caller array (what numpy hands over, and what Keras' model.predict got at classify.py:361) would make
+// cudaMemcpyAsync stage it through the driver on the calling thread at ~10 GB/s; instead the gather pool's threads
+// copy the chunk into pinned staging - float64 windows are cast to float32 there, exactly the cast the kernel does
+// otherwise (and Keras does), which halves the bytes on the wire - and the copy engine takes it from there.
 static int predict_host(db_model* m, const void* x, bool is_f64, int64_t n, float* probs) {
     if (!m) return fail(DBN_EINVAL, "predict: model is NULL");
     if (n < 0) return fail(DBN_EINVAL, "predict: n < 0");
@@ -667,6 +689,14 @@ static int predict_host(db_model* m, const void* x, bool is_f64, int64_t n, floa
     const int64_t cap = std::min(kChunk, n);   // buffers are sized once for the largest chunk
     const size_t row_in = static_cast<size_t>(m->input_size) * esz;
     const size_t row_out = static_cast<size_t>(m->n_classes) * sizeof(float);
+    bool pageable = true;
+    {
+        cudaPointerAttributes attr{};
+        if (cudaPointerGetAttributes(&attr, x) == cudaSuccess && attr.type != cudaMemoryTypeUnregistered) pageable = false;
+        cudaGetLastError();
+        if (getenv("DEEPBINNER_B200_NO_STAGE")) pageable = false;   // measurement knob: let the driver stage pageable arrays
+    }
+    const size_t row_stage = static_cast<size_t>(m->input_size) * sizeof(float);
     DBN_CUDA(cudaEventRecord(m->ev_start, m->streams[0]));
     DBN_CUDA(cudaStreamWaitEvent(m->streams[1], m->ev_start, 0));
     int64_t done = 0;
@@ -692,9 +722,35 @@ static int predict_host(db_model* m, const void* x, bool is_f64, int64_t n, floa
         if (rc) return rc;
         rc = grow_host(&m->h_out[slot], &m->h_out_bytes[slot], cap * row_out);
         if (rc) return rc;
-        DBN_CUDA(cudaMemcpyAsync(m->d_in[slot], static_cast<const char*>(x) + done * row_in,
-                                 cnt * row_in, cudaMemcpyHostToDevice, st));
-        rc = launch_predict(m, m->d_in[slot], is_f64, cnt, m->d_out[slot], st);
+        if (pageable) {
+            // (drain(slot) above waited for the previous chunk of this slot, hence for its copy out of h_in[slot])
+            rc = grow_host(&m->h_in[slot], &m->h_in_bytes[slot], cap * row_stage);
+            if (rc) return rc;
+            float* const stage = m->h_in[slot];
+            const int parts = m->pool ? m->pool->parts() : 1;
+            const int64_t elems = cnt * m->input_size;
+            auto stage_part = [&](int part) {
+                const int64_t e0 = elems * part / parts, e1 = elems * (part + 1) / parts;
+                if (is_f64) {
+                    const double* src = static_cast<const double*>(x) + done * m->input_size;
+                    for (int64_t e = e0; e < e1; ++e) stage[e] = static_cast<float>(src[e]);
+                } else {
+                    std::memcpy(stage + e0, static_cast<const float*>(x) + done * m->input_size + e0,
+                                static_cast<size_t>(e1 - e0) * sizeof(float));
+                }
+            };
+            if (m->pool && elems >= (1 << 17)) {
+                m->pool->parallel(stage_part);
+            } else {
+                for (int part = 0; part < parts; ++part) stage_part(part);
+            }
+            DBN_CUDA(cudaMemcpyAsync(m->d_in[slot], stage, cnt * row_stage, cudaMemcpyHostToDevice, st));
+            rc = launch_predict(m, m->d_in[slot], false, cnt, m->d_out[slot], st);
+        } else {
+            DBN_CUDA(cudaMemcpyAsync(m->d_in[slot], static_cast<const char*>(x) + done * row_in,
+                                     cnt * row_in, cudaMemcpyHostToDevice, st));
+            rc = launch_predict(m, m->d_in[slot], is_f64, cnt, m->d_out[slot], st);
+        }
         if (rc) return rc;
         DBN_CUDA(cudaMemcpyAsync(m->h_out[slot], m->d_out[slot], cnt * row_out, cudaMemcpyDeviceToHost, st));
         DBN_CUDA(cudaEventRecord(m->ev_slot[slot], st));

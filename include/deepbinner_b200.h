@@ -79,9 +79,11 @@ DBN_API int db_get_engine(const db_model *model);
 /*
  * Seam b1 - model.predict(x, batch_size) at classify.py:361.
  * x: host [n, input_size] already-normalised windows (float32, C-contiguous; the _f64 variant
- * takes the float64 array the reference builds at classify.py:340 and casts to float32 on the
- * device, as Keras does).  probs: host [n, n_classes] float32 softmax rows, written in full.
- * n may be any size >= 0; the library tiles it over the device.
+ * takes the float64 array the reference builds at classify.py:340 and casts to float32, as Keras
+ * does).  probs: host [n, n_classes] float32 softmax rows, written in full.
+ * n may be any size >= 0; the library tiles it over the device.  A pageable x (a plain numpy array) is copied
+ * into pinned staging by the library's host threads (float64 cast to float32 there) and transferred
+ * asynchronously from it; a page-locked x goes to the copy engine directly (float64 then cast on the device).
  */
 DBN_API int db_predict_windows(db_model *model, const float *x, int64_t n, float *probs);
 DBN_API int db_predict_windows_f64(db_model *model, const double *x, int64_t n, float *probs);
